@@ -1,0 +1,157 @@
+/*
+ * cryogpu.h -- C ABI of libcryogpu.so, the B200 (sm_100a) block codec for pg_cryogen.
+ *
+ * libcryogpu.so replaces the arithmetic behind the reference's block codec
+ * (reference compression.c:61-159, declared in compression.h:13-24), i.e. the
+ * calls the reference makes into liblz4 / libzstd:
+ *
+ *   LZ4_compressBound    compression.c:67      -> cryogpu_compress_bound
+ *   LZ4_compress_fast    compression.c:70-72   -> cryogpu_compress_{device,host}  (method 0)
+ *   LZ4_decompress_safe  compression.c:84      -> cryogpu_decompress_{device,host} (method 0)
+ *   ZSTD_compressBound   compression.c:99      -> cryogpu_compress_bound
+ *   ZSTD_compress        compression.c:102-104 -> cryogpu_compress_{device,host}  (method 1)
+ *   ZSTD_decompress      compression.c:116     -> cryogpu_decompress_{device,host} (method 1)
+ *
+ * The stream formats are the reference's on-disk formats, unchanged: method 0 is
+ * one raw LZ4 block, method 1 is one standard zstd frame (storage.h:64,
+ * SURVEY.md A.3).  The drop-in compression.c that keeps the reference's
+ * compression.h API on top of this library is pg_cryogen_b200/host/compression.c;
+ * INTEGRATION.md shows the binding.
+ *
+ * Conventions: extern "C"; plain pointers and integers; no exceptions, no
+ * palloc/elog, no longjmp across the boundary.  Every entry point returns a
+ * call-level code (CRYOGPU_OK or CRYOGPU_E_*); per-block outcomes are written to
+ * the caller's status[] array so that one bad block never fails a batch
+ * (cache.c:178-179 maps a failed block to CRYO_ERR_DECOMPRESSION_FAILED).
+ * There is no CPU fallback: without a usable CUDA device every call fails with
+ * CRYOGPU_E_CUDA.
+ */
+#ifndef CRYOGPU_H
+#define CRYOGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRYOGPU_VERSION 100
+
+/* compression.h:7-11 -- stored on disk as a 4-byte int (storage.h:64) */
+#define CRYOGPU_LZ4  0
+#define CRYOGPU_ZSTD 1
+
+/* storage.h:18 */
+#define CRYOGPU_BLCKSZ (1u << 20)
+
+/* call-level return codes */
+#define CRYOGPU_OK          0
+#define CRYOGPU_E_CUDA     (-1)   /* CUDA runtime error; cryogpu_last_error() has the text */
+#define CRYOGPU_E_ARG      (-2)   /* bad argument (NULL, misaligned device pointer, size) */
+#define CRYOGPU_E_NOMEM    (-3)
+#define CRYOGPU_E_METHOD   (-4)   /* unknown compression method (compression.c:137, :157) */
+
+/* per-block status[] values */
+#define CRYOGPU_ST_OK            0
+#define CRYOGPU_ST_INPUT         1   /* truncated stream / input not consumed exactly */
+#define CRYOGPU_ST_OUTPUT        2   /* output would exceed the block capacity */
+#define CRYOGPU_ST_OFFSET        3   /* match offset 0 or before the start of the output */
+#define CRYOGPU_ST_FORMAT        4   /* bad magic, reserved value, invalid entropy table */
+#define CRYOGPU_ST_SIZE          5   /* zstd frame content size does not match */
+#define CRYOGPU_ST_METHOD        6   /* unknown per-block method */
+#define CRYOGPU_ST_UNSUPPORTED   7   /* valid but outside what this build handles */
+
+typedef struct cryogpu_ctx cryogpu_ctx;
+
+int         cryogpu_version(void);
+const char *cryogpu_last_error(void);
+const char *cryogpu_status_string(int status);
+
+/* Number of usable CUDA devices (0 when there is none; never throws). */
+int         cryogpu_device_count(void);
+
+/*
+ * Lazy, per-process, per-device context (stream, scratch, pinned staging).
+ * Safe to call after fork() in a PostgreSQL backend (pg_cryogen.c:169-176):
+ * nothing touches CUDA before the first cryogpu_init.
+ */
+int         cryogpu_init(int device, cryogpu_ctx **ctx);
+void        cryogpu_shutdown(cryogpu_ctx *ctx);
+int         cryogpu_device(const cryogpu_ctx *ctx);
+
+/* LZ4_compressBound / ZSTD_compressBound for one block of block_size bytes. */
+uint64_t    cryogpu_compress_bound(int method, uint64_t block_size);
+
+/* Pinned host memory for the *_host calls (pageable pointers work too, slower). */
+void       *cryogpu_host_alloc(size_t bytes);
+void        cryogpu_host_free(void *p);
+
+/*
+ * Batched decompression, everything device-resident.
+ *
+ *   d_methods[i]   CRYOGPU_LZ4 / CRYOGPU_ZSTD, per block (storage.h:64: the method
+ *                  is a per-block header field)
+ *   d_src          base of the compressed bytes; block i is
+ *                  d_src[d_src_off[i] .. d_src_off[i] + d_src_size[i]); the buffer
+ *                  must be readable up to the next 16-byte boundary
+ *   d_dst          output; block i is written to d_dst + i * dst_stride, capacity
+ *                  block_size (CRYO_BLCKSZ in the reference: compression.c:84, :116);
+ *                  d_dst and dst_stride must be multiples of 16
+ *   d_out_size[i]  bytes produced (the reference only Asserts == CRYO_BLCKSZ,
+ *                  compression.c:88, :120)
+ *   d_status[i]    CRYOGPU_ST_*
+ *   stream         a cudaStream_t (NULL = the context's own stream); the call only
+ *                  enqueues work, it does not synchronise
+ */
+int cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n,
+                              const int32_t *d_methods,
+                              const uint8_t *d_src, const uint64_t *d_src_off,
+                              const uint32_t *d_src_size,
+                              uint8_t *d_dst, uint64_t dst_stride, uint32_t block_size,
+                              uint32_t *d_out_size, int32_t *d_status, void *stream);
+
+/*
+ * Batched compression, everything device-resident.  Block i is read from
+ * d_src + i * src_stride (block_size bytes) and written to d_dst + i * dst_stride
+ * (capacity dst_cap >= cryogpu_compress_bound).  level_or_accel is
+ * lz4_acceleration (compression.c:72) or zstd_compression_level (compression.c:104).
+ */
+int cryogpu_compress_device(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel,
+                            const uint8_t *d_src, uint64_t src_stride, uint32_t block_size,
+                            uint8_t *d_dst, uint64_t dst_stride, uint32_t dst_cap,
+                            uint32_t *d_dst_size, int32_t *d_status, void *stream);
+
+/*
+ * Host-pointer variants: H2D copy, kernels, D2H copy, synchronous.  This is what
+ * the drop-in compression.c calls with n = 1 (pg_cryogen.c:726, cache.c:178) and
+ * what a batched cache fill / COPY flush calls with n > 1.
+ */
+int cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
+                            const void *const *src, const uint32_t *src_size,
+                            void *const *dst, uint32_t block_size,
+                            uint32_t *out_size, int32_t *status);
+
+int cryogpu_compress_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel,
+                          const void *const *src, uint32_t block_size,
+                          void *const *dst, uint32_t dst_cap,
+                          uint32_t *dst_size, int32_t *status);
+
+/*
+ * Multi-GPU host variants: the batch is split into contiguous block ranges, one
+ * per context (one host thread + stream per GPU, no collective).
+ */
+int cryogpu_decompress_host_multi(cryogpu_ctx *const *ctxs, int nctx, size_t n,
+                                  const int32_t *methods, const void *const *src,
+                                  const uint32_t *src_size, void *const *dst,
+                                  uint32_t block_size, uint32_t *out_size, int32_t *status);
+
+int cryogpu_compress_host_multi(cryogpu_ctx *const *ctxs, int nctx, size_t n, int method,
+                                int level_or_accel, const void *const *src,
+                                uint32_t block_size, void *const *dst, uint32_t dst_cap,
+                                uint32_t *dst_size, int32_t *status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRYOGPU_H */

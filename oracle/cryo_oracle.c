@@ -926,8 +926,7 @@ cryo_oracle_zstd_decode(const uint8_t *src, size_t src_size, uint8_t *dst, size_
 
     if (st)
         memset(st, 0, sizeof(*st));
-    if (src_size == 0)
-        ERR(CRYO_ORACLE_ERR_INPUT);
+    /* src_size == 0: ZSTD_decompress returns 0 (no frames), not an error */
     while (ip < src_size)
     {
         uint32_t magic;
@@ -1005,7 +1004,11 @@ cryo_oracle_zstd_decode(const uint8_t *src, size_t src_size, uint8_t *dst, size_
         }
         if (single)
             window = fcs;
-        block_max = window < (1 << 17) ? (size_t) window : (1 << 17);
+        /* RFC 8878: Block_Maximum_Size = min(Window_Size, 128 KiB).  libzstd 1.5.5's one-shot
+         * ZSTD_decompress only enforces the 128 KiB constant, so tiny single-segment frames
+         * whose blocks exceed their own content size decode fine there; follow the library. */
+        block_max = 1 << 17;
+        (void) window;
         if (st)
         {
             st->frames++;
