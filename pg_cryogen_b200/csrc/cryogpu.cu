@@ -9,7 +9,9 @@
 #include "../../include/cryogpu.h"
 
 #include "lz4_decode.cuh"
+#include "lz4_decode_w.cuh"
 #include "zstd_decode.cuh"
+#include "zstd_decode_w.cuh"
 #include "lz4_encode.cuh"
 #include "zstd_encode.cuh"
 
@@ -63,6 +65,21 @@ k_lz4_decode(const int32_t *methods, const uint8_t *src, const uint64_t *src_off
                      status + b);
 }
 
+/* throughput path: one warp per block, LZ4W_WARPS blocks per CTA */
+__global__ void __launch_bounds__(LZ4W_THREADS)
+k_lz4_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
+               const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
+               uint32_t *out_size, int32_t *status, uint32_t n)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * LZ4W_WARPS + warp;
+
+    if (b >= n || methods[b] != CRYOGPU_LZ4)
+        return;
+    lz4w_decode_block(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
+                      status + b, CRYO_SMEM_BASE() + warp * LZ4W_PER_WARP, lane);
+}
+
 __global__ void __launch_bounds__(ZSTDD_THREADS)
 k_zstd_decode(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
               const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
@@ -74,6 +91,32 @@ k_zstd_decode(const int32_t *methods, const uint8_t *src, const uint64_t *src_of
         return;
     zstd_decode_frame(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
                       status + b, scratch + b * scratch_stride);
+}
+
+/* throughput path: one warp per frame, ZSW_WARPS frames per CTA */
+__global__ void __launch_bounds__(ZSW_THREADS)
+k_zstd_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
+                const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
+                uint32_t *out_size, int32_t *status, uint8_t *scratch, uint64_t scratch_stride,
+                const uint32_t *predef, uint32_t n)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * ZSW_WARPS + warp;
+
+    if (b >= n || methods[b] != CRYOGPU_ZSTD)
+        return;
+    zstdw_decode_frame(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
+                       status + b, scratch + b * scratch_stride, predef,
+                       CRYO_SMEM_BASE() + warp * ZSW_PER_WARP, lane);
+}
+
+/* the three predefined FSE tables of RFC 8878 3.1.1.3.2.2, built once per context */
+__global__ void
+k_zstd_build_predef(uint32_t *predef)
+{
+    __shared__ __align__(16) uint8_t sm[2048];
+
+    zsw_build_predef(predef, sm, threadIdx.x);
 }
 
 __global__ void
@@ -110,6 +153,65 @@ k_zstd_encode(const uint8_t *src, uint64_t src_stride, uint32_t block_size, uint
                       dst_size + b, status + b, scratch + b * scratch_stride);
 }
 
+/* which LZ4 decode kernel: CRYOGPU_LZ4_KERNEL=cta selects the one-CTA-per-block variant */
+static bool
+lz4_use_cta_kernel()
+{
+    static int v = -1;
+
+    if (v < 0)
+    {
+        const char *e = getenv("CRYOGPU_LZ4_KERNEL");
+
+        v = (e && strcmp(e, "cta") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
+static void
+launch_lz4_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint8_t *src,
+                  const uint64_t *src_off, const uint32_t *src_size, uint8_t *dst,
+                  uint64_t dst_stride, uint32_t cap, uint32_t *out_size, int32_t *status)
+{
+    if (lz4_use_cta_kernel())
+        k_lz4_decode<<<(unsigned) n, LZ4D_THREADS, LZ4D_SMEM, st>>>(methods, src, src_off, src_size,
+                                                                   dst, dst_stride, cap, out_size,
+                                                                   status);
+    else
+        k_lz4_decode_w<<<(unsigned) ((n + LZ4W_WARPS - 1) / LZ4W_WARPS), LZ4W_THREADS, LZ4W_SMEM, st>>>(
+            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n);
+}
+
+static bool
+zstd_use_cta_kernel()
+{
+    static int v = -1;
+
+    if (v < 0)
+    {
+        const char *e = getenv("CRYOGPU_ZSTD_KERNEL");
+
+        v = (e && strcmp(e, "cta") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
+static void
+launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint8_t *src,
+                   const uint64_t *src_off, const uint32_t *src_size, uint8_t *dst,
+                   uint64_t dst_stride, uint32_t cap, uint32_t *out_size, int32_t *status,
+                   uint8_t *scratch, const uint32_t *predef)
+{
+    if (zstd_use_cta_kernel())
+        k_zstd_decode<<<(unsigned) n, ZSTDD_THREADS, ZSTDD_SMEM, st>>>(
+            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
+            ZSTDD_SCRATCH_BYTES);
+    else
+        k_zstd_decode_w<<<(unsigned) ((n + ZSW_WARPS - 1) / ZSW_WARPS), ZSW_THREADS, ZSW_SMEM, st>>>(
+            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
+            ZSTDD_SCRATCH_BYTES, predef, (uint32_t) n);
+}
+
 /* ----------------------------------------------------------------- context */
 
 struct DevBuf
@@ -125,6 +227,7 @@ struct cryogpu_ctx
     cudaStream_t stream2 = nullptr;     /* second lane for double buffering */
     cudaEvent_t  ev[2] = {nullptr, nullptr};
     DevBuf       scratch;               /* per-block kernel scratch */
+    uint32_t    *predef = nullptr;      /* predefined zstd FSE tables (device) */
     /* *_host staging (device + pinned host), two lanes */
     DevBuf       d_in[2], d_out[2], d_meta[2];
     DevBuf       h_in[2], h_meta[2], h_out[2];
@@ -168,7 +271,13 @@ set_kernel_attrs(cryogpu_ctx *ctx)
     if (ctx->attrs_set)
         return CRYOGPU_OK;
     CU(cudaFuncSetAttribute(k_lz4_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ4D_SMEM));
+    CU(cudaFuncSetAttribute(k_lz4_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ4W_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSTDD_SMEM));
+    CU(cudaFuncSetAttribute(k_zstd_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSW_SMEM));
+    CU(cudaMalloc(&ctx->predef, ZSW_PREDEF_CELLS * sizeof(uint32_t)));
+    k_zstd_build_predef<<<1, 32, 0, ctx->stream>>>(ctx->predef);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaFuncSetAttribute(k_lz4_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ4E_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSTDE_SMEM));
     ctx->attrs_set = true;
@@ -268,6 +377,7 @@ cryogpu_shutdown(cryogpu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->stream2);
     cudaFree(ctx->scratch.p);
+    cudaFree(ctx->predef);
     for (int i = 0; i < 2; i++)
     {
         cudaFree(ctx->d_in[i].p);
@@ -351,12 +461,10 @@ cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
     }
     k_flag_unknown_methods<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(d_methods, n, d_out_size,
                                                                          d_status);
-    k_lz4_decode<<<(unsigned) n, LZ4D_THREADS, LZ4D_SMEM, st>>>(d_methods, d_src, d_src_off,
-                                                               d_src_size, d_dst, dst_stride,
-                                                               block_size, d_out_size, d_status);
-    k_zstd_decode<<<(unsigned) n, ZSTDD_THREADS, ZSTDD_SMEM, st>>>(
-        d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size, d_out_size,
-        d_status, (uint8_t *) ctx->scratch.p, ZSTDD_SCRATCH_BYTES);
+    launch_lz4_decode(st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
+                      d_out_size, d_status);
+    launch_zstd_decode(st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
+                       d_out_size, d_status, (uint8_t *) ctx->scratch.p, ctx->predef);
     CU(cudaGetLastError());
     return CRYOGPU_OK;
 }
@@ -518,14 +626,15 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
 
         k_flag_unknown_methods<<<(unsigned) ((cnt + 255) / 256), 256, 0, st>>>(
             (int32_t *) (dm + cnt * 12), cnt, (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20));
-        k_lz4_decode<<<(unsigned) cnt, LZ4D_THREADS, LZ4D_SMEM, st>>>(
-            (int32_t *) (dm + cnt * 12), (uint8_t *) ctx->d_in[lane].p, (uint64_t *) dm,
-            (uint32_t *) (dm + cnt * 8), (uint8_t *) ctx->d_out[lane].p, stride, block_size,
-            (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20));
-        k_zstd_decode<<<(unsigned) cnt, ZSTDD_THREADS, ZSTDD_SMEM, st>>>(
-            (int32_t *) (dm + cnt * 12), (uint8_t *) ctx->d_in[lane].p, (uint64_t *) dm,
-            (uint32_t *) (dm + cnt * 8), (uint8_t *) ctx->d_out[lane].p, stride, block_size,
-            (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20), scr, ZSTDD_SCRATCH_BYTES);
+        launch_lz4_decode(st, cnt, (int32_t *) (dm + cnt * 12), (uint8_t *) ctx->d_in[lane].p,
+                          (uint64_t *) dm, (uint32_t *) (dm + cnt * 8),
+                          (uint8_t *) ctx->d_out[lane].p, stride, block_size,
+                          (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20));
+        launch_zstd_decode(st, cnt, (int32_t *) (dm + cnt * 12), (uint8_t *) ctx->d_in[lane].p,
+                           (uint64_t *) dm, (uint32_t *) (dm + cnt * 8),
+                           (uint8_t *) ctx->d_out[lane].p, stride, block_size,
+                           (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20), scr,
+                           ctx->predef);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(hm + cnt * 16, dm + cnt * 16, cnt * 8, cudaMemcpyDeviceToHost, st));
         if (dst_pinned)

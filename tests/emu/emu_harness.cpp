@@ -8,6 +8,8 @@
 #include "cuda_emu.h"
 #include "../../pg_cryogen_b200/csrc/lz4_decode.cuh"
 #include "../../pg_cryogen_b200/csrc/zstd_decode.cuh"
+#include "../../pg_cryogen_b200/csrc/lz4_decode_w.cuh"
+#include "../../pg_cryogen_b200/csrc/zstd_decode_w.cuh"
 
 #include <vector>
 
@@ -67,4 +69,95 @@ emu_zstd_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap, 
         if (o[-i] != 0xAA || o[cap + i - 1] != 0xAA)
             return -100;
     return status;
+}
+
+/* warp-per-block LZ4 decoder: two copies of the block so both warps of the CTA run */
+extern "C" int
+emu_lz4w_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap, unsigned shift,
+                uint32_t *out_size)
+{
+    Padded  in(src, csize, shift);
+    std::vector<uint8_t> obuf(2 * (size_t) cap + 512, 0xAA);
+    int32_t status[2] = {-1, -1};
+    uint32_t osz[2] = {0, 0};
+    uint8_t *o = (uint8_t *) ((((uintptr_t) obuf.data() + 63) & ~(uintptr_t) 63) + 64);
+    uint32_t stride = (cap + 15u) & ~15u;
+
+    emu::launch(dim3(1), dim3(LZ4W_THREADS), LZ4W_SMEM, [&]() {
+        uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (warp < 2)
+            lz4w_decode_block(in.p, csize, o + warp * (size_t) stride, cap, osz + warp, status + warp,
+                              CRYO_SMEM_BASE() + warp * LZ4W_PER_WARP, lane);
+    });
+    if (status[0] != status[1] || osz[0] != osz[1] || memcmp(o, o + stride, cap) != 0)
+        return -101;
+    memcpy(dst, o, cap);
+    *out_size = osz[0];
+    for (int i = 1; i <= 64; i++)
+        if (o[-i] != 0xAA)
+            return -100;
+    return status[0];
+}
+
+/* warp-per-frame zstd decoder; the predefined tables are built by the same device code */
+extern "C" int
+emu_zstdw_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap, unsigned shift,
+                 uint32_t *out_size)
+{
+    Padded  in(src, csize, shift);
+    std::vector<uint8_t> obuf(2 * (size_t) cap + 512, 0xAA), scr(2 * ZSTDD_SCRATCH_BYTES + 128, 0x77);
+    static uint32_t predef[ZSW_PREDEF_CELLS];
+    static bool have_predef = false;
+    int32_t status[2] = {-1, -1};
+    uint32_t osz[2] = {0, 0};
+    uint8_t *o = (uint8_t *) ((((uintptr_t) obuf.data() + 63) & ~(uintptr_t) 63) + 64);
+    uint8_t *sc = (uint8_t *) ((((uintptr_t) scr.data() + 63) & ~(uintptr_t) 63));
+    uint32_t stride = (cap + 15u) & ~15u;
+
+    if (!have_predef)
+    {
+        emu::launch(dim3(1), dim3(32), 2048, [&]() { zsw_build_predef(predef, CRYO_SMEM_BASE(), threadIdx.x); });
+        have_predef = true;
+    }
+    emu::launch(dim3(1), dim3(ZSW_THREADS), ZSW_SMEM, [&]() {
+        uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        zstdw_decode_frame(in.p, csize, o + warp * (size_t) stride, cap, osz + warp, status + warp,
+                           sc + warp * ZSTDD_SCRATCH_BYTES, predef,
+                           CRYO_SMEM_BASE() + warp * ZSW_PER_WARP, lane);
+    });
+    if (status[0] != status[1] || osz[0] != osz[1] || memcmp(o, o + stride, cap) != 0)
+        return -101;
+    memcpy(dst, o, cap);
+    *out_size = osz[0];
+    for (int i = 1; i <= 64; i++)
+        if (o[-i] != 0xAA)
+            return -100;
+    return status[0];
+}
+
+/* serial vs warp-parallel FSE table build on the same counts (returns number of differing cells) */
+extern "C" int
+emu_fse_build_compare(const int16_t *counts, int nsym, int log)
+{
+    static uint32_t a[512], b[512];
+    static uint16_t nexts[64];
+    int diff = 0;
+
+    fse_build_table(a, counts, nsym, log, nexts);
+    emu::launch(dim3(1), dim3(32), 4096, [&]() {
+        uint8_t *sm = CRYO_SMEM_BASE();
+        int16_t *c = reinterpret_cast<int16_t *>(sm);
+        for (int i = threadIdx.x; i < nsym; i += 32)
+            c[i] = counts[i];
+        __syncwarp();
+        fse_build_table_warp(reinterpret_cast<uint32_t *>(sm + 1024), c, nsym, log,
+                             reinterpret_cast<uint16_t *>(sm + 256),
+                             reinterpret_cast<uint16_t *>(sm + 512), threadIdx.x);
+        __syncwarp();
+        for (int i = threadIdx.x; i < (1 << log); i += 32)
+            b[i] = reinterpret_cast<uint32_t *>(sm + 1024)[i];
+    });
+    for (int i = 0; i < (1 << log); i++)
+        diff += a[i] != b[i];
+    return diff;
 }
