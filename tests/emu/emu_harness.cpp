@@ -11,6 +11,7 @@
 #include "../../pg_cryogen_b200/csrc/lz4_decode_w.cuh"
 #include "../../pg_cryogen_b200/csrc/zstd_decode_w.cuh"
 #include "../../pg_cryogen_b200/csrc/lz4_encode.cuh"
+#include "../../pg_cryogen_b200/csrc/zstd_encode.cuh"
 
 #include <vector>
 
@@ -177,6 +178,29 @@ emu_lz4_encode(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t dst_cap, i
     memcpy(in, src, n);
     emu::launch(dim3(1), dim3(LZ4E_THREADS), LZ4E_SMEM, [&]() {
         lz4_encode_block(in, n, o, dst_cap, accel, dst_size, &status, sc);
+    });
+    if (status == 0)
+        memcpy(dst, o, *dst_size);
+    for (int i = 1; i <= 64; i++)
+        if (o[-i] != 0xAA || o[dst_cap + i - 1] != 0xAA)
+            return -100;
+    return status;
+}
+
+extern "C" int
+emu_zstd_encode(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t dst_cap, int level,
+                uint32_t *dst_size)
+{
+    std::vector<uint8_t> ibuf((size_t) n + 256, 0xEE), obuf((size_t) dst_cap + 256, 0xAA),
+                         scr(zstde_scratch_bytes(n) + 256, 0x55);
+    uint8_t *in = (uint8_t *) ((((uintptr_t) ibuf.data() + 63) & ~(uintptr_t) 63) + 64);
+    uint8_t *o = (uint8_t *) ((((uintptr_t) obuf.data() + 63) & ~(uintptr_t) 63) + 64);
+    uint8_t *sc = (uint8_t *) ((((uintptr_t) scr.data() + 63) & ~(uintptr_t) 63));
+    int32_t status = -1;
+
+    memcpy(in, src, n);
+    emu::launch(dim3(1), dim3(ZSTDE_THREADS), ZSTDE_SMEM, [&]() {
+        zstd_encode_frame(in, n, o, dst_cap, level, dst_size, &status, sc);
     });
     if (status == 0)
         memcpy(dst, o, *dst_size);
