@@ -142,15 +142,15 @@ k_lz4_encode(const uint8_t *src, uint64_t src_stride, uint32_t block_size, uint8
                      dst_size + b, status + b, scratch + b * scratch_stride);
 }
 
+/* persistent: one CTA per SM walks the batch; scratch is per CTA, not per block */
 __global__ void __launch_bounds__(ZSTDE_THREADS)
 k_zstd_encode(const uint8_t *src, uint64_t src_stride, uint32_t block_size, uint8_t *dst,
               uint64_t dst_stride, uint32_t dst_cap, int level, uint32_t *dst_size,
-              int32_t *status, uint8_t *scratch, uint64_t scratch_stride)
+              int32_t *status, uint8_t *scratch, uint64_t scratch_stride, uint32_t n)
 {
-    const uint32_t b = blockIdx.x;
-
-    zstd_encode_frame(src + b * src_stride, block_size, dst + b * dst_stride, dst_cap, level,
-                      dst_size + b, status + b, scratch + b * scratch_stride);
+    for (uint32_t b = blockIdx.x; b < n; b += gridDim.x)
+        zstd_encode_frame(src + b * src_stride, block_size, dst + b * dst_stride, dst_cap, level,
+                          dst_size + b, status + b, scratch + blockIdx.x * scratch_stride);
 }
 
 /* which LZ4 decode kernel: CRYOGPU_LZ4_KERNEL=cta selects the one-CTA-per-block variant */
@@ -233,6 +233,7 @@ struct cryogpu_ctx
     DevBuf       h_in[2], h_meta[2], h_out[2];
     std::mutex   mu;
     bool         attrs_set = false;
+    int          sm_count = 148;
 };
 
 static int
@@ -348,6 +349,7 @@ cryogpu_init(int device, cryogpu_ctx **out)
     cryogpu_ctx *ctx = new cryogpu_ctx();
 
     ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming) != cudaSuccess ||
@@ -494,9 +496,10 @@ cryogpu_compress_device(cryogpu_ctx *ctx, size_t n, int method, int level_or_acc
 
     CU(cudaSetDevice(ctx->device));
     size_t per = method == CRYOGPU_LZ4 ? lz4e_scratch_bytes(block_size) : zstde_scratch_bytes(block_size);
+    const size_t zgrid = std::min<size_t>(n, (size_t) ctx->sm_count);
     {
         std::lock_guard<std::mutex> g(ctx->mu);
-        int rc = dev_reserve(ctx->scratch, n * per);
+        int rc = dev_reserve(ctx->scratch, (method == CRYOGPU_LZ4 ? n : zgrid) * per);
 
         if (rc != CRYOGPU_OK)
             return rc;
@@ -506,9 +509,9 @@ cryogpu_compress_device(cryogpu_ctx *ctx, size_t n, int method, int level_or_acc
             d_src, src_stride, block_size, d_dst, dst_stride, dst_cap, level_or_accel, d_dst_size,
             d_status, (uint8_t *) ctx->scratch.p, per);
     else
-        k_zstd_encode<<<(unsigned) n, ZSTDE_THREADS, ZSTDE_SMEM, st>>>(
+        k_zstd_encode<<<(unsigned) zgrid, ZSTDE_THREADS, ZSTDE_SMEM, st>>>(
             d_src, src_stride, block_size, d_dst, dst_stride, dst_cap, level_or_accel, d_dst_size,
-            d_status, (uint8_t *) ctx->scratch.p, per);
+            d_status, (uint8_t *) ctx->scratch.p, per, (uint32_t) n);
     CU(cudaGetLastError());
     return CRYOGPU_OK;
 }
@@ -758,10 +761,11 @@ cryogpu_compress_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel
                 dstride, (uint32_t) bound, level_or_accel, (uint32_t *) dm, (int32_t *) (dm + cnt * 4),
                 scr, per);
         else
-            k_zstd_encode<<<(unsigned) cnt, ZSTDE_THREADS, ZSTDE_SMEM, st>>>(
+            k_zstd_encode<<<(unsigned) std::min<size_t>(cnt, (size_t) ctx->sm_count), ZSTDE_THREADS,
+                            ZSTDE_SMEM, st>>>(
                 (uint8_t *) ctx->d_in[lane].p, sstride, block_size, (uint8_t *) ctx->d_out[lane].p,
                 dstride, (uint32_t) bound, level_or_accel, (uint32_t *) dm, (int32_t *) (dm + cnt * 4),
-                scr, per);
+                scr, per, (uint32_t) cnt);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(ctx->h_meta[lane].p, dm, cnt * 8, cudaMemcpyDeviceToHost, st));
         /* compressed sizes are unknown until the kernel ends: bring back whole slots when the

@@ -30,8 +30,8 @@
  *
  * Blocks that do not shrink are stored Raw.  After a CTA barrier the block sizes are
  * prefix-summed and all warps copy header + body into place with coalesced stores.
- * Levels: <= 0 (negative levels): raw literals + accelerated probing, like libzstd;
- * 1..2: Huffman literals, min match 6/5; >= 3: min match 5 + a denser probe schedule.
+ * Levels: negative levels = raw literals + strided probing (stride grows with -level), like
+ * libzstd; level >= 1 (and 0) = Huffman literals, every position probed, min match 5.
  */
 #pragma once
 #include "cryo_common.cuh"
@@ -92,7 +92,7 @@ ZSE_HD size_t zstde_scratch_bytes(uint32_t block_size)
 struct ZseParams
 {
     uint32_t    mm;             /* minimum match length, 4..8 */
-    uint32_t    accel;          /* probe stride schedule, as in liblz4: step = (accel<<6 + misses)>>6 */
+    uint32_t    step;           /* distance between probe pairs: libzstd's stepSize (2 = every position) */
     bool        huffman;        /* compress literals */
 };
 
@@ -111,22 +111,30 @@ CRYO_DEV ZseParams zse_params(int level)
         if (level == 0)
         {
             p.mm = 5;
-            p.accel = 1;
+            p.step = 2;
             p.huffman = true;
         }
         else
         {
-            p.mm = 6;
-            p.accel = (uint32_t) (-level) + 1u;
+            /* raw literals cost 8 bits each, so matches of 5 pay; probes are denser than
+             * libzstd's stepSize = 1 - level because the table only spans this 64 KiB block */
+            p.mm = 5;
+            p.step = 2u + ((uint32_t) (-level) - 1u) / 2u;
             p.huffman = false;
         }
     }
     else
     {
-        p.mm = level == 1 ? 6 : 5;
-        p.accel = 1;
+        p.mm = 5;
+        p.step = 2;
         p.huffman = true;
     }
+#ifdef CRYO_EMU
+    if (getenv("ZSE_DBG_MM"))
+        p.mm = (uint32_t) atoi(getenv("ZSE_DBG_MM"));
+    if (getenv("ZSE_DBG_STEP"))
+        p.step = (uint32_t) atoi(getenv("ZSE_DBG_STEP"));
+#endif
     return p;
 }
 
@@ -402,17 +410,43 @@ CRYO_DEV uint32_t zse_fse_step(uint32_t &X, uint32_t s, const uint16_t *enc, con
 
 /* ---- match finder ------------------------------------------------------------ */
 
+/* warp-uniform forward extension of a match at (pos, pos - off): bytes beyond `have` */
+CRYO_DEV uint32_t zse_extend(const uint8_t *in, uint32_t len, uint32_t pos, uint32_t off, uint32_t have,
+                             uint32_t lane)
+{
+    uint32_t ml = have;
+
+    for (;;)
+    {
+        uint32_t idx = pos + ml + lane;
+        bool     eq = idx < len && in[idx] == in[idx - off];
+        uint32_t ne = ~__ballot_sync(CRYO_FULL, eq);
+
+        if (ne == 0)
+        {
+            ml += 32;
+            continue;
+        }
+        return ml + (uint32_t) __ffs((int) ne) - 1u;
+    }
+}
+
 /*
  * One warp parses in[0, len) greedily.  Sequences go to seq[] (x = ll | (ml-3) << 16,
  * y = offset), their literals are appended to lit[].  Returns the sequence count; *nlit_out
  * is the total literal count including the run after the last match.
+ *
+ * Probe schedule (libzstd's ZSTD_fast, 16 pairs at a time): positions p + k*S and p + k*S + 1,
+ * S = P.step growing by one for every 128 bytes scanned without a match.  Every probe also
+ * tests the last used offset (a repeat-offset match costs almost nothing to code) and a
+ * repeat hit wins over a hash hit that starts at most one byte earlier, like libzstd's
+ * check of ip+1.
  */
 CRYO_DEV uint32_t zse_find_matches(const uint8_t *in, uint32_t len, const ZseParams &P, uint4 *seq,
                                    uint8_t *lit, uint16_t *table, uint32_t lane, uint32_t *nlit_out)
 {
-    uint32_t anchor = 0, p = 0, nseq = 0, nlit = 0;
-    const uint32_t start_attempts = P.accel << 6;
-    uint32_t attempts = start_attempts;
+    uint32_t anchor = 0, p = 0, nseq = 0, nlit = 0, missed = 0;
+    uint32_t rep1 = 0, rep2 = 0;
     const uint32_t mm = P.mm;
     const uint32_t tailmask = mm >= 8 ? 0xFFFFFFFFu : (mm <= 4 ? 0u : ((1u << (8u * (mm - 4u))) - 1u));
 
@@ -426,11 +460,11 @@ CRYO_DEV uint32_t zse_find_matches(const uint8_t *in, uint32_t len, const ZsePar
 
         while (p <= plimit && nseq < ZSE_MAXSEQ)
         {
-            const uint32_t step = attempts >> 6;
-            const uint32_t pos = lane == 0 ? p : p + 1 + (lane - 1) * step;
+            const uint32_t S = P.step + (missed >> 7);
+            const uint32_t pos = p + (lane >> 1) * S + (lane & 1u);
             const bool     valid = pos <= plimit;
             uint32_t v = 0, v2 = 0, h = 0, cand = 0;
-            bool     hit = false;
+            bool     hit = false, rhit = false;
 
             if (valid)
             {
@@ -440,32 +474,36 @@ CRYO_DEV uint32_t zse_find_matches(const uint8_t *in, uint32_t len, const ZsePar
                 cand = table[h];
                 hit = cand < pos && zse_ld4(in + cand) == v &&
                       (zse_ld4(in + cand + 4) & tailmask) == v2;
+                rhit = rep1 != 0 && pos >= rep1 && zse_ld4(in + pos - rep1) == v;
             }
             /* probes of one group cannot see each other through the table: a probe whose
              * bytes repeat the previous probe's (runs, short periods) matches it directly */
             {
                 uint32_t pv = __shfl_up_sync(CRYO_FULL, v, 1), pv2 = __shfl_up_sync(CRYO_FULL, v2, 1);
+                uint32_t pp = __shfl_up_sync(CRYO_FULL, pos, 1);
 
                 if (valid && !hit && lane > 0 && pv == v && pv2 == v2)
                 {
                     hit = true;
-                    cand = lane == 1 ? p : pos - step;
+                    cand = pp;
                 }
             }
-            const uint32_t m = __ballot_sync(CRYO_FULL, hit);
+            const uint32_t mh = __ballot_sync(CRYO_FULL, hit), mr = __ballot_sync(CRYO_FULL, rhit);
+            const int      kh = mh ? __ffs((int) mh) - 1 : 64, kr = mr ? __ffs((int) mr) - 1 : 64;
+            const bool     use_rep = mr != 0 && kr <= kh + 1;
+            const int      k = use_rep ? kr : kh;
 
-            if (valid && (m & ((1u << lane) - 1u)) == 0)
+            if (valid && (int) lane <= (k > 31 ? 31 : k))
                 table[h] = (uint16_t) pos;
             __syncwarp();
-            if (m == 0)
+            if (k > 31)
             {
-                p += 1 + 31 * step;
-                attempts += 32;
+                p += 16 * S;
+                missed += 16 * S;
                 continue;
             }
-            const int k = __ffs((int) m) - 1;
-            uint32_t  mpos = k == 0 ? p : p + 1 + (uint32_t) (k - 1) * step;
-            uint32_t  mcand = __shfl_sync(CRYO_FULL, cand, k);
+            uint32_t  mpos = p + ((uint32_t) k >> 1) * S + ((uint32_t) k & 1u);
+            uint32_t  mcand = use_rep ? mpos - rep1 : __shfl_sync(CRYO_FULL, cand, k);
             const uint32_t off = mpos - mcand;
             const uint32_t mpos0 = mpos;
 
@@ -482,23 +520,7 @@ CRYO_DEV uint32_t zse_find_matches(const uint8_t *in, uint32_t len, const ZsePar
                 if (back < 32)
                     break;
             }
-            /* extend forwards, 32 bytes per step */
-            uint32_t ml = (mm < 4 ? 4 : mm) + (mpos0 - mpos);
-
-            for (;;)
-            {
-                uint32_t idx = mpos + ml + lane;
-                bool     eq = idx < len && in[idx] == in[idx - off];
-                uint32_t ne = ~__ballot_sync(CRYO_FULL, eq);
-
-                if (ne == 0)
-                {
-                    ml += 32;
-                    continue;
-                }
-                ml += (uint32_t) __ffs((int) ne) - 1u;
-                break;
-            }
+            uint32_t ml = zse_extend(in, len, mpos, off, (use_rep || mm < 4 ? 4u : mm) + (mpos0 - mpos), lane);
             const uint32_t ll = mpos - anchor;
 
             if (lane == 0)
@@ -507,15 +529,40 @@ CRYO_DEV uint32_t zse_find_matches(const uint8_t *in, uint32_t len, const ZsePar
             if (ll)
                 team_copy(lit + nlit, in + anchor, ll, lane, 32);
             nlit += ll;
-            p = anchor = mpos + ml;
-            attempts = start_attempts;
-            if (lane == 0 && p >= 2 && p - 2 <= plimit)
+            if (off != rep1)
             {
-                uint32_t a = zse_ld4(in + p - 2), b = zse_ld4(in + p + 2) & tailmask;
+                rep2 = rep1;
+                rep1 = off;
+            }
+            p = anchor = mpos + ml;
+            missed = 0;
+            if (lane < 2)
+            {
+                /* like libzstd: remember match start + 2 and match end - 2 */
+                const uint32_t q = lane == 0 ? mpos + 2 : p - 2;
 
-                table[((a * 2654435761u) ^ (b * 2246822519u)) >> (32 - ZSE_HASHLOG)] = (uint16_t) (p - 2);
+                if (q <= plimit)
+                {
+                    uint32_t a = zse_ld4(in + q), b = zse_ld4(in + q + 4) & tailmask;
+
+                    table[((a * 2654435761u) ^ (b * 2246822519u)) >> (32 - ZSE_HASHLOG)] = (uint16_t) q;
+                }
             }
             __syncwarp();
+            /* immediate matches at the second repeat offset (no literals in between) */
+            while (rep2 != 0 && p <= plimit && nseq < ZSE_MAXSEQ && p >= rep2 &&
+                   zse_ld4(in + p) == zse_ld4(in + p - rep2))
+            {
+                const uint32_t ml2 = zse_extend(in, len, p, rep2, 4u, lane);
+                const uint32_t t = rep2;
+
+                if (lane == 0)
+                    seq[nseq] = make_uint4(0u | ((ml2 - 3u) << 16), rep2, 0u, 0u);
+                nseq++;
+                rep2 = rep1;
+                rep1 = t;
+                p = anchor = p + ml2;
+            }
         }
     }
     if (len > anchor)

@@ -1,0 +1,108 @@
+"""-m gpu: batched zstd frame compression (k_zstd_encode) against the reference.
+
+Replaces ZSTD_compress at reference compression.c:102-104.  Three-part contract
+(BASELINE.json north_star): every GPU-written frame is a standard zstd frame that the
+reference's own cryo_decompress (libzstd) restores byte-identically; its size stays
+within the stated tolerance of the reference's size at the same zstd_compression_level;
+and the GPU decoder reads it back too.
+"""
+import numpy as np
+import pytest
+
+from pg_cryogen_b200 import COMP_ZSTD, CRYO_BLCKSZ, compress_bound
+from pg_cryogen_b200 import blockgen as bg
+
+from gpu_util import decode_device, encode_device
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1.15                  # gpu_csize <= 1.15 x reference at the same level
+
+
+def _blocks():
+    blocks, tags = [], []
+    for kind in "SMD":
+        for pl in bg.PAYLOADS:
+            blocks.append(bg.make_block(kind, pl, 11))
+            tags.append(f"{kind}/{pl}")
+    blocks.append(np.zeros(CRYO_BLCKSZ, dtype=np.uint8))
+    tags.append("zeros")
+    blocks.append(bg.regression_block(1, 290))
+    tags.append("regression-1")
+    blocks.append(bg.regression_block(291, 500))
+    tags.append("regression-2")
+    rnd = np.frombuffer(bg.rand_bytes(99, CRYO_BLCKSZ).tobytes(), dtype=np.uint8)
+    blocks.append(rnd.copy())
+    tags.append("incompressible")
+    return np.stack(blocks), tags
+
+
+@pytest.mark.parametrize("level", [-5, -3, -1, 0, 1, 2, 3])
+def test_zstd_encode_roundtrip_and_ratio(gpu, oracle_ref, level):
+    blocks, tags = _blocks()
+    comp, st = encode_device(gpu, COMP_ZSTD, level, blocks)
+    assert (st == 0).all(), st
+    ref_comp, ref_sizes, _ = oracle_ref.compress(COMP_ZSTD, level, blocks, nthreads=8)
+    back, ok, _ = oracle_ref.decompress([COMP_ZSTD] * len(comp), *oracle_ref.pack(comp))
+    assert ok.all(), "the reference's ZSTD_decompress rejected a GPU-written frame"
+    assert np.array_equal(back, blocks)
+    for i, c in enumerate(comp):
+        assert len(c) <= compress_bound(COMP_ZSTD), tags[i]
+        assert len(c) <= TOL * ref_sizes[i] + 64, (tags[i], level, len(c), int(ref_sizes[i]))
+    out, osz, dst = decode_device(gpu, COMP_ZSTD, comp)
+    assert (dst == 0).all() and (osz == CRYO_BLCKSZ).all() and np.array_equal(out, blocks)
+
+
+@pytest.mark.parametrize("level", [4, 9, 19, 22, -50])
+def test_zstd_encode_levels_outside_the_baseline_sweep(gpu, oracle_ref, level):
+    """The GUC allows -5..22 (compression.c:53); levels above 3 use the level-3 parameters and
+    must stay valid frames (ratio is only promised for -5..3)."""
+    blocks = np.stack([bg.make_block("M", "lowcard", 3), bg.make_block("D", "hex", 4)])
+    comp, st = encode_device(gpu, COMP_ZSTD, level, blocks)
+    assert (st == 0).all()
+    back, ok, _ = oracle_ref.decompress([COMP_ZSTD] * 2, *oracle_ref.pack(comp))
+    assert ok.all() and np.array_equal(back, blocks)
+
+
+def test_zstd_encode_frame_header_is_what_the_reference_stores(gpu):
+    """One frame: magic, content size = block size, no checksum, no dictionary."""
+    blk = bg.make_block("S", "hex", 1)[None]
+    comp, st = encode_device(gpu, COMP_ZSTD, 1, blk)
+    c = comp[0]
+    assert bytes(c[:4]) == b"\x28\xb5\x2f\xfd"
+    fhd = int(c[4])
+    assert fhd & 0x04 == 0 and fhd & 0x03 == 0          # no checksum, no dictionary id
+    assert fhd >> 6 == 2 and fhd & 0x20                 # 4-byte content size, single segment
+    assert int.from_bytes(bytes(c[5:9]), "little") == CRYO_BLCKSZ
+
+
+def test_zstd_encode_small_block_sizes(gpu, oracle_port):
+    """block_size is a runtime parameter of the library; odd sizes exercise the tail paths."""
+    src = bg.make_block("D", "lowcard", 2)
+    for bs in (65536 * 3, 65536 + 4096, 65536, 4096, 1024, 304, 64, 16):
+        blocks = np.ascontiguousarray(src[: bs * 3].reshape(3, bs))
+        comp, st = encode_device(gpu, COMP_ZSTD, 1, blocks, block_size=bs)
+        assert (st == 0).all(), bs
+        for i, c in enumerate(comp):
+            n, out = oracle_port.zstd_decode(c, cap=bs)[:2]
+            assert n == bs and np.array_equal(out[:bs], blocks[i]), (bs, i, n)
+
+
+def test_zstd_encode_host_api_and_shim_contract(gpu, oracle_ref):
+    blocks = np.stack([bg.make_block(k, "hex", 40 + i) for i, k in enumerate("SMD")])
+    comp, st = gpu.compress_host(COMP_ZSTD, 1, blocks)
+    assert (st == 0).all()
+    back, ok, _ = oracle_ref.decompress([COMP_ZSTD] * 3, *oracle_ref.pack(comp))
+    assert ok.all() and np.array_equal(back, blocks)
+
+
+def test_zstd_encode_large_batch_persistent_grid(gpu, oracle_ref):
+    """More blocks than SMs: the persistent CTAs reuse their scratch across blocks."""
+    uniq = np.stack([bg.make_block("SMD"[i % 3], bg.PAYLOADS[i % len(bg.PAYLOADS)], 70 + i) for i in range(6)])
+    blocks = np.concatenate([uniq] * 60)               # 360 blocks > 148 SMs
+    comp, st = encode_device(gpu, COMP_ZSTD, 1, blocks)
+    assert (st == 0).all()
+    for i in range(6, len(comp)):
+        assert np.array_equal(comp[i], comp[i % 6]), i  # deterministic, no cross-block leakage
+    back, ok, _ = oracle_ref.decompress([COMP_ZSTD] * 6, *oracle_ref.pack(comp[:6]))
+    assert ok.all() and np.array_equal(back, uniq)

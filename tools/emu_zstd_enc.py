@@ -19,7 +19,7 @@ def enc(blk, level):
 
 if __name__ == "__main__":
     levels = [int(a) for a in sys.argv[1:]] or [1]
-    cases = [("S", "hex"), ("S", "lowcard"), ("M", "hex"), ("M", "lowcard"), ("D", "hex"), ("D", "lowcard"), ("D", "random")]
+    cases = [tuple(c.split("/")) for c in os.environ["CASES"].split(",")] if os.environ.get("CASES") else [("S", "hex"), ("S", "lowcard"), ("M", "hex"), ("M", "lowcard"), ("D", "hex"), ("D", "lowcard"), ("D", "random")]
     for lv in levels:
         for kind, pl in cases:
             blk = bg.make_block(kind, pl, 11)
@@ -27,4 +27,4 @@ if __name__ == "__main__":
             back, ok = ref.decompress_one(1, c) if st == 0 else (None, False)
             good = ok and np.array_equal(back, blk)
             rsz = int(ref.compress(1, lv, blk)[1][0])
-            print(f"level {lv:3d} {kind}/{pl:8s} status={st} size={len(c):8d} ref={rsz:8d} ratio={len(c)/rsz:6.3f} roundtrip={'OK' if good else 'FAIL'}  ({dt:.1f}s)", flush=True)
+            print(os.environ.get("ZSE_DBG_MM","-"), os.environ.get("ZSE_DBG_STEP","-"), end=" "); print(f"level {lv:3d} {kind}/{pl:8s} status={st} size={len(c):8d} ref={rsz:8d} ratio={len(c)/rsz:6.3f} roundtrip={'OK' if good else 'FAIL'}  ({dt:.1f}s)", flush=True)

@@ -34,7 +34,8 @@ def probe(method, level, kind, payload, n):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
-    for sp in sys.argv[2:] or ["0:1:S:hex", "0:1:M:hex", "0:1:D:hex", "0:1:D:lowcard"]:
+    for sp in sys.argv[2:] or ["0:1:S:hex", "0:1:M:hex", "0:1:D:hex", "0:1:D:lowcard",
+                              "1:1:S:hex", "1:1:M:hex", "1:1:D:hex", "1:1:D:lowcard", "1:-5:D:lowcard", "1:3:M:lowcard"]:
         m, l, k, pl = sp.split(":")
         try:
             probe(int(m), int(l), k, pl, n)
