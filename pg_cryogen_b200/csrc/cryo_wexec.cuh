@@ -23,12 +23,12 @@
 #include "cryo_common.cuh"
 
 #ifndef WX_RING
-#define WX_RING   4096u           /* power of two */
+#define WX_RING   2048u           /* power of two */
 #endif
 #define WX_RMASK  (WX_RING - 1u)
 #define WX_DRAIN  512u            /* bytes per drain step (32 lanes x 16 B) */
 #define WX_BULK   512u            /* runs at least this long bypass the ring */
-#define WX_PAT_MAXOFF 1024u      /* k*off + 32 must fit the ring */
+#define WX_PAT_MAXOFF 512u       /* k*off + 32 must fit the ring */
 
 struct WOut
 {

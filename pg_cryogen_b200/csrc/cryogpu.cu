@@ -94,7 +94,7 @@ k_zstd_decode(const int32_t *methods, const uint8_t *src, const uint64_t *src_of
 }
 
 /* throughput path: one warp per frame, ZSW_WARPS frames per CTA */
-__global__ void __launch_bounds__(ZSW_THREADS)
+__global__ void __launch_bounds__(ZSW_THREADS, ZSW_CTAS_PER_SM)
 k_zstd_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
                 const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
                 uint32_t *out_size, int32_t *status, uint8_t *scratch, uint64_t scratch_stride,

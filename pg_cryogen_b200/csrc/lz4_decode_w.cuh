@@ -122,6 +122,33 @@ CRYO_DEV void lz4w_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
         uint32_t token = in.win[rel];
         uint32_t ll = token >> 4, ml = token & 15u;
 
+        /*
+         * Fast path: no length-extension bytes (ll <= 14, match <= 18), everything well inside
+         * the input window and the output capacity, the match source inside the ring and not
+         * overlapping its destination.  One predicated move each for literals and match.
+         */
+        if (ll != 15u && ml != 15u && rel + 24u <= LZ4W_WIN && ip + ll + 11u <= in.end &&
+            o.pos + ll + ml + 21u <= cap)
+        {
+            const uint32_t off = in.win[rel + 1 + ll] | ((uint32_t) in.win[rel + 2 + ll] << 8);
+            const uint32_t mlen = ml + 4u;
+            const uint32_t mpos = o.pos + ll;
+
+            if (off >= mlen && off <= WX_RING - 64u && off <= mpos && mpos - off >= o.lo)
+            {
+                if (lane < ll)
+                    o.ring[(o.pos + lane) & WX_RMASK] = in.win[rel + 1 + lane];
+                __syncwarp();
+                if (lane < mlen)
+                    o.ring[(mpos + lane) & WX_RMASK] = o.ring[(mpos - off + lane) & WX_RMASK];
+                o.pos = mpos + mlen;
+                ip += 3u + ll;
+                __syncwarp();
+                if (o.pos - o.flushed >= WX_DRAIN)
+                    wx_drain(o, lane);
+                continue;
+            }
+        }
         ip++;
         if (ll == 15)
         {

@@ -23,24 +23,49 @@
 #include "cryo_wexec.cuh"
 #include "zstd_decode.cuh"
 
-#define ZSW_WARPS     2
+#define ZSW_WARPS     8
 #define ZSW_THREADS   (32 * ZSW_WARPS)
-#define ZSW_LITWIN    1024u
-/* per-warp shared memory: [0,6K) ring+litwin / Huffman table+scratch, then the FSE tables */
+#define ZSW_CTAS_PER_SM 3
+#define ZSW_LITWIN    512u
+#define ZSW_SEQWIN    512u
+/*
+ * per-warp shared memory, 9 216 bytes (24 frames in flight per SM):
+ *   [0, 4096)     literal phase : Huffman table u16[2048]
+ *                 table phase   : FSE build scratch at ZSW_OFF_FSEWORK (the Huffman table is dead)
+ *                 sequence phase: ring [0, 2048) | literal window | sequence-bitstream window
+ *   [4096, 9216)  FSE cells LL u32[512] | OF u32[256] | ML u32[512]; the Huffman build scratch
+ *                 overlays the LL cells, so a table reused through Repeat_Mode is rebuilt from its
+ *                 remembered description
+ */
 #define ZSW_OFF_RING    0
-#define ZSW_OFF_LITWIN  WX_RING                 /* sequence phase */
-#define ZSW_OFF_HUF     0                       /* entropy phase: u16[2048] */
-#define ZSW_OFF_WORK    4096                    /* entropy phase: 2 KB */
-#define ZSW_OFF_LL      6144
+#define ZSW_OFF_LITWIN  WX_RING                               /* 2048 */
+#define ZSW_OFF_SEQWIN  (ZSW_OFF_LITWIN + ZSW_LITWIN)         /* 2560: 16 B zero pad + window + 16 */
+#define ZSW_OFF_HUF     0
+#define ZSW_OFF_FSEWORK 2048                                  /* ZW_COUNTS.. offsets land in [3200, 3900) */
+#define ZSW_OFF_LL      4096
 #define ZSW_OFF_OF      (ZSW_OFF_LL + 2048)
 #define ZSW_OFF_ML      (ZSW_OFF_OF + 1024)
-#define ZSW_PER_WARP    (ZSW_OFF_ML + 2048)     /* 11264 */
+#define ZSW_OFF_HUFWORK ZSW_OFF_LL
+#define ZSW_PER_WARP    (ZSW_OFF_ML + 2048)     /* 9216 */
 #define ZSW_SMEM        (ZSW_WARPS * ZSW_PER_WARP)
 #define ZSW_PREDEF_CELLS (64 + 32 + 64)         /* LL, OF, ML predefined tables */
 
-#if WX_RING + ZSW_LITWIN > 6144
-#error "ring + literal window must fit the 6 KB they share with the Huffman table"
+#if ZSW_OFF_SEQWIN + ZSW_SEQWIN + 32 > 4096
+#error "ring + windows must fit the 4 KB they share with the Huffman table"
 #endif
+
+/* code -> baseline | extra bits << 24 (RFC 8878 3.1.1.3.2.1.1) */
+CRYO_CONST uint32_t ZS_LL_PACK[36] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15,
+    16 | (1u << 24), 18 | (1u << 24), 20 | (1u << 24), 22 | (1u << 24), 24 | (2u << 24), 28 | (2u << 24),
+    32 | (3u << 24), 40 | (3u << 24), 48 | (4u << 24), 64 | (6u << 24), 128 | (7u << 24), 256 | (8u << 24),
+    512 | (9u << 24), 1024 | (10u << 24), 2048 | (11u << 24), 4096 | (12u << 24), 8192 | (13u << 24),
+    16384 | (14u << 24), 32768 | (15u << 24), 65536 | (16u << 24)};
+CRYO_CONST uint32_t ZS_ML_PACK[53] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20,
+    21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35 | (1u << 24), 37 | (1u << 24),
+    39 | (1u << 24), 41 | (1u << 24), 43 | (2u << 24), 47 | (2u << 24), 51 | (3u << 24), 59 | (3u << 24),
+    67 | (4u << 24), 83 | (4u << 24), 99 | (5u << 24), 131 | (7u << 24), 259 | (8u << 24), 515 | (9u << 24),
+    1027 | (10u << 24), 2051 | (11u << 24), 4099 | (12u << 24), 8195 | (13u << 24), 16387 | (14u << 24),
+    32771 | (15u << 24), 65539 | (16u << 24)};
 
 CRYO_DEV uint32_t zsw_match_any(uint32_t v)
 {
@@ -166,17 +191,34 @@ struct ZswState
     const uint8_t *huf_desc;                            /* last Huffman tree description */
     uint32_t    huf_desc_len;
     uint32_t    rep0, rep1, rep2;
+    /* how each sequence table was last defined, for Repeat_Mode: 0 predefined, 1 RLE, 2 FSE */
+    int         tmode[3];
+    const uint8_t *tdesc[3];
+    uint32_t    tlen[3];
 };
 
 /* one sequence table (t: 0 LL, 1 OF, 2 ML); returns bytes of description consumed or ~0u */
-CRYO_DEV uint32_t zsw_seq_table(int mode, int t, const uint8_t *p, uint32_t left, uint32_t *cell,
-                                uint8_t *work, const uint32_t *predef, int &logv, uint32_t lane)
+CRYO_DEV uint32_t zsw_seq_table(ZswState &z, int mode, int t, const uint8_t *p, uint32_t left,
+                                uint32_t *cell, uint8_t *work, const uint32_t *predef, int &logv,
+                                uint32_t lane)
 {
     const int max_log = t == 1 ? 8 : 9, max_sym = t == 0 ? 35 : t == 1 ? 31 : 52;
     int16_t  *counts = reinterpret_cast<int16_t *>(work + ZW_COUNTS);
     uint16_t *next = reinterpret_cast<uint16_t *>(work + ZW_NEXT);
     uint16_t *cum = reinterpret_cast<uint16_t *>(work + ZW_NEXT + 128);
+    bool      repeat = false;
 
+    if (mode == 3)
+    {
+        /* Repeat_Mode: the cells may have been overwritten since (the Huffman build scratch
+         * overlays them), so the table is rebuilt from how it was last defined */
+        if (logv < 0 || z.tmode[t] < 0)
+            return ~0u;
+        mode = z.tmode[t];
+        p = z.tdesc[t];
+        left = z.tlen[t];
+        repeat = true;
+    }
     switch (mode)
     {
         case 0:
@@ -186,6 +228,7 @@ CRYO_DEV uint32_t zsw_seq_table(int mode, int t, const uint8_t *p, uint32_t left
             for (uint32_t i = lane; i < n; i += 32)
                 cell[i] = predef[o + i];
             logv = t == 1 ? 5 : 6;
+            z.tmode[t] = 0;
             __syncwarp();
             return 0;
         }
@@ -195,9 +238,12 @@ CRYO_DEV uint32_t zsw_seq_table(int mode, int t, const uint8_t *p, uint32_t left
             if (lane == 0)
                 cell[0] = p[0];                       /* nbits 0, base 0 */
             logv = 0;
+            z.tmode[t] = 1;
+            z.tdesc[t] = p;
+            z.tlen[t] = 1;
             __syncwarp();
-            return 1;
-        case 2:
+            return repeat ? 0u : 1u;
+        default:
         {
             int32_t  nsym = 0, log = 0;
             uint32_t used = 0;
@@ -212,25 +258,312 @@ CRYO_DEV uint32_t zsw_seq_table(int mode, int t, const uint8_t *p, uint32_t left
             __syncwarp();
             fse_build_table_warp(cell, counts, nsym, log, next, cum, lane);
             logv = log;
-            return used;
+            z.tmode[t] = 2;
+            z.tdesc[t] = p;
+            z.tlen[t] = used;
+            return repeat ? 0u : used;
         }
-        default:
-            return logv < 0 ? ~0u : 0u;
     }
 }
 
-/* Huffman literals of one block -> dst (global).  Table + scratch live in the idle ring. */
+/*
+ * Huffman tree description -> decoding table huf[1 << log] (u16: symbol | nbits << 8), same
+ * result as huf_build_table (zstd_decode.cuh) with the per-symbol ranking done by the whole
+ * warp: 32 symbols per step, rank inside the step by __match_any_sync, running per-weight
+ * counters in shared memory.  Returns bytes used by the description, 0 on error.
+ */
+CRYO_DEV uint32_t zsw_huf_build(const uint8_t *src, uint32_t n, uint16_t *huf, uint8_t *work,
+                                int32_t *log_out, uint32_t lane)
+{
+    uint8_t  *weights = work + ZW_WEIGHTS;
+    uint16_t *symstart = reinterpret_cast<uint16_t *>(work + ZW_SYMSTART);
+    uint32_t *wfse = reinterpret_cast<uint32_t *>(work + ZW_WFSE);
+    int16_t  *wcounts = reinterpret_cast<int16_t *>(work + ZW_WCOUNTS);
+    uint16_t *wnext = reinterpret_cast<uint16_t *>(work + ZW_NEXT + 3 * 128);
+    uint32_t *rankc = reinterpret_cast<uint32_t *>(work + ZW_COUNTS);      /* u32[16] counts, u32[16] starts */
+    uint32_t  used = 0, nw = 0;
+    int       bad = 0;
+
+    if (n == 0)
+        return 0;
+    uint32_t h = src[0];
+
+    if (h >= 128)
+    {
+        nw = h - 127;
+        used = 1 + (nw + 1) / 2;
+        if (used > n)
+            return 0;
+        for (uint32_t i = lane; i < nw; i += 32)
+        {
+            uint32_t b = src[1 + i / 2];
+
+            weights[i] = (uint8_t) ((i & 1) ? (b & 15u) : (b >> 4));
+        }
+        __syncwarp();
+    }
+    else
+    {
+        used = 1 + h;
+        if (used > n || h == 0)
+            return 0;
+        if (lane == 0)
+        {
+            int32_t  nsym = 0, flog = 0;
+            uint32_t hdr = fse_read_counts(src + 1, h, 6, 12, wcounts, &nsym, &flog);
+
+            if (hdr == 0 || hdr >= h)
+                bad = 1;
+            else
+            {
+                BitsBack bb;
+
+                fse_build_table(wfse, wcounts, nsym, flog, wnext);
+                if (!bb_init(bb, src + 1 + hdr, h - hdr))
+                    bad = 1;
+                else
+                {
+                    bb_refill(bb);
+                    uint32_t s1 = bb_read(bb, (uint32_t) flog);
+                    uint32_t s2 = bb_read(bb, (uint32_t) flog);
+
+                    for (;;)
+                    {
+                        if (nw > 253)
+                        {
+                            bad = 1;
+                            break;
+                        }
+                        uint32_t c1 = wfse[s1];
+
+                        weights[nw++] = (uint8_t) c1;
+                        bb_refill(bb);
+                        s1 = (c1 >> 16) + bb_read(bb, (c1 >> 8) & 0xFFu);
+                        if (bb.remaining < 0)
+                        {
+                            weights[nw++] = (uint8_t) wfse[s2];
+                            break;
+                        }
+                        uint32_t c2 = wfse[s2];
+
+                        weights[nw++] = (uint8_t) c2;
+                        bb_refill(bb);
+                        s2 = (c2 >> 16) + bb_read(bb, (c2 >> 8) & 0xFFu);
+                        if (bb.remaining < 0)
+                        {
+                            weights[nw++] = (uint8_t) wfse[s1];
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+        bad = __shfl_sync(CRYO_FULL, bad, 0);
+        nw = __shfl_sync(CRYO_FULL, nw, 0);
+        if (bad)
+            return 0;
+        __syncwarp();
+    }
+    /* sum of 2^(w-1), implied last weight */
+    uint32_t sum = 0, over = 0;
+
+    for (uint32_t i = lane; i < nw; i += 32)
+    {
+        uint32_t w = weights[i];
+
+        if (w > 11)
+            over = 1;
+        else if (w)
+            sum += 1u << (w - 1);
+    }
+    sum = __reduce_add_sync(CRYO_FULL, sum);
+    over = __reduce_or_sync(CRYO_FULL, over);
+    if (over || sum == 0)
+        return 0;
+    const int log = zs_highbit(sum) + 1;
+
+    if (log > 11)
+        return 0;
+    const uint32_t left = (1u << log) - sum;
+
+    if (left & (left - 1))
+        return 0;
+    if (lane == 0)
+        weights[nw] = (uint8_t) (zs_highbit(left) + 1);
+    nw += 1;
+    if (lane < 16)
+        rankc[lane] = 0;
+    __syncwarp();
+    /* pass 1: symbols per weight */
+    const uint32_t lt = (1u << lane) - 1u;
+
+    for (uint32_t s0 = 0; s0 < nw; s0 += 32)
+    {
+        const uint32_t s = s0 + lane;
+        const uint32_t w = s < nw ? weights[s] : 0u;
+        const uint32_t m = zsw_match_any(w);
+
+        if (w && (m & lt) == 0)
+            rankc[w] += (uint32_t) __popc(m);
+        __syncwarp();
+    }
+    /* first cell of every weight class: cells ordered by ascending weight, then symbol */
+    if (lane == 0)
+    {
+        uint32_t a = 0;
+
+        for (int r = 1; r <= log; r++)
+        {
+            uint32_t c = rankc[r];
+
+            rankc[16 + r] = a;
+            a += c << (r - 1);
+        }
+    }
+    __syncwarp();
+    /* pass 2: first cell of every symbol */
+    for (uint32_t s0 = 0; s0 < nw; s0 += 32)
+    {
+        const uint32_t s = s0 + lane;
+        const uint32_t w = s < nw ? weights[s] : 0u;
+        const uint32_t m = zsw_match_any(w);
+
+        if (w)
+            symstart[s] = (uint16_t) (rankc[16 + w] + ((uint32_t) __popc(m & lt) << (w - 1)));
+        __syncwarp();
+        if (w && (m & lt) == 0)
+            rankc[16 + w] += (uint32_t) __popc(m) << (w - 1);
+        __syncwarp();
+    }
+    /* fill: long codes (few cells) one symbol per lane, short codes by the whole warp */
+    for (uint32_t s0 = 0; s0 < nw; s0 += 32)
+    {
+        const uint32_t s = s0 + lane;
+        const uint32_t w = s < nw ? weights[s] : 0u;
+        const uint32_t len = w ? 1u << (w - 1) : 0u;
+        const uint32_t st = w ? symstart[s] : 0u;
+        const uint16_t ent = (uint16_t) (s | ((uint32_t) (log + 1 - (int) w) << 8));
+
+        if (len && len <= 8)
+            for (uint32_t i = 0; i < len; i++)
+                huf[st + i] = ent;
+        uint32_t big = __ballot_sync(CRYO_FULL, len > 8);
+
+        while (big)
+        {
+            const int      k = __ffs((int) big) - 1;
+            const uint32_t klen = __shfl_sync(CRYO_FULL, len, k), kst = __shfl_sync(CRYO_FULL, st, k);
+            const uint32_t kent = __shfl_sync(CRYO_FULL, (uint32_t) ent, k);
+
+            for (uint32_t i = lane; i < klen; i += 32)
+                huf[kst + i] = (uint16_t) kent;
+            big &= big - 1;
+        }
+    }
+    __syncwarp();
+    *log_out = log;
+    return used;
+}
+
+/*
+ * One Huffman stream, one lane: `count` symbols to dst; returns false on corruption.
+ * The accumulator is an explicit (hi, lo) register pair with the next bit at bit 31 of hi: a
+ * table index is one shift of hi (log <= 11), consuming a code is one funnel shift.  Two
+ * symbols per refill check (2 x 11 <= 32), four symbols per 32-bit store.
+ */
+CRYO_DEV bool zsw_huf_stream(const uint16_t *huf, int log, const uint8_t *src, uint32_t n,
+                             uint8_t *dst, uint32_t count)
+{
+    BitsBack bb;
+
+    if (!bb_init(bb, src, n))
+        return false;
+    uint32_t hi = (uint32_t) (bb.acc >> 32), lo = (uint32_t) bb.acc;
+    int32_t  avail = bb.avail;
+    uintptr_t cur = bb.cur;
+    uint32_t nextw = bb.nextw;
+    const uintptr_t start = bb.start;
+    const uint32_t sh = 32u - (uint32_t) log;
+    uint32_t i = 0;
+
+#define ZSW_HREFILL()                                                        \
+    if (avail <= 32)                                                         \
+    {                                                                        \
+        /* acc |= nextw << (32 - avail) in 64 bits */                        \
+        if (avail == 32)                                                     \
+            lo = nextw;                                                      \
+        else                                                                 \
+        {                                                                    \
+            hi |= nextw >> avail;                                            \
+            lo = nextw << (32 - avail);                                      \
+        }                                                                    \
+        if (avail == 0)                                                      \
+        {                                                                    \
+            hi = nextw;                                                      \
+            lo = 0;                                                          \
+        }                                                                    \
+        avail += 32;                                                         \
+        cur -= 4;                                                            \
+        nextw = bb_load(cur, start);                                         \
+    }
+#define ZSW_HDEC(sym)                                                        \
+    {                                                                        \
+        const uint32_t ent = huf[hi >> sh];                                  \
+        const uint32_t nb = ent >> 8;                                        \
+        sym = ent & 0xFFu;                                                   \
+        hi = __funnelshift_l(lo, hi, nb);                                    \
+        lo <<= nb;                                                           \
+        avail -= (int32_t) nb;                                               \
+    }
+    /* head: until dst + i is 4-byte aligned */
+    while (i < count && ((uintptr_t) (dst + i) & 3u))
+    {
+        uint32_t s;
+
+        ZSW_HREFILL();
+        ZSW_HDEC(s);
+        dst[i++] = (uint8_t) s;
+    }
+    while (i + 4 <= count)
+    {
+        uint32_t s0, s1, s2, s3;
+
+        ZSW_HREFILL();
+        ZSW_HDEC(s0);
+        ZSW_HDEC(s1);
+        ZSW_HREFILL();
+        ZSW_HDEC(s2);
+        ZSW_HDEC(s3);
+        *reinterpret_cast<uint32_t *>(dst + i) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+        i += 4;
+    }
+    while (i < count)
+    {
+        uint32_t s;
+
+        ZSW_HREFILL();
+        ZSW_HDEC(s);
+        dst[i++] = (uint8_t) s;
+    }
+#undef ZSW_HREFILL
+#undef ZSW_HDEC
+    /* every bit consumed exactly: bits still in the accumulator plus the bytes not loaded yet
+     * (negative when the reader ran past the start of the stream) */
+    return (int64_t) avail + 8 * ((int64_t) (cur + 4) - (int64_t) start) == 0;
+}
+
+/* Huffman literals of one block -> dst (global).  The table lives in the idle ring region. */
 CRYO_DEV int zsw_huffman_literals(ZswState &z, int lit_type, const uint8_t *p, uint32_t left,
                                   uint32_t regen, uint32_t streams, uint8_t *dst, uint8_t *smem,
                                   uint32_t lane)
 {
     uint16_t *huf = reinterpret_cast<uint16_t *>(smem + ZSW_OFF_HUF);
-    uint8_t  *work = smem + ZSW_OFF_WORK;
+    uint8_t  *work = smem + ZSW_OFF_HUFWORK;
 
     if (lit_type == 2)
     {
         int32_t  log = 0;
-        uint32_t used = huf_build_table(p, left, huf, work, &log, lane);
+        uint32_t used = zsw_huf_build(p, left, huf, work, &log, lane);
 
         if (used == 0)
             return ST_FORMAT;
@@ -246,7 +579,7 @@ CRYO_DEV int zsw_huffman_literals(ZswState &z, int lit_type, const uint8_t *p, u
          * since, so rebuild it from the remembered tree description */
         int32_t log = 0;
 
-        if (z.huf_log < 1 || huf_build_table(z.huf_desc, z.huf_desc_len, huf, work, &log, lane) == 0)
+        if (z.huf_log < 1 || zsw_huf_build(z.huf_desc, z.huf_desc_len, huf, work, &log, lane) == 0)
             return ST_FORMAT;
     }
     __syncwarp();
@@ -255,7 +588,7 @@ CRYO_DEV int zsw_huffman_literals(ZswState &z, int lit_type, const uint8_t *p, u
     if (streams == 1)
     {
         if (lane == 0)
-            ok = huf_decode_stream(huf, z.huf_log, p, left, dst, regen);
+            ok = zsw_huf_stream(huf, z.huf_log, p, left, dst, regen);
     }
     else
     {
@@ -277,10 +610,11 @@ CRYO_DEV int zsw_huffman_literals(ZswState &z, int lit_type, const uint8_t *p, u
                 uint32_t sn = lane == 0 ? s1 : lane == 1 ? s2 : lane == 2 ? s3 : s4;
                 uint32_t cnt = lane < 3 ? seg : regen - 3 * seg;
 
-                ok = huf_decode_stream(huf, z.huf_log, p + 6 + so, sn, dst + lane * seg, cnt);
+                ok = zsw_huf_stream(huf, z.huf_log, p + 6 + so, sn, dst + lane * seg, cnt);
             }
         }
     }
+    __threadfence_block();
     return __any_sync(CRYO_FULL, !ok) ? ST_FORMAT : ST_OK;
 }
 
@@ -294,42 +628,136 @@ struct ZswLits
     uint8_t     rle_byte;
 };
 
+CRYO_DEV void zsw_lits_fill(ZswLits &L, uint32_t ip, uint32_t lane)
+{
+    __syncwarp();
+    L.wbase = ip & ~15u;
+    L.wvalid = true;
+    {
+        uint32_t a = L.wbase + 16u * lane;
+
+        if (a < L.lim)
+            st16(L.win + 16u * lane, ld16(L.abase + a));
+    }
+    __syncwarp();
+}
+
 CRYO_DEV void zsw_lits_emit(WOut &o, ZswLits &L, uint32_t n, uint32_t lane)
 {
     if (n == 0)
         return;
     if (L.rle)
         wx_fill_byte(o, L.rle_byte, n, lane);
-    else if (n >= WX_BULK)
-        wx_literals(o, L.abase + L.delta + L.pos, n, lane);
+    else if (n >= WX_BULK || n + 16u > ZSW_LITWIN)
+    {
+        /* long run: straight from global memory (through the ring when it is short of a bulk) */
+        if (n >= WX_BULK)
+            wx_literals(o, L.abase + L.delta + L.pos, n, lane);
+        else
+        {
+            const uint8_t *g = L.abase + L.delta + L.pos;
+
+            for (uint32_t i = lane; i < n; i += 32)
+                o.ring[(o.pos + i) & WX_RMASK] = g[i];
+            o.pos += n;
+            __syncwarp();
+            wx_drain(o, lane);
+        }
+    }
     else
     {
         uint32_t ip = L.delta + L.pos;
 
         if (!L.wvalid || ip + n > L.wbase + ZSW_LITWIN)
-        {
-            __syncwarp();
-            L.wbase = ip & ~15u;
-            L.wvalid = true;
-#pragma unroll
-            for (uint32_t k = 0; k < ZSW_LITWIN / 512; k++)
-            {
-                uint32_t a = L.wbase + 512u * k + 16u * lane;
-
-                if (a < L.lim)
-                    st16(L.win + 512u * k + 16u * lane, ld16(L.abase + a));
-            }
-            __syncwarp();
-        }
+            zsw_lits_fill(L, ip, lane);
         wx_literals(o, L.win + (ip - L.wbase), n, lane);
     }
     L.pos += n;
 }
 
 /*
+ * Backward bit reader over a shared-memory window of the sequence bitstream.  Positions are
+ * bit offsets from `abase` (16-byte aligned, at or before the stream); bits [lowbit, bitpos)
+ * are unread.  A read takes the 64 bits below bitpos out of three aligned words; there is no
+ * accumulator to maintain.  The window slides down as the stream is consumed; below the
+ * stream start it reads zeros (the 16 bytes in front of the window are kept zero for that).
+ */
+struct ZswBits
+{
+    const uint8_t *abase;
+    const uint32_t *w32;        /* shared: word 0 = abase[wlo .. wlo + 4) */
+    uint8_t    *win;            /* shared: 16 zero bytes, then the window */
+    uint32_t    wlo;            /* byte offset of the window in abase coordinates, multiple of 16 */
+    uint32_t    lim;            /* stream end rounded up to 16 (abase coordinates) */
+    uint32_t    bitpos, lowbit;
+};
+
+CRYO_DEV void zsw_bits_fill(ZswBits &B, uint32_t lane)
+{
+    const uint32_t topbyte = B.bitpos >> 3;     /* highest byte still needed */
+
+    __syncwarp();
+    B.wlo = topbyte + 16u > ZSW_SEQWIN ? ((topbyte + 16u - ZSW_SEQWIN) & ~15u) : 0u;
+    {
+        const uint32_t a = B.wlo + 16u * lane;
+        uint4 v = make_uint4(0, 0, 0, 0);
+
+        if (a < B.lim)
+            v = ld16(B.abase + a);
+        st16(B.win + 16u + 16u * lane, v);
+    }
+    __syncwarp();
+    if (B.wlo == 0 && lane < (B.lowbit >> 3))
+        B.win[16u + lane] = 0;                  /* bytes in front of the stream read as zero */
+    __syncwarp();
+}
+
+CRYO_DEV bool zsw_bits_init(ZswBits &B, const uint8_t *p, uint32_t n, uint8_t *win, uint32_t lane)
+{
+    if (n == 0)
+        return false;
+    const uint32_t last = p[n - 1];
+
+    if (last == 0)
+        return false;
+    const uint32_t delta = (uint32_t) ((uintptr_t) p & 15u);
+
+    B.abase = p - delta;
+    B.win = win;
+    B.w32 = reinterpret_cast<const uint32_t *>(win + 16);
+    B.lowbit = delta * 8u;
+    B.bitpos = (delta + n - 1u) * 8u + (uint32_t) zs_highbit(last);
+    B.lim = (delta + n + 15u) & ~15u;
+    if (lane < 4)
+        reinterpret_cast<uint32_t *>(win)[lane] = 0;
+    zsw_bits_fill(B, lane);
+    return true;
+}
+
+/* the 64 bits below bitpos as (hi, lo); callers keep bitpos - 64 - 32 >= wlo * 8 or wlo == 0 */
+CRYO_DEV void zsw_bits_peek(const ZswBits &B, uint32_t &hi, uint32_t &lo)
+{
+    const int32_t rel = (int32_t) B.bitpos - 64 - (int32_t) (B.wlo * 8u);
+    const int32_t wi = rel >> 5;
+    const uint32_t sh = (uint32_t) rel & 31u;
+    const uint32_t w0 = B.w32[wi], w1 = B.w32[wi + 1], w2 = B.w32[wi + 2];
+
+    lo = __funnelshift_r(w0, w1, sh);
+    hi = __funnelshift_r(w1, w2, sh);
+}
+
+/* n bits (n <= 32) that follow the first c bits of the peeked window, c + n <= 64 */
+CRYO_DEV uint32_t zsw_bits_get(uint32_t hi, uint32_t lo, uint32_t c, uint32_t n)
+{
+    const uint32_t top = c < 32u ? __funnelshift_l(lo, hi, c) : (lo << (c - 32u));
+
+    return n ? top >> (32u - n) : 0u;
+}
+
+/*
  * Decode the zstd frame(s) at src[0, csize) into out[0, cap).  One warp; `smem` is this
- * warp's ZSW_PER_WARP bytes; `scratch` is ZSTDD_SCRATCH_BYTES of global memory private
- * to this warp (16-byte aligned); predef holds the three predefined FSE tables.
+ * warp's ZSW_PER_WARP bytes; `scratch` is ZSTDD_SCRATCH_BYTES of global memory private to
+ * this warp (16-byte aligned); predef holds the three predefined FSE tables.
  */
 CRYO_DEV void zstdw_decode_frame(const uint8_t *src, uint32_t csize, uint8_t *out, uint32_t cap,
                                  uint32_t *out_size, int32_t *status, uint8_t *scratch,
@@ -445,6 +873,9 @@ CRYO_DEV void zstdw_decode_frame(const uint8_t *src, uint32_t csize, uint8_t *ou
         z.rep0 = 1;
         z.rep1 = 4;
         z.rep2 = 8;
+        z.tmode[0] = z.tmode[1] = z.tmode[2] = -1;
+        z.tdesc[0] = z.tdesc[1] = z.tdesc[2] = nullptr;
+        z.tlen[0] = z.tlen[1] = z.tlen[2] = 0;
 
         /* ---- blocks ---- */
         for (;;)
@@ -637,8 +1068,9 @@ CRYO_DEV void zstdw_decode_frame(const uint8_t *src, uint32_t csize, uint8_t *ou
                 }
                 /* ---- entropy phase: the ring's shared memory holds tables and scratch ---- */
                 if (lt >= 2)
-                {
                     wx_drain_all(o, lane);          /* the Huffman table overlays the ring */
+                if (lt >= 2)
+                {
                     err = zsw_huffman_literals(z, (int) lt, bp + lhdr, lcsize, regen, streams,
                                                scratch, smem, lane);
                     if (err != ST_OK)
@@ -646,10 +1078,11 @@ CRYO_DEV void zstdw_decode_frame(const uint8_t *src, uint32_t csize, uint8_t *ou
                 }
                 if (nseq)
                 {
-                    uint8_t *work = smem + ZSW_OFF_WORK;
+                    uint8_t *work = smem + ZSW_OFF_FSEWORK;
                     uint32_t u;
 
-                    u = zsw_seq_table((modes >> 6) & 3, 0, bp + sp, bsize - sp, ll_tab, work, predef,
+                    __syncwarp();
+                    u = zsw_seq_table(z, (modes >> 6) & 3, 0, bp + sp, bsize - sp, ll_tab, work, predef,
                                       z.ll_log, lane);
                     if (u == ~0u)
                     {
@@ -657,7 +1090,7 @@ CRYO_DEV void zstdw_decode_frame(const uint8_t *src, uint32_t csize, uint8_t *ou
                         break;
                     }
                     sp += u;
-                    u = zsw_seq_table((modes >> 4) & 3, 1, bp + sp, bsize - sp, of_tab, work, predef,
+                    u = zsw_seq_table(z, (modes >> 4) & 3, 1, bp + sp, bsize - sp, of_tab, work, predef,
                                       z.of_log, lane);
                     if (u == ~0u)
                     {
@@ -665,7 +1098,7 @@ CRYO_DEV void zstdw_decode_frame(const uint8_t *src, uint32_t csize, uint8_t *ou
                         break;
                     }
                     sp += u;
-                    u = zsw_seq_table((modes >> 2) & 3, 2, bp + sp, bsize - sp, ml_tab, work, predef,
+                    u = zsw_seq_table(z, (modes >> 2) & 3, 2, bp + sp, bsize - sp, ml_tab, work, predef,
                                       z.ml_log, lane);
                     if (u == ~0u)
                     {
@@ -689,74 +1122,104 @@ CRYO_DEV void zstdw_decode_frame(const uint8_t *src, uint32_t csize, uint8_t *ou
                 /* ---- sequence phase ---- */
                 if (nseq)
                 {
-                    BitsBack bb;
-                    const int ll_log = z.ll_log, of_log = z.of_log, ml_log = z.ml_log;
+                    ZswBits  B;
+                    const uint32_t ll_log = (uint32_t) z.ll_log, of_log = (uint32_t) z.of_log,
+                                   ml_log = (uint32_t) z.ml_log;
 
-                    if (sp > bsize || !bb_init(bb, bp + sp, bsize - sp))
+                    if (sp > bsize || !zsw_bits_init(B, bp + sp, bsize - sp, smem + ZSW_OFF_SEQWIN, lane))
                     {
                         err = ST_FORMAT;
                         break;
                     }
-                    bb_refill(bb);
-                    uint32_t sl = bb_read(bb, (uint32_t) ll_log);
-                    uint32_t so = bb_read(bb, (uint32_t) of_log);
+                    uint32_t sl, so, sm;
+                    {
+                        uint32_t hi, lo;
 
-                    bb_refill(bb);
-                    uint32_t sm = bb_read(bb, (uint32_t) ml_log);
+                        zsw_bits_peek(B, hi, lo);
+                        sl = zsw_bits_get(hi, lo, 0, ll_log);
+                        so = zsw_bits_get(hi, lo, ll_log, of_log);
+                        sm = zsw_bits_get(hi, lo, ll_log + of_log, ml_log);
+                        if (B.bitpos - B.lowbit < ll_log + of_log + ml_log)
+                        {
+                            err = ST_INPUT;
+                            break;
+                        }
+                        B.bitpos -= ll_log + of_log + ml_log;
+                    }
+                    uint32_t rep0 = z.rep0, rep1 = z.rep1, rep2 = z.rep2;
+                    uint32_t lpos = 0;                  /* literals consumed (mirrors L.pos) */
 
                     for (uint32_t i = 0; i < nseq; i++)
                     {
-                        uint32_t cl = ll_tab[sl], co = of_tab[so], cm = ml_tab[sm];
-                        uint32_t lc = cl & 0xFFu, oc = co & 0xFFu, mc = cm & 0xFFu;
+                        /* keep the three words of a peek inside the window */
+                        if (B.wlo != 0 && B.bitpos < B.wlo * 8u + 160u)
+                            zsw_bits_fill(B, lane);
+                        const uint32_t cl = ll_tab[sl], co = of_tab[so], cm = ml_tab[sm];
+                        const uint32_t pl = ZS_LL_PACK[cl & 0xFFu], pm = ZS_ML_PACK[cm & 0xFFu];
+                        const uint32_t ofb = co & 0xFFu, mlb = pm >> 24, llb = pl >> 24;
+                        const bool     more = i + 1 < nseq;
+                        const uint32_t nbl = more ? (cl >> 8) & 0xFFu : 0u, nbm = more ? (cm >> 8) & 0xFFu : 0u,
+                                       nbo = more ? (co >> 8) & 0xFFu : 0u;
+                        uint32_t T = ofb + mlb + llb + nbl + nbm + nbo;
+                        uint32_t hi, lo, c = 0, ov;
 
-                        if (lc > 35 || mc > 52 || oc > 31)
+                        if (B.bitpos - B.lowbit < T)
                         {
-                            err = ST_FORMAT;
+                            err = ST_INPUT;
                             break;
                         }
-                        bb_refill(bb);
-                        uint32_t ov = (1u << oc) + bb_read(bb, oc);
+                        zsw_bits_peek(B, hi, lo);
+                        ov = (1u << ofb) + zsw_bits_get(hi, lo, 0, ofb);
+                        if (T > 64u)
+                        {
+                            /* a long offset code next to long length codes: take the offset
+                             * bits alone, then a fresh window for the rest (<= 58 bits) */
+                            B.bitpos -= ofb;
+                            T -= ofb;
+                            if (B.wlo != 0 && B.bitpos < B.wlo * 8u + 160u)
+                                zsw_bits_fill(B, lane);
+                            zsw_bits_peek(B, hi, lo);
+                        }
+                        else
+                            c = ofb;
+                        const uint32_t ml = (pm & 0xFFFFFFu) + zsw_bits_get(hi, lo, c, mlb);
 
-                        bb_refill(bb);
-                        uint32_t ml = ZS_ML_BASE[mc] + bb_read(bb, ZS_ML_BITS[mc]);
-                        uint32_t ll = ZS_LL_BASE[lc] + bb_read(bb, ZS_LL_BITS[lc]);
+                        c += mlb;
+                        const uint32_t ll = (pl & 0xFFFFFFu) + zsw_bits_get(hi, lo, c, llb);
+
+                        c += llb;
+                        sl = (cl >> 16) + zsw_bits_get(hi, lo, c, nbl);
+                        c += nbl;
+                        sm = (cm >> 16) + zsw_bits_get(hi, lo, c, nbm);
+                        c += nbm;
+                        so = (co >> 16) + zsw_bits_get(hi, lo, c, nbo);
+                        B.bitpos -= T;
+
                         uint32_t off;
 
                         if (ov > 3)
                         {
                             off = ov - 3;
-                            z.rep2 = z.rep1;
-                            z.rep1 = z.rep0;
-                            z.rep0 = off;
+                            rep2 = rep1;
+                            rep1 = rep0;
+                            rep0 = off;
                         }
                         else
                         {
-                            uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+                            const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
 
                             if (idx == 0)
-                                off = z.rep0;
+                                off = rep0;
                             else
                             {
-                                off = idx == 1 ? z.rep1 : idx == 2 ? z.rep2 : z.rep0 - 1;
+                                off = idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
                                 if (idx > 1)
-                                    z.rep2 = z.rep1;
-                                z.rep1 = z.rep0;
-                                z.rep0 = off;
+                                    rep2 = rep1;
+                                rep1 = rep0;
+                                rep0 = off;
                             }
                         }
-                        if (i + 1 < nseq)
-                        {
-                            bb_refill(bb);
-                            sl = (cl >> 16) + bb_read(bb, (cl >> 8) & 0xFFu);
-                            sm = (cm >> 16) + bb_read(bb, (cm >> 8) & 0xFFu);
-                            so = (co >> 16) + bb_read(bb, (co >> 8) & 0xFFu);
-                        }
-                        if (bb.remaining < 0)
-                        {
-                            err = ST_INPUT;
-                            break;
-                        }
-                        if (ll > L.n - L.pos)
+                        if (ll > regen - lpos)
                         {
                             err = ST_FORMAT;
                             break;
@@ -771,17 +1234,52 @@ CRYO_DEV void zstdw_decode_frame(const uint8_t *src, uint32_t csize, uint8_t *ou
                             err = ST_FORMAT;
                             break;
                         }
-                        zsw_lits_emit(o, L, ll, lane);
-                        if (off == 0 || off > o.pos - frame_start)
+                        const uint32_t mpos = o.pos + ll;
+
+                        if (off == 0 || off > mpos - frame_start)
                         {
                             err = ST_OFFSET;
                             break;
                         }
+                        /*
+                         * Fast path: a short literal run served from the literal window and a
+                         * short non-overlapping match whose source is in the ring: one
+                         * predicated shared-memory move each.
+                         */
+                        const uint32_t lip = L.delta + lpos;
+
+                        if (ll <= 32u && ml <= 32u && !L.rle && off >= ml && off <= WX_RING - 64u &&
+                            mpos - off >= o.lo)
+                        {
+                            if (ll)
+                            {
+                                if (!L.wvalid || lip + ll > L.wbase + ZSW_LITWIN || lip < L.wbase)
+                                    zsw_lits_fill(L, lip, lane);
+                                if (lane < ll)
+                                    o.ring[(o.pos + lane) & WX_RMASK] = L.win[lip - L.wbase + lane];
+                                __syncwarp();
+                            }
+                            if (lane < ml)
+                                o.ring[(mpos + lane) & WX_RMASK] = o.ring[(mpos - off + lane) & WX_RMASK];
+                            o.pos = mpos + ml;
+                            lpos += ll;
+                            __syncwarp();
+                            if (o.pos - o.flushed >= WX_DRAIN)
+                                wx_drain(o, lane);
+                            continue;
+                        }
+                        L.pos = lpos;
+                        zsw_lits_emit(o, L, ll, lane);
+                        lpos += ll;
                         wx_match(o, off, ml, lane);
                     }
+                    z.rep0 = rep0;
+                    z.rep1 = rep1;
+                    z.rep2 = rep2;
+                    L.pos = lpos;
                     if (err != ST_OK)
                         break;
-                    if (bb.remaining != 0)
+                    if (B.bitpos != B.lowbit)
                     {
                         err = ST_INPUT;
                         break;

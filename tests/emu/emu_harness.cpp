@@ -123,9 +123,10 @@ emu_zstdw_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap,
     }
     emu::launch(dim3(1), dim3(ZSW_THREADS), ZSW_SMEM, [&]() {
         uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        zstdw_decode_frame(in.p, csize, o + warp * (size_t) stride, cap, osz + warp, status + warp,
-                           sc + warp * ZSTDD_SCRATCH_BYTES, predef,
-                           CRYO_SMEM_BASE() + warp * ZSW_PER_WARP, lane);
+        if (warp < 2)
+            zstdw_decode_frame(in.p, csize, o + warp * (size_t) stride, cap, osz + warp, status + warp,
+                               sc + warp * ZSTDD_SCRATCH_BYTES, predef,
+                               CRYO_SMEM_BASE() + warp * ZSW_PER_WARP, lane);
     });
     if (status[0] != status[1] || osz[0] != osz[1] || memcmp(o, o + stride, cap) != 0)
         return -101;

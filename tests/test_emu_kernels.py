@@ -18,11 +18,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 MiB = 1 << 20
 
 
-@pytest.fixture(scope="module")
-def emu():
+@pytest.fixture(scope="module", params=["warp", "cta"])
+def emu(request):
+    """warp = the throughput kernels (one warp per block), cta = the one-CTA-per-block variants."""
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
     L = C.CDLL(os.path.join(HERE, "emu", "libcryoemu.so"))
-    for f in (L.emu_lz4_decode, L.emu_zstd_decode):
+    warp = request.param == "warp"
+    for f in (L.emu_lz4_decode, L.emu_zstd_decode, L.emu_lz4w_decode, L.emu_zstdw_decode):
         f.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint, C.POINTER(C.c_uint32)]
         f.restype = C.c_int
 
@@ -30,7 +32,10 @@ def emu():
         s = np.ascontiguousarray(stream, dtype=np.uint8)
         out = np.zeros(cap, dtype=np.uint8)
         sz = C.c_uint32(0)
-        fn = L.emu_lz4_decode if method == 0 else L.emu_zstd_decode
+        if warp:
+            fn = L.emu_lz4w_decode if method == 0 else L.emu_zstdw_decode
+        else:
+            fn = L.emu_lz4_decode if method == 0 else L.emu_zstd_decode
         st = fn(s.ctypes.data if s.size else None, s.size, out.ctypes.data, cap, shift, C.byref(sz))
         return st, sz.value, out
     return run
