@@ -54,13 +54,22 @@
 #error "ring + windows must fit the 4 KB they share with the Huffman table"
 #endif
 
-/* code -> baseline | extra bits << 24 (RFC 8878 3.1.1.3.2.1.1) */
-CRYO_CONST uint32_t ZS_LL_PACK[36] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15,
+/* code -> baseline | extra bits << 24 (RFC 8878 3.1.1.3.2.1.1).  Looked up with a different
+ * index per lane, so they live in global memory (read-only cache), not in the constant bank
+ * where divergent indices serialise. */
+#ifdef CRYO_EMU
+#define CRYO_GTABLE static const
+#define CRYO_GLD(x) (x)
+#else
+#define CRYO_GTABLE __device__ const
+#define CRYO_GLD(x) __ldg(&(x))
+#endif
+CRYO_GTABLE uint32_t ZS_LL_PACK[36] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15,
     16 | (1u << 24), 18 | (1u << 24), 20 | (1u << 24), 22 | (1u << 24), 24 | (2u << 24), 28 | (2u << 24),
     32 | (3u << 24), 40 | (3u << 24), 48 | (4u << 24), 64 | (6u << 24), 128 | (7u << 24), 256 | (8u << 24),
     512 | (9u << 24), 1024 | (10u << 24), 2048 | (11u << 24), 4096 | (12u << 24), 8192 | (13u << 24),
     16384 | (14u << 24), 32768 | (15u << 24), 65536 | (16u << 24)};
-CRYO_CONST uint32_t ZS_ML_PACK[53] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20,
+CRYO_GTABLE uint32_t ZS_ML_PACK[53] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20,
     21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35 | (1u << 24), 37 | (1u << 24),
     39 | (1u << 24), 41 | (1u << 24), 43 | (2u << 24), 47 | (2u << 24), 51 | (3u << 24), 59 | (3u << 24),
     67 | (4u << 24), 83 | (4u << 24), 99 | (5u << 24), 131 | (7u << 24), 259 | (8u << 24), 515 | (9u << 24),
@@ -219,6 +228,8 @@ CRYO_DEV uint32_t zsw_seq_table(ZswState &z, int mode, int t, const uint8_t *p, 
         left = z.tlen[t];
         repeat = true;
     }
+    uint32_t ret;
+
     switch (mode)
     {
         case 0:
@@ -229,8 +240,8 @@ CRYO_DEV uint32_t zsw_seq_table(ZswState &z, int mode, int t, const uint8_t *p, 
                 cell[i] = predef[o + i];
             logv = t == 1 ? 5 : 6;
             z.tmode[t] = 0;
-            __syncwarp();
-            return 0;
+            ret = 0;
+            break;
         }
         case 1:
             if (left < 1 || p[0] > max_sym)
@@ -241,8 +252,8 @@ CRYO_DEV uint32_t zsw_seq_table(ZswState &z, int mode, int t, const uint8_t *p, 
             z.tmode[t] = 1;
             z.tdesc[t] = p;
             z.tlen[t] = 1;
-            __syncwarp();
-            return repeat ? 0u : 1u;
+            ret = repeat ? 0u : 1u;
+            break;
         default:
         {
             int32_t  nsym = 0, log = 0;
@@ -261,9 +272,22 @@ CRYO_DEV uint32_t zsw_seq_table(ZswState &z, int mode, int t, const uint8_t *p, 
             z.tmode[t] = 2;
             z.tdesc[t] = p;
             z.tlen[t] = used;
-            return repeat ? 0u : used;
+            ret = repeat ? 0u : used;
+            break;
         }
     }
+    /* the number of extra bits of every cell's code goes into bits 26..30 (base < 2^9 leaves
+     * them free), so the sequence walk needs one lookup per table and state */
+    __syncwarp();
+    for (uint32_t i = lane; i < (1u << logv); i += 32)
+    {
+        const uint32_t c = cell[i], sym = c & 0xFFu;
+        const uint32_t xb = t == 1 ? sym : (t == 0 ? CRYO_GLD(ZS_LL_PACK[sym]) : CRYO_GLD(ZS_ML_PACK[sym])) >> 24;
+
+        cell[i] = (c & 0x03FFFFFFu) | (xb << 26);
+    }
+    __syncwarp();
+    return ret;
 }
 
 /*
@@ -474,37 +498,54 @@ CRYO_DEV uint32_t zsw_huf_build(const uint8_t *src, uint32_t n, uint16_t *huf, u
 CRYO_DEV bool zsw_huf_stream(const uint16_t *huf, int log, const uint8_t *src, uint32_t n,
                              uint8_t *dst, uint32_t count)
 {
-    BitsBack bb;
-
-    if (!bb_init(bb, src, n))
+    if (n == 0)
         return false;
-    uint32_t hi = (uint32_t) (bb.acc >> 32), lo = (uint32_t) bb.acc;
-    int32_t  avail = bb.avail;
-    uintptr_t cur = bb.cur;
-    uint32_t nextw = bb.nextw;
-    const uintptr_t start = bb.start;
+    /* words of the stream, addressed from the aligned word that holds its first byte; the
+     * bytes in front of the stream inside that word are never consumed by a valid stream and
+     * a corrupt one fails the final bit count */
+    const uint32_t head = (uint32_t) ((uintptr_t) src & 3u);
+    const uint32_t *wb = reinterpret_cast<const uint32_t *>(src - head);
+    const uint32_t nbytes = head + n;
+    int32_t  wi = (int32_t) ((nbytes - 1u) >> 2);           /* word of the last byte */
+    uint32_t w = wb[wi];
+    const uint32_t keep = nbytes - 4u * (uint32_t) wi;       /* 1..4 valid low bytes */
+
+    if (keep < 4)
+        w &= (1u << (8u * keep)) - 1u;
+    if (wi == 0 && head)
+        w &= ~0u << (8u * head);
+    if ((w >> (8u * (keep - 1u))) == 0)
+        return false;                                       /* no end mark in the last byte */
+    const int hb = zs_highbit(w);
+    /* accumulator (hi:lo), next bit at bit 31 of hi; `avail` valid bits */
+    uint32_t hi = hb ? w << (32 - hb) : 0u, lo = 0u;
+    int32_t  avail = hb;
+    /* bits of the stream not yet in the accumulator */
+    int32_t  below = (int32_t) (8u * (4u * (uint32_t) wi - head));
+    const int32_t total = below + hb;                       /* stream bits under the end mark */
+    int32_t  used = 0;
+    uint32_t nextw;
+
+    wi--;
+    nextw = wi >= 0 ? wb[wi] : 0u;
     const uint32_t sh = 32u - (uint32_t) log;
     uint32_t i = 0;
 
+#ifdef CRYO_EMU
+#define ZSW_SHR_C(x, s) ((s) >= 32 ? 0u : (x) >> (s))
+#define ZSW_SHL_C(x, s) ((s) >= 32 ? 0u : (x) << (s))
+#else
+#define ZSW_SHR_C(x, s) __funnelshift_rc((x), 0u, (uint32_t) (s))
+#define ZSW_SHL_C(x, s) __funnelshift_lc(0u, (x), (uint32_t) (s))
+#endif
 #define ZSW_HREFILL()                                                        \
     if (avail <= 32)                                                         \
     {                                                                        \
-        /* acc |= nextw << (32 - avail) in 64 bits */                        \
-        if (avail == 32)                                                     \
-            lo = nextw;                                                      \
-        else                                                                 \
-        {                                                                    \
-            hi |= nextw >> avail;                                            \
-            lo = nextw << (32 - avail);                                      \
-        }                                                                    \
-        if (avail == 0)                                                      \
-        {                                                                    \
-            hi = nextw;                                                      \
-            lo = 0;                                                          \
-        }                                                                    \
+        hi |= ZSW_SHR_C(nextw, avail);                                       \
+        lo = ZSW_SHL_C(nextw, 32 - avail);                                   \
         avail += 32;                                                         \
-        cur -= 4;                                                            \
-        nextw = bb_load(cur, start);                                         \
+        wi--;                                                                \
+        nextw = wi >= 0 ? wb[wi] : 0u;                                       \
     }
 #define ZSW_HDEC(sym)                                                        \
     {                                                                        \
@@ -514,6 +555,7 @@ CRYO_DEV bool zsw_huf_stream(const uint16_t *huf, int log, const uint8_t *src, u
         hi = __funnelshift_l(lo, hi, nb);                                    \
         lo <<= nb;                                                           \
         avail -= (int32_t) nb;                                               \
+        used += (int32_t) nb;                                                \
     }
     /* head: until dst + i is 4-byte aligned */
     while (i < count && ((uintptr_t) (dst + i) & 3u))
@@ -524,18 +566,23 @@ CRYO_DEV bool zsw_huf_stream(const uint16_t *huf, int log, const uint8_t *src, u
         ZSW_HDEC(s);
         dst[i++] = (uint8_t) s;
     }
-    while (i + 4 <= count)
     {
-        uint32_t s0, s1, s2, s3;
+        uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + i);
+        const uint32_t quads = (count - i) >> 2;
 
-        ZSW_HREFILL();
-        ZSW_HDEC(s0);
-        ZSW_HDEC(s1);
-        ZSW_HREFILL();
-        ZSW_HDEC(s2);
-        ZSW_HDEC(s3);
-        *reinterpret_cast<uint32_t *>(dst + i) = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
-        i += 4;
+        for (uint32_t q = 0; q < quads; q++)
+        {
+            uint32_t s0, s1, s2, s3;
+
+            ZSW_HREFILL();
+            ZSW_HDEC(s0);
+            ZSW_HDEC(s1);
+            ZSW_HREFILL();
+            ZSW_HDEC(s2);
+            ZSW_HDEC(s3);
+            d4[q] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+        }
+        i += quads << 2;
     }
     while (i < count)
     {
@@ -547,9 +594,11 @@ CRYO_DEV bool zsw_huf_stream(const uint16_t *huf, int log, const uint8_t *src, u
     }
 #undef ZSW_HREFILL
 #undef ZSW_HDEC
-    /* every bit consumed exactly: bits still in the accumulator plus the bytes not loaded yet
-     * (negative when the reader ran past the start of the stream) */
-    return (int64_t) avail + 8 * ((int64_t) (cur + 4) - (int64_t) start) == 0;
+#undef ZSW_SHR_C
+#undef ZSW_SHL_C
+    (void) below;
+    /* every bit under the end mark consumed, no more, no less */
+    return used == total;
 }
 
 /* Huffman literals of one block -> dst (global).  The table lives in the idle ring region. */
@@ -1149,129 +1198,149 @@ CRYO_DEV void zstdw_decode_frame(const uint8_t *src, uint32_t csize, uint8_t *ou
                     uint32_t rep0 = z.rep0, rep1 = z.rep1, rep2 = z.rep2;
                     uint32_t lpos = 0;                  /* literals consumed (mirrors L.pos) */
 
-                    for (uint32_t i = 0; i < nseq; i++)
+                    /*
+                     * 32 sequences at a time.  Pass 1 (warp-uniform, serial): walk the three FSE
+                     * states; only the state bits are read here, lane k keeps the cells and the
+                     * bit position of sequence k.  Pass 2 (one sequence per lane): every lane
+                     * extracts its own offset / match-length / literal-length extra bits.  Then
+                     * the 32 sequences are executed in order (repeat offsets, checks, copies).
+                     */
+                    for (uint32_t done = 0; done < nseq && err == ST_OK; done += 32)
                     {
-                        /* keep the three words of a peek inside the window */
-                        if (B.wlo != 0 && B.bitpos < B.wlo * 8u + 160u)
-                            zsw_bits_fill(B, lane);
-                        const uint32_t cl = ll_tab[sl], co = of_tab[so], cm = ml_tab[sm];
-                        const uint32_t pl = ZS_LL_PACK[cl & 0xFFu], pm = ZS_ML_PACK[cm & 0xFFu];
-                        const uint32_t ofb = co & 0xFFu, mlb = pm >> 24, llb = pl >> 24;
-                        const bool     more = i + 1 < nseq;
-                        const uint32_t nbl = more ? (cl >> 8) & 0xFFu : 0u, nbm = more ? (cm >> 8) & 0xFFu : 0u,
-                                       nbo = more ? (co >> 8) & 0xFFu : 0u;
-                        uint32_t T = ofb + mlb + llb + nbl + nbm + nbo;
-                        uint32_t hi, lo, c = 0, ov;
+                        const uint32_t g = nseq - done < 32u ? nseq - done : 32u;
+                        uint32_t my_cl = 0, my_co = 0, my_cm = 0, my_bp = 0;
+                        int32_t  under = 0;
 
-                        if (B.bitpos - B.lowbit < T)
+                        /* 32 sequences take at most 32 x 89 bits; keep them and a peek inside the window */
+                        if (B.wlo != 0 && B.bitpos < B.wlo * 8u + 3200u)
+                            zsw_bits_fill(B, lane);
+                        const int32_t wbits = (int32_t) (B.wlo * 8u);
+
+                        for (uint32_t k = 0; k < g; k++)
                         {
-                            err = ST_INPUT;
+                            const uint32_t cl = ll_tab[sl], co = of_tab[so], cm = ml_tab[sm];
+                            const uint32_t text = (cl >> 26) + (co >> 26) + (cm >> 26);
+
+                            if (lane == k)
+                            {
+                                my_cl = cl;
+                                my_co = co;
+                                my_cm = cm;
+                                my_bp = B.bitpos;
+                            }
+                            if (done + k + 1 < nseq)
+                            {
+                                const uint32_t nbl = (cl >> 8) & 0xFFu, nbm = (cm >> 8) & 0xFFu,
+                                               nbo = (co >> 8) & 0xFFu;
+                                const uint32_t p = B.bitpos - text;         /* state bits end here */
+                                const int32_t  rel = (int32_t) p - 32 - wbits;
+                                const int32_t  wi = rel >> 5;
+                                uint32_t top = __funnelshift_r(B.w32[wi], B.w32[wi + 1], (uint32_t) rel & 31u);
+
+                                sl = ((cl >> 16) & 0x3FFu) + __funnelshift_l(top, 0u, nbl);
+                                top <<= nbl;
+                                sm = ((cm >> 16) & 0x3FFu) + __funnelshift_l(top, 0u, nbm);
+                                top <<= nbm;
+                                so = ((co >> 16) & 0x3FFu) + __funnelshift_l(top, 0u, nbo);
+                                B.bitpos = p - (nbl + nbm + nbo);
+                            }
+                            else
+                                B.bitpos -= text;
+                            under |= (int32_t) (B.bitpos - B.lowbit);
+                        }
+                        if (under < 0)
+                        {
+                            err = ST_INPUT;         /* the stream ended inside a sequence */
                             break;
                         }
-                        zsw_bits_peek(B, hi, lo);
-                        ov = (1u << ofb) + zsw_bits_get(hi, lo, 0, ofb);
-                        if (T > 64u)
+                        /* pass 2: lane k = sequence done + k */
+                        uint32_t my_ov = 0, my_ml = 0, my_ll = 0;
+
+                        if (lane < g)
                         {
-                            /* a long offset code next to long length codes: take the offset
-                             * bits alone, then a fresh window for the rest (<= 58 bits) */
-                            B.bitpos -= ofb;
-                            T -= ofb;
-                            if (B.wlo != 0 && B.bitpos < B.wlo * 8u + 160u)
-                                zsw_bits_fill(B, lane);
-                            zsw_bits_peek(B, hi, lo);
+                            const uint32_t xo = my_co >> 26, xm = my_cm >> 26, xl = my_cl >> 26;
+                            const int32_t  rel = (int32_t) my_bp - 64 - wbits;
+                            const int32_t  wi = rel >> 5;
+                            const uint32_t sh = (uint32_t) rel & 31u;
+                            const uint32_t w0 = B.w32[wi], w1 = B.w32[wi + 1], w2 = B.w32[wi + 2];
+                            const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+
+                            my_ov = (1u << xo) + zsw_bits_get(hi, lo, 0, xo);
+                            my_ml = (CRYO_GLD(ZS_ML_PACK[my_cm & 0xFFu]) & 0xFFFFFFu) + zsw_bits_get(hi, lo, xo, xm);
+                            my_ll = (CRYO_GLD(ZS_LL_PACK[my_cl & 0xFFu]) & 0xFFFFFFu) + zsw_bits_get(hi, lo, xo + xm, xl);
                         }
-                        else
-                            c = ofb;
-                        const uint32_t ml = (pm & 0xFFFFFFu) + zsw_bits_get(hi, lo, c, mlb);
-
-                        c += mlb;
-                        const uint32_t ll = (pl & 0xFFFFFFu) + zsw_bits_get(hi, lo, c, llb);
-
-                        c += llb;
-                        sl = (cl >> 16) + zsw_bits_get(hi, lo, c, nbl);
-                        c += nbl;
-                        sm = (cm >> 16) + zsw_bits_get(hi, lo, c, nbm);
-                        c += nbm;
-                        so = (co >> 16) + zsw_bits_get(hi, lo, c, nbo);
-                        B.bitpos -= T;
-
-                        uint32_t off;
-
-                        if (ov > 3)
+                        /* execution, in order */
+                        for (uint32_t k = 0; k < g; k++)
                         {
-                            off = ov - 3;
-                            rep2 = rep1;
-                            rep1 = rep0;
-                            rep0 = off;
-                        }
-                        else
-                        {
-                            const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+                            const uint32_t ov = __shfl_sync(CRYO_FULL, my_ov, (int) k);
+                            const uint32_t ml = __shfl_sync(CRYO_FULL, my_ml, (int) k);
+                            const uint32_t ll = __shfl_sync(CRYO_FULL, my_ll, (int) k);
+                            uint32_t off;
 
-                            if (idx == 0)
-                                off = rep0;
-                            else
+                            if (ov > 3)
                             {
-                                off = idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
-                                if (idx > 1)
-                                    rep2 = rep1;
+                                off = ov - 3;
+                                rep2 = rep1;
                                 rep1 = rep0;
                                 rep0 = off;
                             }
-                        }
-                        if (ll > regen - lpos)
-                        {
-                            err = ST_FORMAT;
-                            break;
-                        }
-                        if ((uint64_t) o.pos + ll + ml > cap)
-                        {
-                            err = ST_OUTPUT;
-                            break;
-                        }
-                        if (o.pos + ll + ml - block_start > block_max)
-                        {
-                            err = ST_FORMAT;
-                            break;
-                        }
-                        const uint32_t mpos = o.pos + ll;
-
-                        if (off == 0 || off > mpos - frame_start)
-                        {
-                            err = ST_OFFSET;
-                            break;
-                        }
-                        /*
-                         * Fast path: a short literal run served from the literal window and a
-                         * short non-overlapping match whose source is in the ring: one
-                         * predicated shared-memory move each.
-                         */
-                        const uint32_t lip = L.delta + lpos;
-
-                        if (ll <= 32u && ml <= 32u && !L.rle && off >= ml && off <= WX_RING - 64u &&
-                            mpos - off >= o.lo)
-                        {
-                            if (ll)
+                            else
                             {
-                                if (!L.wvalid || lip + ll > L.wbase + ZSW_LITWIN || lip < L.wbase)
-                                    zsw_lits_fill(L, lip, lane);
-                                if (lane < ll)
-                                    o.ring[(o.pos + lane) & WX_RMASK] = L.win[lip - L.wbase + lane];
-                                __syncwarp();
+                                const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+
+                                if (idx == 0)
+                                    off = rep0;
+                                else
+                                {
+                                    off = idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
+                                    if (idx > 1)
+                                        rep2 = rep1;
+                                    rep1 = rep0;
+                                    rep0 = off;
+                                }
                             }
-                            if (lane < ml)
-                                o.ring[(mpos + lane) & WX_RMASK] = o.ring[(mpos - off + lane) & WX_RMASK];
-                            o.pos = mpos + ml;
+                            const uint32_t mpos = o.pos + ll, epos = mpos + ml;     /* < 2^28: no wrap */
+
+                            if ((ll > regen - lpos) | (epos > cap) | (epos - block_start > block_max) |
+                                (off - 1u >= mpos - frame_start))
+                            {
+                                err = ll > regen - lpos ? ST_FORMAT
+                                      : epos > cap ? ST_OUTPUT
+                                      : epos - block_start > block_max ? ST_FORMAT : ST_OFFSET;
+                                break;
+                            }
+                            /*
+                             * Fast path: a short literal run served from the literal window and a
+                             * short non-overlapping match whose source is in the ring: one
+                             * predicated shared-memory move each.
+                             */
+                            const uint32_t lip = L.delta + lpos;
+
+                            if (ll <= 32u && ml <= 32u && !L.rle && off >= ml && off <= WX_RING - 64u &&
+                                mpos - off >= o.lo)
+                            {
+                                if (ll)
+                                {
+                                    if (!L.wvalid || lip + ll > L.wbase + ZSW_LITWIN || lip < L.wbase)
+                                        zsw_lits_fill(L, lip, lane);
+                                    if (lane < ll)
+                                        o.ring[(o.pos + lane) & WX_RMASK] = L.win[lip - L.wbase + lane];
+                                    __syncwarp();
+                                }
+                                if (lane < ml)
+                                    o.ring[(mpos + lane) & WX_RMASK] = o.ring[(mpos - off + lane) & WX_RMASK];
+                                o.pos = epos;
+                                lpos += ll;
+                                __syncwarp();
+                                if (o.pos - o.flushed >= WX_DRAIN)
+                                    wx_drain(o, lane);
+                                continue;
+                            }
+                            L.pos = lpos;
+                            zsw_lits_emit(o, L, ll, lane);
                             lpos += ll;
-                            __syncwarp();
-                            if (o.pos - o.flushed >= WX_DRAIN)
-                                wx_drain(o, lane);
-                            continue;
+                            wx_match(o, off, ml, lane);
                         }
-                        L.pos = lpos;
-                        zsw_lits_emit(o, L, ll, lane);
-                        lpos += ll;
-                        wx_match(o, off, ml, lane);
                     }
                     z.rep0 = rep0;
                     z.rep1 = rep1;
