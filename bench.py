@@ -58,7 +58,7 @@ def recorded_traffic():
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("k_zstd_decode_dram_bytes_per_launch")
+            return json.load(open(p)).get("k_zstd_decode_w_dram_bytes_per_launch")
         except Exception:
             return None
     return None
@@ -190,7 +190,7 @@ def main():
     import torch.distributed as dist
 
     import benchdata
-    from pg_cryogen_b200 import CryoGPU, blockgen as bg
+    from pg_cryogen_b200 import CryoGPU, blockgen as bg, shard
     from pg_cryogen_b200.codec import pack_chunks
 
     if not torch.cuda.is_available():
@@ -205,9 +205,11 @@ def main():
     host_threads = max(1, (os.cpu_count() or 8) // max(world, 1))
     chunks, plain = benchdata.build_table(args.rows, KIND, PAYLOAD, METHOD, LEVEL,
                                           threads=min(host_threads, 16),
-                                          block_seed_offset=rank * nblk)
+                                          block_seed_offset=shard.rank_block_seed_offset(rank, nblk))
     buf, offs, sizes = pack_chunks(chunks)
     csize_total = int(sizes.astype(np.int64).sum())
+    # host threads of the library's result placement (sparse return): this rank's share of cores
+    os.environ.setdefault("CRYOGPU_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 8) // max(world, 1)))))
     gpu = CryoGPU(local_rank)
     d_src = torch.from_numpy(buf).to(dev)
     d_off = torch.from_numpy(offs.view(np.int64)).to(dev)
@@ -247,14 +249,11 @@ def main():
     clocks = sampler.stop()
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = shard.max_over_ranks(total_ms, dev)          # slowest rank, on-device events
     ms_per_step = total_ms / args.steps
-    value = world * nblk * CRYO_BLCKSZ / (ms_per_step * 1e-3) / 1e9
+    value = shard.whole_job_rate(nblk * CRYO_BLCKSZ, world, ms_per_step * 1e-3) / 1e9
 
-    # ---- roofline of the dominant kernel (k_zstd_decode): the step is that one launch plus
+    # ---- roofline of the dominant kernel (k_zstd_decode_w): the step is that one launch plus
     #      two launches that exit immediately, so the event-timed step is the launch time ----
     peak, peak_src = measured_peak()
     kern_ms = statistics.mean(step_ms)
@@ -262,7 +261,7 @@ def main():
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": recorded_traffic(), "peak_source": peak_src,
-                "frac_of_nominal_8TBps": achieved / 8000.0, "kernel": "k_zstd_decode",
+                "frac_of_nominal_8TBps": achieved / 8000.0, "kernel": "k_zstd_decode_w",
                 "algorithmic_bytes_per_launch": alg_bytes}
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
@@ -301,13 +300,14 @@ def main():
             host_step()
         torch.cuda.synchronize(dev)
         t_e2e = (time.perf_counter() - t0) / e2e_steps
-        if world > 1:
-            t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_e2e = float(t.item())
-        e2e = {"value": world * nblk * CRYO_BLCKSZ / t_e2e / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": in_bytes + nblk * 16, "d2h_bytes_per_step": nblk * (CRYO_BLCKSZ + 8),
-               "steps": e2e_steps, "api": "cryogpu_decompress_host, pinned host buffers"}
+        t_e2e = shard.max_over_ranks(t_e2e, dev)
+        bi, bo = gpu.last_transfer_bytes()              # counted by the library from what it copied
+        e2e = {"value": shard.whole_job_rate(nblk * CRYO_BLCKSZ, world, t_e2e) / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
+               "steps": e2e_steps,
+               "api": "cryogpu_decompress_host, pinned host buffers; only the non-zero 4 KiB pages of "
+                      "each decoded block cross the bus, the library zero-fills the rest of the "
+                      "caller's block with %s host threads" % os.environ["CRYOGPU_HOST_THREADS"]}
         lib.cryogpu_host_free(h_in)
         lib.cryogpu_host_free(h_out)
 

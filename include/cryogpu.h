@@ -138,6 +138,15 @@ int cryogpu_compress_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_a
                           uint32_t *dst_size, int32_t *status);
 
 /*
+ * Bytes the last cryogpu_decompress_host call on this context moved over the bus.  The call
+ * returns only the 4 KiB pages of a decoded block that hold a non-zero byte and zero-fills the
+ * rest of the caller's block on the host (a cryo block of narrow rows is ~98 % zeros,
+ * storage.c:18); CRYOGPU_SPARSE_D2H=0 restores the plain copy, CRYOGPU_HOST_THREADS sets the
+ * number of host threads that place the pages (default: min(cores, 16)).
+ */
+void cryogpu_last_transfer_bytes(const cryogpu_ctx *ctx, uint64_t *h2d, uint64_t *d2h);
+
+/*
  * Multi-GPU host variants: the batch is split into contiguous block ranges, one
  * per context (one host thread + stream per GPU, no collective).
  */

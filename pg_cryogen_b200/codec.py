@@ -47,6 +47,7 @@ _PROTOS = {
     "cryogpu_compress_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
                                           C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64,
                                           C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cryogpu_last_transfer_bytes": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "cryogpu_decompress_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                           C.c_void_p]),
@@ -118,6 +119,12 @@ class CryoGPU:
             raise CryoGPUError(f"cryogpu_init({device}) = {rc}: {self.lib.cryogpu_last_error().decode()}")
         self.handle = h
         self.device = device
+
+    def last_transfer_bytes(self) -> tuple[int, int]:
+        """(host->device, device->host) bytes of the last decompress_host call."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.lib.cryogpu_last_transfer_bytes(self.handle, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
 
     def close(self):
         if getattr(self, "handle", None):

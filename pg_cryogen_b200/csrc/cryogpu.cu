@@ -17,7 +17,15 @@
 
 #include <cuda_runtime.h>
 
+#if defined(__x86_64__) || defined(_M_X64)
+#include <emmintrin.h>
+#define CRYO_HAVE_SSE2 1
+#endif
+
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -153,6 +161,88 @@ k_zstd_encode(const uint8_t *src, uint64_t src_stride, uint32_t block_size, uint
                           dst_size + b, status + b, scratch + blockIdx.x * scratch_stride);
 }
 
+
+/*
+ * Sparse return for the host-pointer decompress call: a 1 MiB cryo block of narrow rows is
+ * ~98 % zeros, and shipping zeros over PCIe is what bounds the host call.
+ * One CTA per block marks which 4 KiB pages of the decoded block hold a non-zero byte and
+ * packs those pages into a staging buffer; the host copies only them and zero-fills the rest
+ * of the caller's block itself.  The chunk was just written, so this scan reads L2.
+ */
+#define SP_PAGE      4096u
+#define SP_MAXPAGES  2048u          /* blocks up to 8 MiB */
+#define SP_WORDS     (SP_MAXPAGES / 32u)
+
+__global__ void __launch_bounds__(256)
+k_page_compact(const uint8_t *out, uint64_t stride, uint32_t block_size, uint32_t *bitmap,
+               uint32_t *page_off, uint32_t *counter, uint8_t *staging)
+{
+    __shared__ uint32_t flags[SP_WORDS];
+    __shared__ uint32_t base_sh;
+    const uint32_t b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint8_t *blk = out + b * stride;
+    const uint32_t pages = (block_size + SP_PAGE - 1) / SP_PAGE, words = (pages + 31) / 32;
+
+    for (uint32_t i = tid; i < SP_WORDS; i += 256)
+        flags[i] = 0;
+    __syncthreads();
+    for (uint32_t p = warp; p < pages; p += 8)
+    {
+        const uint32_t len = block_size - p * SP_PAGE < SP_PAGE ? block_size - p * SP_PAGE : SP_PAGE;
+        bool nz = (len & 15u) != 0;         /* a ragged tail page is always shipped */
+
+        if (!nz)
+        {
+            const uint4 *q = reinterpret_cast<const uint4 *>(blk + (size_t) p * SP_PAGE);
+            uint32_t acc = 0;
+
+            for (uint32_t v = lane; v < len / 16; v += 32)
+            {
+                uint4 x = q[v];
+
+                acc |= x.x | x.y | x.z | x.w;
+            }
+            nz = __any_sync(0xffffffffu, acc != 0);
+        }
+        if (nz && lane == 0)
+            atomicOr(&flags[p >> 5], 1u << (p & 31));
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        uint32_t c = 0;
+
+        for (uint32_t w = 0; w < words; w++)
+            c += (uint32_t) __popc(flags[w]);
+        base_sh = atomicAdd(counter, c);
+        page_off[b] = base_sh;
+    }
+    for (uint32_t w = tid; w < SP_WORDS; w += 256)
+        bitmap[b * SP_WORDS + w] = w < words ? flags[w] : 0u;
+    __syncthreads();
+    const uint32_t base = base_sh;
+
+    for (uint32_t p = warp; p < pages; p += 8)
+    {
+        if (!(flags[p >> 5] & (1u << (p & 31))))
+            continue;
+        uint32_t rank = (uint32_t) __popc(flags[p >> 5] & ((1u << (p & 31)) - 1u));
+
+        for (uint32_t w = 0; w < (p >> 5); w++)
+            rank += (uint32_t) __popc(flags[w]);
+        const uint32_t len = block_size - p * SP_PAGE < SP_PAGE ? block_size - p * SP_PAGE : SP_PAGE;
+        const uint8_t *src = blk + (size_t) p * SP_PAGE;
+        uint8_t *dst = staging + (size_t) (base + rank) * SP_PAGE;
+
+        if ((len & 15u) == 0)
+            for (uint32_t v = lane; v < len / 16; v += 32)
+                reinterpret_cast<uint4 *>(dst)[v] = reinterpret_cast<const uint4 *>(src)[v];
+        else
+            for (uint32_t i = lane; i < len; i += 32)
+                dst[i] = src[i];
+    }
+}
+
 /* which LZ4 decode kernel: CRYOGPU_LZ4_KERNEL=cta selects the one-CTA-per-block variant */
 static bool
 lz4_use_cta_kernel()
@@ -212,6 +302,90 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             ZSTDD_SCRATCH_BYTES, predef, (uint32_t) n);
 }
 
+
+/* ------------------------------------------------------- host worker pool */
+
+/* A few host threads that place sparse results into the caller's blocks (copy the non-zero
+ * pages, zero-fill the rest).  This is data placement for the host-pointer API, not a codec. */
+struct HostPool
+{
+    std::vector<std::thread> th;
+    std::mutex              m;
+    std::condition_variable cv, done;
+    std::function<void(size_t)> job;
+    std::atomic<size_t>     next{0};
+    size_t                  total = 0, active = 0;
+    uint64_t                gen = 0;
+    bool                    stop = false;
+
+    void start(int n)
+    {
+        for (int i = 0; i < n; i++)
+            th.emplace_back([this]() {
+                uint64_t seen = 0;
+
+                for (;;)
+                {
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+
+                        cv.wait(lk, [&]() { return stop || gen != seen; });
+                        if (stop)
+                            return;
+                        seen = gen;
+                    }
+                    work();
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+
+                        if (--active == 0)
+                            done.notify_all();
+                    }
+                }
+            });
+    }
+    void work()
+    {
+        for (;;)
+        {
+            size_t i = next.fetch_add(1);
+
+            if (i >= total)
+                return;
+            job(i);
+        }
+    }
+    /* run f(0..items-1) on the pool and the calling thread; returns when all are done */
+    void run(size_t items, std::function<void(size_t)> f)
+    {
+        {
+            std::lock_guard<std::mutex> lk(m);
+
+            job = std::move(f);
+            total = items;
+            next = 0;
+            active = th.size();
+            gen++;
+        }
+        cv.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m);
+
+        done.wait(lk, [&]() { return active == 0; });
+    }
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m);
+
+            stop = true;
+        }
+        cv.notify_all();
+        for (auto &t : th)
+            t.join();
+    }
+};
+
 /* ----------------------------------------------------------------- context */
 
 struct DevBuf
@@ -234,6 +408,12 @@ struct cryogpu_ctx
     std::mutex   mu;
     bool         attrs_set = false;
     int          sm_count = 148;
+    /* sparse return of the host decompress call */
+    DevBuf       d_stage[2], d_sp[2];   /* packed non-zero pages; bitmap + page_off + counter */
+    DevBuf       h_stage[2], h_sp[2];
+    HostPool    *pool = nullptr;
+    int          sparse = -1;           /* -1 unset, 0 off, 1 on (CRYOGPU_SPARSE_D2H) */
+    uint64_t     last_h2d = 0, last_d2h = 0;
 };
 
 static int
@@ -388,10 +568,15 @@ cryogpu_shutdown(cryogpu_ctx *ctx)
         cudaFreeHost(ctx->h_in[i].p);
         cudaFreeHost(ctx->h_meta[i].p);
         cudaFreeHost(ctx->h_out[i].p);
+        cudaFree(ctx->d_stage[i].p);
+        cudaFree(ctx->d_sp[i].p);
+        cudaFreeHost(ctx->h_stage[i].p);
+        cudaFreeHost(ctx->h_sp[i].p);
         cudaEventDestroy(ctx->ev[i]);
     }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream2);
+    delete ctx->pool;
     delete ctx;
 }
 
@@ -399,6 +584,15 @@ extern "C" int
 cryogpu_device(const cryogpu_ctx *ctx)
 {
     return ctx ? ctx->device : -1;
+}
+
+extern "C" void
+cryogpu_last_transfer_bytes(const cryogpu_ctx *ctx, uint64_t *h2d, uint64_t *d2h)
+{
+    if (h2d)
+        *h2d = ctx ? ctx->last_h2d : 0;
+    if (d2h)
+        *d2h = ctx ? ctx->last_d2h : 0;
 }
 
 extern "C" uint64_t
@@ -518,11 +712,11 @@ cryogpu_compress_device(cryogpu_ctx *ctx, size_t n, int method, int level_or_acc
 
 /* -------------------------------------------------------------- host API */
 
-/* blocks per pipeline chunk: bounds device/pinned staging to ~64 MiB per lane */
+/* blocks per pipeline chunk: bounds device/pinned staging to ~128 MiB per lane */
 static size_t
 chunk_blocks(uint32_t block_size)
 {
-    size_t c = (64u << 20) / block_size;
+    size_t c = (128u << 20) / block_size;
 
     return c < 1 ? 1 : c;
 }
@@ -538,6 +732,87 @@ is_pinned(const void *p)
         return false;
     }
     return a.type == cudaMemoryTypeHost;
+}
+
+static bool
+sparse_enabled(cryogpu_ctx *ctx)
+{
+    if (ctx->sparse < 0)
+    {
+        const char *e = getenv("CRYOGPU_SPARSE_D2H");
+
+        ctx->sparse = (e && strcmp(e, "0") == 0) ? 0 : 1;
+    }
+    return ctx->sparse == 1;
+}
+
+static HostPool *
+host_pool(cryogpu_ctx *ctx)
+{
+    if (!ctx->pool)
+    {
+        const char *e = getenv("CRYOGPU_HOST_THREADS");
+        int         n = e ? atoi(e) : (int) std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+
+        ctx->pool = new HostPool();
+        ctx->pool->start(n > 1 ? n - 1 : 0);        /* the calling thread works too */
+    }
+    return ctx->pool;
+}
+
+/* zero-fill with non-temporal stores: the run is far larger than any cache and is not read
+ * back by this thread, so write-combining avoids the read-for-ownership of every line */
+static void
+zero_fill(uint8_t *p, size_t n)
+{
+#ifdef CRYO_HAVE_SSE2
+    if (n >= 4096 && ((uintptr_t) p & 15u) == 0)
+    {
+        const __m128i z = _mm_setzero_si128();
+        size_t        i = 0;
+
+        for (; i + 64 <= n; i += 64)
+        {
+            _mm_stream_si128((__m128i *) (p + i), z);
+            _mm_stream_si128((__m128i *) (p + i + 16), z);
+            _mm_stream_si128((__m128i *) (p + i + 32), z);
+            _mm_stream_si128((__m128i *) (p + i + 48), z);
+        }
+        _mm_sfence();
+        if (i < n)
+            memset(p + i, 0, n - i);
+        return;
+    }
+#endif
+    memset(p, 0, n);
+}
+
+/* place one sparse block: non-zero pages from the packed staging buffer, zeros elsewhere */
+static void
+place_sparse_block(uint8_t *dst, uint32_t block_size, const uint32_t *bits, const uint8_t *pages)
+{
+    const uint32_t npages = (block_size + SP_PAGE - 1) / SP_PAGE;
+    uint32_t       p = 0;
+
+    while (p < npages)
+    {
+        uint32_t q = p;
+        const bool nz = (bits[p >> 5] >> (p & 31)) & 1u;
+
+        while (q < npages && (((bits[q >> 5] >> (q & 31)) & 1u) != 0) == nz)
+            q++;
+        const size_t lo = (size_t) p * SP_PAGE;
+        const size_t hi = std::min<size_t>((size_t) q * SP_PAGE, block_size);
+
+        if (nz)
+        {
+            memcpy(dst + lo, pages, hi - lo);
+            pages += (size_t) (q - p) * SP_PAGE;
+        }
+        else
+            zero_fill(dst + lo, hi - lo);
+        p = q;
+    }
 }
 
 extern "C" int
@@ -559,8 +834,52 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
     const size_t   chunk = chunk_blocks(block_size);
     const uint64_t stride = ((uint64_t) block_size + 15) & ~(uint64_t) 15;
     const bool     dst_pinned = is_pinned(dst[0]);
+    /* sparse return pays when a batch is worth a second kernel and blocks have whole pages */
+    const bool     sparse = sparse_enabled(ctx) && n >= 4 && block_size >= 16 * SP_PAGE &&
+                            block_size <= SP_MAXPAGES * SP_PAGE;
     cudaStream_t   lanes[2] = {ctx->stream, ctx->stream2};
     size_t         pending_lo[2] = {0, 0}, pending_n[2] = {0, 0};
+    uint64_t       h2d = 0, d2h = 0;
+
+    /* dense return of lane l's chunk, enqueued on its stream */
+    auto dense_d2h = [&](int l, size_t lo, size_t cnt) -> int {
+        cudaStream_t st = lanes[l];
+
+        if (dst_pinned)
+        {
+            /* straight into the caller's pinned blocks; merge contiguous runs */
+            size_t i = 0;
+
+            while (i < cnt)
+            {
+                size_t j = i + 1;
+
+                while (j < cnt && stride == block_size &&
+                       (uint8_t *) dst[lo + j] == (uint8_t *) dst[lo + j - 1] + block_size)
+                    j++;
+                CU(cudaMemcpyAsync(dst[lo + i], (uint8_t *) ctx->d_out[l].p + i * stride,
+                                   (j - i - 1) * stride + block_size, cudaMemcpyDeviceToHost, st));
+                i = j;
+            }
+        }
+        else
+        {
+            int rc = host_reserve(ctx->h_out[l], cnt * stride);
+
+            if (rc != CRYOGPU_OK)
+                return rc;
+            CU(cudaMemcpyAsync(ctx->h_out[l].p, ctx->d_out[l].p, cnt * stride, cudaMemcpyDeviceToHost, st));
+        }
+        d2h += cnt * (uint64_t) block_size;
+        return CRYOGPU_OK;
+    };
+    auto dense_finish = [&](int l, size_t lo, size_t cnt) -> int {
+        CU(cudaStreamSynchronize(lanes[l]));
+        if (!dst_pinned)
+            for (size_t i = 0; i < cnt; i++)
+                memcpy(dst[lo + i], (uint8_t *) ctx->h_out[l].p + i * stride, block_size);
+        return CRYOGPU_OK;
+    };
 
     /* finish a lane: wait, then hand results to the caller */
     auto drain = [&](int l) -> int {
@@ -574,10 +893,35 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
 
         memcpy(out_size + lo, h_osz, cnt * 4);
         memcpy(status + lo, h_st, cnt * 4);
-        if (!dst_pinned)
-            for (size_t i = 0; i < cnt; i++)
-                memcpy(dst[lo + i], (uint8_t *) ctx->h_out[l].p + i * stride, block_size);
         pending_n[l] = 0;
+        if (!sparse)
+            return dense_finish(l, lo, cnt);
+        const uint32_t *h_bits = (const uint32_t *) ctx->h_sp[l].p;
+        const uint32_t *h_off = h_bits + cnt * SP_WORDS;
+        const uint32_t  total = h_off[cnt];
+
+        if ((uint64_t) total * SP_PAGE * 2 > cnt * (uint64_t) block_size)
+        {
+            /* mostly non-zero pages: the plain copy is the cheaper one */
+            int rc = dense_d2h(l, lo, cnt);
+
+            return rc != CRYOGPU_OK ? rc : dense_finish(l, lo, cnt);
+        }
+        int rc = host_reserve(ctx->h_stage[l], (size_t) total * SP_PAGE + SP_PAGE);
+
+        if (rc != CRYOGPU_OK)
+            return rc;
+        if (total)
+            CU(cudaMemcpyAsync(ctx->h_stage[l].p, ctx->d_stage[l].p, (size_t) total * SP_PAGE,
+                               cudaMemcpyDeviceToHost, lanes[l]));
+        d2h += (uint64_t) total * SP_PAGE;
+        CU(cudaStreamSynchronize(lanes[l]));
+        const uint8_t *pages = (const uint8_t *) ctx->h_stage[l].p;
+
+        host_pool(ctx)->run(cnt, [&](size_t i) {
+            place_sparse_block((uint8_t *) dst[lo + i], block_size, h_bits + i * SP_WORDS,
+                               pages + (size_t) h_off[i] * SP_PAGE);
+        });
         return CRYOGPU_OK;
     };
 
@@ -603,7 +947,12 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
             (rc = dev_reserve(ctx->d_out[lane], cnt * stride)) != CRYOGPU_OK ||
             (rc = dev_reserve(ctx->scratch, chunk * (size_t) ZSTDD_SCRATCH_BYTES * 2)) != CRYOGPU_OK)
             return rc;
-        if (!dst_pinned && (rc = host_reserve(ctx->h_out[lane], cnt * stride)) != CRYOGPU_OK)
+        const size_t sp_bytes = (cnt * (SP_WORDS + 1) + 1) * 4;
+
+        if (sparse &&
+            ((rc = dev_reserve(ctx->d_stage[lane], cnt * stride + SP_PAGE)) != CRYOGPU_OK ||
+             (rc = dev_reserve(ctx->d_sp[lane], sp_bytes)) != CRYOGPU_OK ||
+             (rc = host_reserve(ctx->h_sp[lane], sp_bytes)) != CRYOGPU_OK))
             return rc;
         uint8_t  *hm = (uint8_t *) ctx->h_meta[lane].p;
         uint64_t *h_off = (uint64_t *) hm;
@@ -625,6 +974,7 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
 
         CU(cudaMemcpyAsync(ctx->d_in[lane].p, ctx->h_in[lane].p, in_bytes + 16, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(dm, hm, cnt * 16, cudaMemcpyHostToDevice, st));
+        h2d += in_bytes + 16 + cnt * 16;
         uint8_t *scr = (uint8_t *) ctx->scratch.p + (size_t) lane * chunk * ZSTDD_SCRATCH_BYTES;
 
         k_flag_unknown_methods<<<(unsigned) ((cnt + 255) / 256), 256, 0, st>>>(
@@ -640,26 +990,22 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
                            ctx->predef);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(hm + cnt * 16, dm + cnt * 16, cnt * 8, cudaMemcpyDeviceToHost, st));
-        if (dst_pinned)
+        d2h += cnt * 8;
+        if (sparse)
         {
-            /* straight into the caller's pinned blocks; merge contiguous runs */
-            size_t i = 0;
+            uint32_t *d_bits = (uint32_t *) ctx->d_sp[lane].p;
+            uint32_t *d_off = d_bits + cnt * SP_WORDS;
 
-            while (i < cnt)
-            {
-                size_t j = i + 1;
-
-                while (j < cnt && stride == block_size &&
-                       (uint8_t *) dst[lo + j] == (uint8_t *) dst[lo + j - 1] + block_size)
-                    j++;
-                CU(cudaMemcpyAsync(dst[lo + i], (uint8_t *) ctx->d_out[lane].p + i * stride,
-                                   (j - i - 1) * stride + block_size, cudaMemcpyDeviceToHost, st));
-                i = j;
-            }
+            CU(cudaMemsetAsync(d_off + cnt, 0, 4, st));
+            k_page_compact<<<(unsigned) cnt, 256, 0, st>>>((uint8_t *) ctx->d_out[lane].p, stride, block_size,
+                                                          d_bits, d_off, d_off + cnt,
+                                                          (uint8_t *) ctx->d_stage[lane].p);
+            CU(cudaGetLastError());
+            CU(cudaMemcpyAsync(ctx->h_sp[lane].p, ctx->d_sp[lane].p, sp_bytes, cudaMemcpyDeviceToHost, st));
+            d2h += sp_bytes;
         }
-        else
-            CU(cudaMemcpyAsync(ctx->h_out[lane].p, ctx->d_out[lane].p, cnt * stride,
-                               cudaMemcpyDeviceToHost, st));
+        else if ((rc = dense_d2h(lane, lo, cnt)) != CRYOGPU_OK)
+            return rc;
         pending_lo[lane] = lo;
         pending_n[lane] = cnt;
     }
@@ -667,6 +1013,8 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
 
     if (rc == CRYOGPU_OK)
         rc = drain(1);
+    ctx->last_h2d = h2d;
+    ctx->last_d2h = d2h;
     return rc;
 }
 

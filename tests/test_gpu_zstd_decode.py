@@ -145,3 +145,48 @@ def test_zstd_decode_host_api(gpu, oracle_ref):
     out, osz, st = gpu.decompress_host(COMP_ZSTD, comp)
     assert (st == 0).all() and (osz == CRYO_BLCKSZ).all()
     assert np.array_equal(out, blocks)
+
+
+def _host_batch(oracle_ref):
+    blocks = [bg.make_block("S", "hex", 60), bg.make_block("S", "lowcard", 61), bg.make_block("M", "hex", 62),
+              bg.make_block("D", "hex", 63), np.zeros(CRYO_BLCKSZ, dtype=np.uint8),
+              bg.make_block("D", "random", 64), bg.regression_block(1, 290), bg.make_block("M", "lowcard", 65)]
+    blocks = np.stack(blocks * 3)                       # 24 blocks
+    methods = np.array([i % 2 for i in range(len(blocks))], dtype=np.int32)
+    comp = [oracle_ref.compress(int(m), 1, b)[0][0] for m, b in zip(methods, blocks)]
+    return blocks, methods, comp
+
+
+def test_host_api_sparse_return_is_bit_exact(gpu, oracle_ref):
+    """cryogpu_decompress_host ships only the non-zero 4 KiB pages and zero-fills the rest on the
+    host; the caller's blocks must come out bit-exact whether they are sparse, dense or all zero,
+    and a pre-filled destination must be fully overwritten."""
+    blocks, methods, comp = _host_batch(oracle_ref)
+    out = np.full(blocks.shape, 0xA5, dtype=np.uint8)
+    got, osz, st = gpu.decompress_host(methods, comp, out=out)
+    assert (st == 0).all() and (osz == CRYO_BLCKSZ).all()
+    assert np.array_equal(got, blocks)
+    h2d, d2h = gpu.last_transfer_bytes()
+    assert h2d >= sum(len(c) for c in comp)
+    assert d2h < blocks.size                            # the sparse blocks did not cross the bus whole
+
+
+def test_host_api_dense_return_env_switch(oracle_ref, monkeypatch):
+    from pg_cryogen_b200 import CryoGPU
+    monkeypatch.setenv("CRYOGPU_SPARSE_D2H", "0")
+    g = CryoGPU(0)
+    try:
+        blocks, methods, comp = _host_batch(oracle_ref)
+        got, osz, st = g.decompress_host(methods, comp)
+        assert (st == 0).all() and np.array_equal(got, blocks)
+        assert g.last_transfer_bytes()[1] >= blocks.size
+    finally:
+        g.close()
+
+
+def test_host_api_dense_batch_takes_the_plain_copy(gpu, oracle_ref):
+    blocks = np.stack([bg.make_block("D", "hex", 80 + i) for i in range(6)])
+    comp = [oracle_ref.compress(1, 1, b)[0][0] for b in blocks]
+    got, osz, st = gpu.decompress_host([1] * 6, comp)
+    assert (st == 0).all() and np.array_equal(got, blocks)
+    assert gpu.last_transfer_bytes()[1] >= blocks.size
