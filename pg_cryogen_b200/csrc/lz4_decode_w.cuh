@@ -123,30 +123,60 @@ CRYO_DEV void lz4w_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
         uint32_t ll = token >> 4, ml = token & 15u;
 
         /*
-         * Fast path: no length-extension bytes (ll <= 14, match <= 18), everything well inside
-         * the input window and the output capacity, the match source inside the ring and not
-         * overlapping its destination.  One predicated move each for literals and match.
+         * Fast path: at most one length-extension byte each, runs up to 64 bytes, everything
+         * well inside the input window and the output capacity, the match source inside the
+         * ring and not overlapping its destination.  Two predicated moves each for literals
+         * and match.
          */
-        if (ll != 15u && ml != 15u && rel + 24u <= LZ4W_WIN && ip + ll + 11u <= in.end &&
-            o.pos + ll + ml + 21u <= cap)
+        if (rel + 144u <= LZ4W_WIN)
         {
-            const uint32_t off = in.win[rel + 1 + ll] | ((uint32_t) in.win[rel + 2 + ll] << 8);
-            const uint32_t mlen = ml + 4u;
-            const uint32_t mpos = o.pos + ll;
+            uint32_t q = rel + 1, fl = ll, fm = ml;
+            bool     ok = true;
 
-            if (off >= mlen && off <= WX_RING - 64u && off <= mpos && mpos - off >= o.lo)
+            if (fl == 15u)
             {
-                if (lane < ll)
-                    o.ring[(o.pos + lane) & WX_RMASK] = in.win[rel + 1 + lane];
-                __syncwarp();
-                if (lane < mlen)
-                    o.ring[(mpos + lane) & WX_RMASK] = o.ring[(mpos - off + lane) & WX_RMASK];
-                o.pos = mpos + mlen;
-                ip += 3u + ll;
-                __syncwarp();
-                if (o.pos - o.flushed >= WX_DRAIN)
-                    wx_drain(o, lane);
-                continue;
+                const uint32_t e = in.win[q++];
+
+                fl += e;
+                ok = e != 255u;
+            }
+            const uint32_t lit = q;
+
+            q += fl;
+            if (ok && fl <= 64u)
+            {
+                const uint32_t off = in.win[q] | ((uint32_t) in.win[q + 1] << 8);
+
+                q += 2;
+                if (fm == 15u)
+                {
+                    const uint32_t e = in.win[q++];
+
+                    fm += e;
+                    ok = e != 255u;
+                }
+                const uint32_t mlen = fm + 4u, mpos = o.pos + fl;
+                const uint32_t used = q - rel;
+
+                if (ok && mlen <= 64u && ip + used + 8u <= in.end && mpos + mlen + 21u <= cap &&
+                    off >= mlen && off <= WX_RING - 64u && off <= mpos && mpos - off >= o.lo)
+                {
+                    if (lane < fl)
+                        o.ring[(o.pos + lane) & WX_RMASK] = in.win[lit + lane];
+                    if (lane + 32u < fl)
+                        o.ring[(o.pos + lane + 32u) & WX_RMASK] = in.win[lit + lane + 32u];
+                    __syncwarp();
+                    if (lane < mlen)
+                        o.ring[(mpos + lane) & WX_RMASK] = o.ring[(mpos - off + lane) & WX_RMASK];
+                    if (lane + 32u < mlen)
+                        o.ring[(mpos + lane + 32u) & WX_RMASK] = o.ring[(mpos - off + lane + 32u) & WX_RMASK];
+                    o.pos = mpos + mlen;
+                    ip += used;
+                    __syncwarp();
+                    if (o.pos - o.flushed >= WX_DRAIN)
+                        wx_drain(o, lane);
+                    continue;
+                }
             }
         }
         ip++;

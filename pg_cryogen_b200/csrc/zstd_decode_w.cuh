@@ -1310,13 +1310,13 @@ CRYO_DEV void zstdw_decode_frame(const uint8_t *src, uint32_t csize, uint8_t *ou
                                 break;
                             }
                             /*
-                             * Fast path: a short literal run served from the literal window and a
-                             * short non-overlapping match whose source is in the ring: one
-                             * predicated shared-memory move each.
+                             * Fast path: a literal run of up to 64 bytes served from the literal
+                             * window and a non-overlapping match of up to 64 bytes whose source is
+                             * in the ring: two predicated shared-memory moves each.
                              */
                             const uint32_t lip = L.delta + lpos;
 
-                            if (ll <= 32u && ml <= 32u && !L.rle && off >= ml && off <= WX_RING - 64u &&
+                            if (ll <= 64u && ml <= 64u && !L.rle && off >= ml && off <= WX_RING - 64u &&
                                 mpos - off >= o.lo)
                             {
                                 if (ll)
@@ -1325,10 +1325,15 @@ CRYO_DEV void zstdw_decode_frame(const uint8_t *src, uint32_t csize, uint8_t *ou
                                         zsw_lits_fill(L, lip, lane);
                                     if (lane < ll)
                                         o.ring[(o.pos + lane) & WX_RMASK] = L.win[lip - L.wbase + lane];
+                                    if (lane + 32u < ll)
+                                        o.ring[(o.pos + lane + 32u) & WX_RMASK] = L.win[lip - L.wbase + lane + 32u];
                                     __syncwarp();
                                 }
                                 if (lane < ml)
                                     o.ring[(mpos + lane) & WX_RMASK] = o.ring[(mpos - off + lane) & WX_RMASK];
+                                if (lane + 32u < ml)
+                                    o.ring[(mpos + lane + 32u) & WX_RMASK] =
+                                        o.ring[(mpos - off + lane + 32u) & WX_RMASK];
                                 o.pos = epos;
                                 lpos += ll;
                                 __syncwarp();
