@@ -247,7 +247,32 @@ CRYO_DEV void wx_match(WOut &o, uint32_t off, uint32_t n, uint32_t lane)
         wx_drain(o, lane);
         return;
     }
-    if (off >= 32 || off >= n)
+    if (off >= n && (!in_ring || src + n <= o.lo))
+    {
+        /* the whole source is in global memory and does not overlap the destination: issue
+         * every load before the first store, so a run costs one memory round trip */
+        for (uint32_t i0 = 0; i0 < n; i0 += 128)
+        {
+            uint8_t b[4];
+
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++)
+            {
+                const uint32_t i = i0 + 32 * k + lane;
+
+                b[k] = i < n ? o.out[src + i] : (uint8_t) 0;
+            }
+#pragma unroll
+            for (uint32_t k = 0; k < 4; k++)
+            {
+                const uint32_t i = i0 + 32 * k + lane;
+
+                if (i < n)
+                    o.ring[(o.pos + i) & WX_RMASK] = b[k];
+            }
+        }
+    }
+    else if (off >= 32 || off >= n)
     {
         for (uint32_t i0 = 0; i0 < n; i0 += 32)
         {

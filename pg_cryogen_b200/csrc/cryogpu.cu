@@ -12,6 +12,7 @@
 #include "lz4_decode_w.cuh"
 #include "zstd_decode.cuh"
 #include "zstd_decode_w.cuh"
+#include "zstd_decode_g.cuh"
 #include "lz4_encode.cuh"
 #include "zstd_encode.cuh"
 
@@ -101,7 +102,7 @@ k_zstd_decode(const int32_t *methods, const uint8_t *src, const uint64_t *src_of
                       status + b, scratch + b * scratch_stride);
 }
 
-/* throughput path: one warp per frame, ZSW_WARPS frames per CTA */
+/* throughput path (default): one warp per frame, ZSW_WARPS frames per CTA */
 __global__ void __launch_bounds__(ZSW_THREADS, ZSW_CTAS_PER_SM)
 k_zstd_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
                 const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
@@ -116,6 +117,24 @@ k_zstd_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_
     zstdw_decode_frame(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
                        status + b, scratch + b * scratch_stride, predef,
                        CRYO_SMEM_BASE() + warp * ZSW_PER_WARP, lane);
+}
+
+/* sub-warp variant: ZSG_W lanes per frame, ZSG_GROUPS frames per CTA (CRYOGPU_ZSTD_KERNEL=group) */
+__global__ void __launch_bounds__(ZSG_THREADS, ZSG_CTAS_PER_SM)
+k_zstd_decode_g(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
+                const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
+                uint32_t *out_size, int32_t *status, uint8_t *scratch, uint64_t scratch_stride,
+                const uint32_t *predef, uint32_t n)
+{
+    const uint32_t grp = threadIdx.x / ZSG_W;
+    const uint32_t b = blockIdx.x * ZSG_GROUPS + grp;
+    const Grp<ZSG_W> g = grp_make<ZSG_W>(threadIdx.x & 31u);
+
+    if (b >= n || methods[b] != CRYOGPU_ZSTD)
+        return;
+    zstdg_decode_frame<ZSG_W>(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
+                              status + b, scratch + b * scratch_stride, predef,
+                              CRYO_SMEM_BASE() + grp * ZSW_PER_WARP, g);
 }
 
 /* the three predefined FSE tables of RFC 8878 3.1.1.3.2.2, built once per context */
@@ -272,8 +291,10 @@ launch_lz4_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint8
             methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n);
 }
 
-static bool
-zstd_use_cta_kernel()
+/* CRYOGPU_ZSTD_KERNEL = cta | group selects another variant; default: one warp per frame (the
+ * sub-warp group variant measured no faster on B200: see DESIGN.md section 3) */
+static int
+zstd_kernel_variant()
 {
     static int v = -1;
 
@@ -281,9 +302,9 @@ zstd_use_cta_kernel()
     {
         const char *e = getenv("CRYOGPU_ZSTD_KERNEL");
 
-        v = (e && strcmp(e, "cta") == 0) ? 1 : 0;
+        v = (e && strcmp(e, "cta") == 0) ? 1 : (e && strcmp(e, "group") == 0) ? 0 : 2;
     }
-    return v == 1;
+    return v;
 }
 
 static void
@@ -292,10 +313,16 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
                    uint64_t dst_stride, uint32_t cap, uint32_t *out_size, int32_t *status,
                    uint8_t *scratch, const uint32_t *predef)
 {
-    if (zstd_use_cta_kernel())
+    const int variant = zstd_kernel_variant();
+
+    if (variant == 1)
         k_zstd_decode<<<(unsigned) n, ZSTDD_THREADS, ZSTDD_SMEM, st>>>(
             methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
             ZSTDD_SCRATCH_BYTES);
+    else if (variant == 0)
+        k_zstd_decode_g<<<(unsigned) ((n + ZSG_GROUPS - 1) / ZSG_GROUPS), ZSG_THREADS, ZSG_SMEM, st>>>(
+            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
+            ZSTDD_SCRATCH_BYTES, predef, (uint32_t) n);
     else
         k_zstd_decode_w<<<(unsigned) ((n + ZSW_WARPS - 1) / ZSW_WARPS), ZSW_THREADS, ZSW_SMEM, st>>>(
             methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
@@ -455,6 +482,7 @@ set_kernel_attrs(cryogpu_ctx *ctx)
     CU(cudaFuncSetAttribute(k_lz4_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ4W_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSTDD_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSW_SMEM));
+    CU(cudaFuncSetAttribute(k_zstd_decode_g, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSG_SMEM));
     CU(cudaMalloc(&ctx->predef, ZSW_PREDEF_CELLS * sizeof(uint32_t)));
     k_zstd_build_predef<<<1, 32, 0, ctx->stream>>>(ctx->predef);
     CU(cudaGetLastError());

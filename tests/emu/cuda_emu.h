@@ -47,10 +47,18 @@ struct Fiber
     unsigned    tid;
 };
 
-struct WarpState
+/* one barrier instance per participation mask, so that sub-warp groups (e.g. four 8-lane
+ * groups using 0xFF << 8g) synchronise independently, as they do on the hardware */
+struct MaskBarrier
 {
+    unsigned    mask = 0;
     int         gen = 0;
     int         arrived = 0;
+};
+
+struct WarpState
+{
+    std::vector<MaskBarrier> bars;
     uint64_t    slot[32];
 };
 
@@ -187,15 +195,42 @@ cta_barrier(int &gen, int &arrived, int count)
 }
 
 static inline void
-warp_barrier()
+warp_barrier(unsigned mask = 0xffffffffu)
 {
     Cta *c = g_cta;
     WarpState &w = c->warps[c->cur / 32];
     int lanes = c->nthreads - (int) (c->cur / 32) * 32;
 
-    if (lanes > 32)
-        lanes = 32;
-    cta_barrier(w.gen, w.arrived, lanes);
+    if (lanes < 32)
+        mask &= (1u << lanes) - 1u;
+    if (!(mask & (1u << (c->cur % 32))))
+    {
+        fprintf(stderr, "cuda_emu: lane %u calls a warp collective without being in its mask %08x\n",
+                c->cur % 32, mask);
+        abort();
+    }
+    size_t k = 0;
+
+    for (; k < w.bars.size(); k++)
+        if (w.bars[k].mask == mask)
+            break;
+    if (k == w.bars.size())
+    {
+        w.bars.emplace_back();
+        w.bars[k].mask = mask;
+    }
+    /* index, not reference: other fibers may grow the vector while this one waits */
+    int g = w.bars[k].gen;
+
+    progress();
+    if (++w.bars[k].arrived >= __builtin_popcount(mask))
+    {
+        w.bars[k].arrived = 0;
+        w.bars[k].gen++;
+        return;
+    }
+    while (c->warps[c->cur / 32].bars[k].gen == g)
+        yield();
 }
 
 struct Tidx { unsigned x, y, z; };
@@ -209,7 +244,7 @@ static inline Tidx tidx() { return Tidx{g_cta->cur, 0, 0}; }
 #define gridDim (emu::g_cta->grid_dim)
 
 static inline void __syncthreads() { emu::cta_barrier(emu::g_cta->bar_gen, emu::g_cta->bar_arrived, emu::g_cta->nthreads); }
-static inline void __syncwarp(unsigned mask = 0xffffffffu) { (void) mask; emu::warp_barrier(); }
+static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_barrier(mask); }
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline void __nanosleep(unsigned) { emu::yield(); }
@@ -221,87 +256,96 @@ static inline void emu_named_barrier(int id, int count)
 }
 
 template <typename T>
-static inline T emu_exchange(T v, int src_lane)
+static inline T emu_exchange(unsigned mask, T v, int src_lane)
 {
     emu::Cta *c = emu::g_cta;
-    emu::WarpState &w = c->warps[c->cur / 32];
     uint64_t raw = 0;
 
     memcpy(&raw, &v, sizeof(T));
-    w.slot[c->cur % 32] = raw;
-    emu::warp_barrier();
-    raw = w.slot[src_lane & 31];
-    emu::warp_barrier();
+    c->warps[c->cur / 32].slot[c->cur % 32] = raw;
+    emu::warp_barrier(mask);
+    raw = c->warps[c->cur / 32].slot[src_lane & 31];
+    emu::warp_barrier(mask);
     T r;
     memcpy(&r, &raw, sizeof(T));
     return r;
 }
 
-template <typename T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_exchange(v, src); }
-template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned d)
+/* width: the warp is cut into segments of `width` lanes; src / delta are relative to the segment */
+template <typename T> static inline T __shfl_sync(unsigned mask, T v, int src, int width = 32)
+{
+    int lane = emu::g_cta->cur % 32, base = lane & ~(width - 1);
+    return emu_exchange(mask, v, base + (src & (width - 1)));
+}
+template <typename T> static inline T __shfl_up_sync(unsigned mask, T v, unsigned d, int width = 32)
+{
+    int lane = emu::g_cta->cur % 32, base = lane & ~(width - 1);
+    return emu_exchange(mask, v, lane - (int) d >= base ? lane - (int) d : lane);
+}
+template <typename T> static inline T __shfl_down_sync(unsigned mask, T v, unsigned d, int width = 32)
+{
+    int lane = emu::g_cta->cur % 32, base = lane & ~(width - 1);
+    return emu_exchange(mask, v, lane + (int) d < base + width ? lane + (int) d : lane);
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned mask, T v, int m, int width = 32)
 {
     int lane = emu::g_cta->cur % 32;
-    T r = emu_exchange(v, lane >= (int) d ? lane - (int) d : lane);
-    return r;
+    (void) width;
+    return emu_exchange(mask, v, lane ^ m);
 }
-template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned d)
-{
-    int lane = emu::g_cta->cur % 32;
-    return emu_exchange(v, lane + (int) d < 32 ? lane + (int) d : lane);
-}
-template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m)
-{
-    int lane = emu::g_cta->cur % 32;
-    return emu_exchange(v, lane ^ m);
-}
-static inline unsigned __ballot_sync(unsigned, int pred)
+static inline unsigned __ballot_sync(unsigned mask, int pred)
 {
     emu::Cta *c = emu::g_cta;
-    emu::WarpState &w = c->warps[c->cur / 32];
     int lanes = c->nthreads - (int) (c->cur / 32) * 32;
     unsigned r = 0;
 
     if (lanes > 32)
         lanes = 32;
-    w.slot[c->cur % 32] = pred ? 1 : 0;
-    emu::warp_barrier();
+    c->warps[c->cur / 32].slot[c->cur % 32] = pred ? 1 : 0;
+    emu::warp_barrier(mask);
     for (int i = 0; i < lanes; i++)
-        r |= (unsigned) w.slot[i] << i;
-    emu::warp_barrier();
+        if (mask & (1u << i))
+            r |= (unsigned) c->warps[c->cur / 32].slot[i] << i;
+    emu::warp_barrier(mask);
+    return r;
+}
+static inline unsigned __match_any_sync(unsigned mask, unsigned v)
+{
+    emu::Cta *c = emu::g_cta;
+    unsigned r = 0;
+
+    c->warps[c->cur / 32].slot[c->cur % 32] = v;
+    emu::warp_barrier(mask);
+    for (int i = 0; i < 32; i++)
+        if ((mask & (1u << i)) && (unsigned) c->warps[c->cur / 32].slot[i] == v)
+            r |= 1u << i;
+    emu::warp_barrier(mask);
     return r;
 }
 static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
 static inline int __all_sync(unsigned m, int p) { return __ballot_sync(m, !p) == 0; }
-static inline unsigned __reduce_add_sync(unsigned m, unsigned v)
+template <typename F> static inline unsigned emu_reduce(unsigned mask, unsigned v, F f)
 {
-    for (int o = 16; o; o >>= 1)
-        v += __shfl_xor_sync(m, v, o);
-    return v;
+    emu::Cta *c = emu::g_cta;
+    unsigned r = 0;
+    bool first = true;
+
+    c->warps[c->cur / 32].slot[c->cur % 32] = v;
+    emu::warp_barrier(mask);
+    for (int i = 0; i < 32; i++)
+        if (mask & (1u << i))
+        {
+            unsigned x = (unsigned) c->warps[c->cur / 32].slot[i];
+            r = first ? x : f(r, x);
+            first = false;
+        }
+    emu::warp_barrier(mask);
+    return r;
 }
-static inline unsigned __reduce_max_sync(unsigned m, unsigned v)
-{
-    for (int o = 16; o; o >>= 1)
-    {
-        unsigned t = __shfl_xor_sync(m, v, o);
-        v = t > v ? t : v;
-    }
-    return v;
-}
-static inline unsigned __reduce_min_sync(unsigned m, unsigned v)
-{
-    for (int o = 16; o; o >>= 1)
-    {
-        unsigned t = __shfl_xor_sync(m, v, o);
-        v = t < v ? t : v;
-    }
-    return v;
-}
-static inline unsigned __reduce_or_sync(unsigned m, unsigned v)
-{
-    for (int o = 16; o; o >>= 1)
-        v |= __shfl_xor_sync(m, v, o);
-    return v;
-}
+static inline unsigned __reduce_add_sync(unsigned m, unsigned v) { return emu_reduce(m, v, [](unsigned a, unsigned b) { return a + b; }); }
+static inline unsigned __reduce_max_sync(unsigned m, unsigned v) { return emu_reduce(m, v, [](unsigned a, unsigned b) { return a > b ? a : b; }); }
+static inline unsigned __reduce_min_sync(unsigned m, unsigned v) { return emu_reduce(m, v, [](unsigned a, unsigned b) { return a < b ? a : b; }); }
+static inline unsigned __reduce_or_sync(unsigned m, unsigned v) { return emu_reduce(m, v, [](unsigned a, unsigned b) { return a | b; }); }
 
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
