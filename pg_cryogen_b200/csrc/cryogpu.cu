@@ -13,6 +13,7 @@
 #include "zstd_decode.cuh"
 #include "zstd_decode_w.cuh"
 #include "zstd_decode_g.cuh"
+#include "zstd_decode_p.cuh"
 #include "lz4_encode.cuh"
 #include "zstd_encode.cuh"
 
@@ -107,12 +108,12 @@ __global__ void __launch_bounds__(ZSW_THREADS, ZSW_CTAS_PER_SM)
 k_zstd_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
                 const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
                 uint32_t *out_size, int32_t *status, uint8_t *scratch, uint64_t scratch_stride,
-                const uint32_t *predef, uint32_t n)
+                const uint32_t *predef, uint32_t n, const uint32_t *only)
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b = blockIdx.x * ZSW_WARPS + warp;
 
-    if (b >= n || methods[b] != CRYOGPU_ZSTD)
+    if (b >= n || methods[b] != CRYOGPU_ZSTD || (only && only[b] == 0))
         return;
     zstdw_decode_frame(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
                        status + b, scratch + b * scratch_stride, predef,
@@ -135,6 +136,67 @@ k_zstd_decode_g(const int32_t *methods, const uint8_t *src, const uint64_t *src_
     zstdg_decode_frame<ZSG_W>(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
                               status + b, scratch + b * scratch_stride, predef,
                               CRYO_SMEM_BASE() + grp * ZSW_PER_WARP, g);
+}
+
+/* phase-split pipeline (default zstd path): zstd_decode_p.cuh */
+__global__ void __launch_bounds__(32)
+k_zp_parse(const ZpArgs a)
+{
+    const uint32_t f = blockIdx.x * 32u + threadIdx.x;
+
+    if (f < a.n)
+        zp_stage1(a, f);
+}
+
+__global__ void __launch_bounds__(256)
+k_zp_prefill(const ZpArgs a)
+{
+    zp_stage0(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, threadIdx.x, 256);
+}
+
+__global__ void __launch_bounds__(32 * ZP2A_WARPS)
+k_zp_huftab(const ZpArgs a)
+{
+    /* CTA = the same block index of 8 consecutive frames: its warps have work together or not at all */
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    zp_stage2a(a, (blockIdx.x / ZP_MAXB) * ZP2A_WARPS + warp, blockIdx.x % ZP_MAXB,
+               CRYO_SMEM_BASE() + warp * ZP2A_PER_WARP, lane);
+}
+
+__global__ void __launch_bounds__(32)
+k_zp_literals(const ZpArgs a)
+{
+    zp_stage2b(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+}
+
+__global__ void __launch_bounds__(32 * ZP3A_WARPS)
+k_zp_fsetab(const ZpArgs a)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    zp_stage3a(a, (blockIdx.x / ZP_MAXB) * ZP3A_WARPS + warp, blockIdx.x % ZP_MAXB,
+               CRYO_SMEM_BASE() + warp * ZP3A_PER_WARP, lane);
+}
+
+__global__ void __launch_bounds__(32)
+k_zp_sequences_small(const ZpArgs a)
+{
+    zp_stage3b<ZP3B_SMALL, 0>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+}
+
+__global__ void __launch_bounds__(32)
+k_zp_sequences_large(const ZpArgs a)
+{
+    zp_stage3b<ZP3B_LARGE, ZP3B_SMALL>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+}
+
+__global__ void __launch_bounds__(ZP4_THREADS)
+k_zp_execute(const ZpArgs a)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    zp_stage4(a, blockIdx.x * ZP4_WARPS + warp, CRYO_SMEM_BASE() + warp * ZP4_PER_WARP, lane);
 }
 
 /* the three predefined FSE tables of RFC 8878 3.1.1.3.2.2, built once per context */
@@ -291,8 +353,8 @@ launch_lz4_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint8
             methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n);
 }
 
-/* CRYOGPU_ZSTD_KERNEL = cta | group selects another variant; default: one warp per frame (the
- * sub-warp group variant measured no faster on B200: see DESIGN.md section 3) */
+/* CRYOGPU_ZSTD_KERNEL = cta | group | warp selects another variant; default: the phase-split
+ * pipeline (zstd_decode_p.cuh) */
 static int
 zstd_kernel_variant()
 {
@@ -302,16 +364,59 @@ zstd_kernel_variant()
     {
         const char *e = getenv("CRYOGPU_ZSTD_KERNEL");
 
-        v = (e && strcmp(e, "cta") == 0) ? 1 : (e && strcmp(e, "group") == 0) ? 0 : 2;
+        v = (e && strcmp(e, "cta") == 0) ? 1 : (e && strcmp(e, "group") == 0) ? 0
+            : (e && strcmp(e, "warp") == 0) ? 2 : 3;
     }
     return v;
+}
+
+/* device memory behind the pipeline for n frames of capacity cap, and its carving */
+static size_t
+zp_al(size_t v)
+{
+    return (v + 255) & ~(size_t) 255;
+}
+
+static size_t
+zp_bytes(size_t n, uint32_t cap)
+{
+    return zp_al(n * ZP_FF * 4) + zp_al(n * 4) + zp_al(n * 8) + 256 + zp_al(n * ZP_MAXB * ZP_BF * 4) +
+           zp_al(n * zp_lit_stride(cap)) + zp_al(zp_seq_cap(n, cap) * 8) + zp_al(n * ZP_MAXB * 4096) +
+           zp_al(n * ZP_MAXB * ZP3_CELLS * 4);
+}
+
+static void
+zp_carve(ZpArgs &a, void *base, size_t n, uint32_t cap)
+{
+    uint8_t *p = (uint8_t *) base;
+
+    a.fr = (uint32_t *) p;
+    p += zp_al(n * ZP_FF * 4);
+    a.flag = (uint32_t *) p;
+    p += zp_al(n * 4);
+    a.seqbase = (uint64_t *) p;
+    p += zp_al(n * 8);
+    a.seq_alloc = (unsigned long long *) p;
+    p += 256;
+    a.blk = (uint32_t *) p;
+    p += zp_al(n * ZP_MAXB * ZP_BF * 4);
+    a.lit = p;
+    a.lit_stride = zp_lit_stride(cap);
+    p += zp_al(n * a.lit_stride);
+    a.seq = (uint64_t *) p;
+    a.seq_cap = zp_seq_cap(n, cap);
+    p += zp_al(a.seq_cap * 8);
+    a.huftab = (uint16_t *) p;
+    p += zp_al(n * ZP_MAXB * 4096);
+    a.fsetab = (uint32_t *) p;
 }
 
 static void
 launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint8_t *src,
                    const uint64_t *src_off, const uint32_t *src_size, uint8_t *dst,
                    uint64_t dst_stride, uint32_t cap, uint32_t *out_size, int32_t *status,
-                   uint8_t *scratch, const uint32_t *predef)
+                   uint8_t *scratch, const uint32_t *predef, void *zpbuf, cudaStream_t *aux,
+                   cudaEvent_t *ev)
 {
     const int variant = zstd_kernel_variant();
 
@@ -323,10 +428,50 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         k_zstd_decode_g<<<(unsigned) ((n + ZSG_GROUPS - 1) / ZSG_GROUPS), ZSG_THREADS, ZSG_SMEM, st>>>(
             methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
             ZSTDD_SCRATCH_BYTES, predef, (uint32_t) n);
-    else
+    else if (variant == 2)
         k_zstd_decode_w<<<(unsigned) ((n + ZSW_WARPS - 1) / ZSW_WARPS), ZSW_THREADS, ZSW_SMEM, st>>>(
             methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
-            ZSTDD_SCRATCH_BYTES, predef, (uint32_t) n);
+            ZSTDD_SCRATCH_BYTES, predef, (uint32_t) n, nullptr);
+    else
+    {
+        ZpArgs a;
+        const unsigned ngroups = (unsigned) ((n + ZP_G - 1) / ZP_G);
+
+        a.methods = methods;
+        a.src = src;
+        a.src_off = src_off;
+        a.src_size = src_size;
+        a.dst = dst;
+        a.dst_stride = dst_stride;
+        a.cap = cap;
+        a.n = (uint32_t) n;
+        a.out_size = out_size;
+        a.status = status;
+        a.predef = predef;
+        zp_carve(a, zpbuf, n, cap);
+        cudaMemsetAsync(a.seq_alloc, 0, 8, st);
+        k_zp_parse<<<(unsigned) ((n + 31) / 32), 32, 0, st>>>(a);
+        /* literals (st), sequences (aux 0) and the raw / RLE blocks (aux 1) are independent of
+         * each other: the first two are bound by latency, the third by HBM */
+        cudaEventRecord(ev[0], st);
+        cudaStreamWaitEvent(aux[0], ev[0], 0);
+        cudaStreamWaitEvent(aux[1], ev[0], 0);
+        k_zp_fsetab<<<(unsigned) ((n + ZP3A_WARPS - 1) / ZP3A_WARPS) * ZP_MAXB, 32 * ZP3A_WARPS, ZP3A_SMEM, aux[0]>>>(a);
+        k_zp_sequences_small<<<ngroups * ZP_MAXB, 32, ZP_G * ZP3B_SMALL * 4, aux[0]>>>(a);
+        k_zp_sequences_large<<<ngroups * ZP_MAXB, 32, ZP_G * ZP3B_LARGE * 4, aux[0]>>>(a);
+        cudaEventRecord(ev[1], aux[0]);
+        k_zp_prefill<<<(unsigned) n * ZP_MAXB, 256, 0, aux[1]>>>(a);
+        cudaEventRecord(ev[2], aux[1]);
+        k_zp_huftab<<<(unsigned) ((n + ZP2A_WARPS - 1) / ZP2A_WARPS) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
+        k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
+        cudaStreamWaitEvent(st, ev[1], 0);
+        cudaStreamWaitEvent(st, ev[2], 0);
+        k_zp_execute<<<(unsigned) ((n + ZP4_WARPS - 1) / ZP4_WARPS), ZP4_THREADS, ZP4_SMEM, st>>>(a);
+        /* frames the pipeline declined (flag set): decoded from scratch, one warp per frame */
+        k_zstd_decode_w<<<(unsigned) ((n + ZSW_WARPS - 1) / ZSW_WARPS), ZSW_THREADS, ZSW_SMEM, st>>>(
+            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
+            ZSTDD_SCRATCH_BYTES, predef, (uint32_t) n, a.flag);
+    }
 }
 
 
@@ -428,6 +573,9 @@ struct cryogpu_ctx
     cudaStream_t stream2 = nullptr;     /* second lane for double buffering */
     cudaEvent_t  ev[2] = {nullptr, nullptr};
     DevBuf       scratch;               /* per-block kernel scratch */
+    DevBuf       zp[2];                 /* zstd pipeline work areas (zstd_decode_p.cuh), per lane */
+    cudaStream_t zaux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   /* side streams of the pipeline's concurrent stages */
+    cudaEvent_t  zev[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     uint32_t    *predef = nullptr;      /* predefined zstd FSE tables (device) */
     /* *_host staging (device + pinned host), two lanes */
     DevBuf       d_in[2], d_out[2], d_meta[2];
@@ -567,6 +715,21 @@ cryogpu_init(int device, cryogpu_ctx **out)
         return fail(CRYOGPU_E_CUDA, "stream/event creation failed: %s",
                     cudaGetErrorString(cudaGetLastError()));
     }
+    for (int l = 0; l < 2; l++)
+    {
+        for (int k = 0; k < 2; k++)
+            if (cudaStreamCreateWithFlags(&ctx->zaux[l][k], cudaStreamNonBlocking) != cudaSuccess)
+            {
+                delete ctx;
+                return fail(CRYOGPU_E_CUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+        for (int k = 0; k < 3; k++)
+            if (cudaEventCreateWithFlags(&ctx->zev[l][k], cudaEventDisableTiming) != cudaSuccess)
+            {
+                delete ctx;
+                return fail(CRYOGPU_E_CUDA, "event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+    }
     int rc = set_kernel_attrs(ctx);
 
     if (rc != CRYOGPU_OK)
@@ -587,6 +750,8 @@ cryogpu_shutdown(cryogpu_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->stream2);
     cudaFree(ctx->scratch.p);
+    cudaFree(ctx->zp[0].p);
+    cudaFree(ctx->zp[1].p);
     cudaFree(ctx->predef);
     for (int i = 0; i < 2; i++)
     {
@@ -604,6 +769,13 @@ cryogpu_shutdown(cryogpu_ctx *ctx)
     }
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream2);
+    for (int l = 0; l < 2; l++)
+    {
+        for (int k = 0; k < 2; k++)
+            cudaStreamDestroy(ctx->zaux[l][k]);
+        for (int k = 0; k < 3; k++)
+            cudaEventDestroy(ctx->zev[l][k]);
+    }
     delete ctx->pool;
     delete ctx;
 }
@@ -682,13 +854,16 @@ cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
 
         if (rc != CRYOGPU_OK)
             return rc;
+        if (zstd_kernel_variant() == 3 && (rc = dev_reserve(ctx->zp[0], zp_bytes(n, block_size))) != CRYOGPU_OK)
+            return rc;
     }
     k_flag_unknown_methods<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(d_methods, n, d_out_size,
                                                                          d_status);
     launch_lz4_decode(st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
                       d_out_size, d_status);
     launch_zstd_decode(st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
-                       d_out_size, d_status, (uint8_t *) ctx->scratch.p, ctx->predef);
+                       d_out_size, d_status, (uint8_t *) ctx->scratch.p, ctx->predef, ctx->zp[0].p, ctx->zaux[0],
+                       ctx->zev[0]);
     CU(cudaGetLastError());
     return CRYOGPU_OK;
 }
@@ -973,7 +1148,9 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
             (rc = dev_reserve(ctx->d_in[lane], in_bytes + 16)) != CRYOGPU_OK ||
             (rc = dev_reserve(ctx->d_meta[lane], cnt * 24)) != CRYOGPU_OK ||
             (rc = dev_reserve(ctx->d_out[lane], cnt * stride)) != CRYOGPU_OK ||
-            (rc = dev_reserve(ctx->scratch, chunk * (size_t) ZSTDD_SCRATCH_BYTES * 2)) != CRYOGPU_OK)
+            (rc = dev_reserve(ctx->scratch, chunk * (size_t) ZSTDD_SCRATCH_BYTES * 2)) != CRYOGPU_OK ||
+            (zstd_kernel_variant() == 3 &&
+             (rc = dev_reserve(ctx->zp[lane], zp_bytes(chunk, block_size))) != CRYOGPU_OK))
             return rc;
         const size_t sp_bytes = (cnt * (SP_WORDS + 1) + 1) * 4;
 
@@ -1015,7 +1192,7 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
                            (uint64_t *) dm, (uint32_t *) (dm + cnt * 8),
                            (uint8_t *) ctx->d_out[lane].p, stride, block_size,
                            (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20), scr,
-                           ctx->predef);
+                           ctx->predef, ctx->zp[lane].p, ctx->zaux[lane], ctx->zev[lane]);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(hm + cnt * 16, dm + cnt * 16, cnt * 8, cudaMemcpyDeviceToHost, st));
         d2h += cnt * 8;

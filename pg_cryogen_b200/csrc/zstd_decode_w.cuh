@@ -296,6 +296,9 @@ CRYO_DEV uint32_t zsw_seq_table(ZswState &z, int mode, int t, const uint8_t *p, 
  * warp: 32 symbols per step, rank inside the step by __match_any_sync, running per-weight
  * counters in shared memory.  Returns bytes used by the description, 0 on error.
  */
+CRYO_DEV bool zsw_huf_table(uint8_t *weights, uint32_t nw, uint16_t *huf, uint16_t *symstart,
+                            uint32_t *rankc, int32_t *log_out, uint32_t lane);
+
 CRYO_DEV uint32_t zsw_huf_build(const uint8_t *src, uint32_t n, uint16_t *huf, uint8_t *work,
                                 int32_t *log_out, uint32_t lane)
 {
@@ -388,6 +391,16 @@ CRYO_DEV uint32_t zsw_huf_build(const uint8_t *src, uint32_t n, uint16_t *huf, u
             return 0;
         __syncwarp();
     }
+    return zsw_huf_table(weights, nw, huf, symstart, rankc, log_out, lane) ? used : 0u;
+}
+
+/*
+ * Huffman weights[0, nw) (shared memory, room for one more) -> decoding table.  Whole warp;
+ * symstart u16[256] and rankc u32[32] are shared scratch.  False on an invalid weight set.
+ */
+CRYO_DEV bool zsw_huf_table(uint8_t *weights, uint32_t nw, uint16_t *huf, uint16_t *symstart,
+                            uint32_t *rankc, int32_t *log_out, uint32_t lane)
+{
     /* sum of 2^(w-1), implied last weight */
     uint32_t sum = 0, over = 0;
 
@@ -403,15 +416,15 @@ CRYO_DEV uint32_t zsw_huf_build(const uint8_t *src, uint32_t n, uint16_t *huf, u
     sum = __reduce_add_sync(CRYO_FULL, sum);
     over = __reduce_or_sync(CRYO_FULL, over);
     if (over || sum == 0)
-        return 0;
+        return false;
     const int log = zs_highbit(sum) + 1;
 
     if (log > 11)
-        return 0;
+        return false;
     const uint32_t left = (1u << log) - sum;
 
     if (left & (left - 1))
-        return 0;
+        return false;
     if (lane == 0)
         weights[nw] = (uint8_t) (zs_highbit(left) + 1);
     nw += 1;
@@ -486,7 +499,7 @@ CRYO_DEV uint32_t zsw_huf_build(const uint8_t *src, uint32_t n, uint16_t *huf, u
     }
     __syncwarp();
     *log_out = log;
-    return used;
+    return true;
 }
 
 /*
@@ -528,6 +541,13 @@ CRYO_DEV bool zsw_huf_stream(const uint16_t *huf, int log, const uint8_t *src, u
 
     wi--;
     nextw = wi >= 0 ? wb[wi] : 0u;
+#ifndef CRYO_EMU
+    /* the two sectors below the one just touched (see ZSW_HPREFETCH) */
+    if (wi >= 8)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + wi - 8));
+    if (wi >= 16)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + wi - 16));
+#endif
     const uint32_t sh = 32u - (uint32_t) log;
     uint32_t i = 0;
 
@@ -543,7 +563,12 @@ CRYO_DEV bool zsw_huf_stream(const uint16_t *huf, int log, const uint8_t *src, u
 #ifdef CRYO_EMU
 #define ZSW_HPREFETCH()
 #else
-#define ZSW_HPREFETCH()
+/* L1 fills by 32-byte sector: ask for the sector three below at every refill (8 refills share a
+ * sector), so the dependent word loads hit L1.  A miss stalls every lane of the warp, and with
+ * one stream per lane (zstd_decode_p.cuh) the lanes would take their misses at different times. */
+#define ZSW_HPREFETCH()                                                      \
+    if (wi >= 24)                                                            \
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + wi - 24));
 #endif
 #define ZSW_HREFILL()                                                        \
     if (avail <= 32)                                                         \

@@ -11,10 +11,13 @@
 #include "../../pg_cryogen_b200/csrc/lz4_decode_w.cuh"
 #include "../../pg_cryogen_b200/csrc/zstd_decode_w.cuh"
 #include "../../pg_cryogen_b200/csrc/zstd_decode_g.cuh"
+#include "../../pg_cryogen_b200/csrc/zstd_decode_p.cuh"
 #include "../../pg_cryogen_b200/csrc/lz4_encode.cuh"
 #include "../../pg_cryogen_b200/csrc/zstd_encode.cuh"
 
 #include <vector>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace {
 /* 16-byte aligned copy with `shift` bytes of misalignment and 64 bytes of slack */
@@ -285,4 +288,136 @@ emu_zstdg_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap,
     memcpy(dst, dsts[0], cap);
     *out_size = osz[0];
     return st[0];
+}
+
+/*
+ * phase-split pipeline (zstd_decode_p.cuh): n frames through stages 1-4, then the
+ * warp-per-frame decoder for every frame whose flag was raised.  flags[i] reports which frames
+ * took the fallback, so tests can assert that the pipeline itself decoded what it should.
+ */
+extern "C" int
+emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes, uint8_t *const *dsts,
+                       uint32_t cap, unsigned shift, uint32_t *out_sizes, int32_t *statuses,
+                       uint32_t *flags)
+{
+    static uint32_t predef[ZSW_PREDEF_CELLS];
+    static bool have_predef = false;
+    const uint32_t stride = (cap + 15u) & ~15u;
+    std::vector<uint8_t> obuf((size_t) n * stride + 512, 0xAA), scr(ZSTDD_SCRATCH_BYTES + 128, 0x77);
+    uint8_t *o = (uint8_t *) ((((uintptr_t) obuf.data() + 63) & ~(uintptr_t) 63) + 64);
+    uint8_t *sc = (uint8_t *) ((((uintptr_t) scr.data() + 63) & ~(uintptr_t) 63));
+
+    if (n < 1)
+        return -102;
+    if (!have_predef)
+    {
+        emu::launch(dim3(1), dim3(32), 2048, [&]() { zsw_build_predef(predef, CRYO_SMEM_BASE(), threadIdx.x); });
+        have_predef = true;
+    }
+    /* pack the inputs the way the library does: one buffer, per-frame offsets, odd alignments */
+    std::vector<uint64_t> off(n);
+    std::vector<int32_t>  methods(n, ZP_METHOD_ZSTD);
+    size_t total = 64;
+
+    for (int i = 0; i < n; i++)
+    {
+        off[i] = total + ((shift + 3 * i) & 15);
+        total = (off[i] + csizes[i] + 15 + 16) & ~(size_t) 15;
+    }
+    std::vector<uint8_t> inbuf(total + 256, 0xEE);
+    uint8_t *ib = (uint8_t *) ((((uintptr_t) inbuf.data() + 63) & ~(uintptr_t) 63));
+
+    for (int i = 0; i < n; i++)
+        if (csizes[i])
+            memcpy(ib + off[i], srcs[i], csizes[i]);
+    const uint64_t lit_stride = zp_lit_stride(cap), seq_cap = zp_seq_cap((uint64_t) n, cap);
+    std::vector<uint32_t> fr((size_t) n * ZP_FF, 0xCDCDCDCD), blk((size_t) n * ZP_MAXB * ZP_BF, 0xCDCDCDCD),
+                          flag(n, 0xCDCDCDCD);
+    std::vector<uint64_t> seqbase(n, 0), seq(seq_cap + 8, 0x7777777777777777ull);
+    std::vector<uint8_t>  lit((size_t) n * lit_stride + 64, 0x99);
+    std::vector<uint16_t> huftab((size_t) n * ZP_MAXB * 2048, 0x3333);
+    std::vector<uint32_t> fsetab((size_t) n * ZP_MAXB * ZP3_CELLS, 0x44444444);
+    unsigned long long    seq_alloc = 0;
+    ZpArgs a;
+
+    a.methods = methods.data();
+    a.src = ib;
+    a.src_off = off.data();
+    a.src_size = csizes;
+    a.dst = o;
+    a.dst_stride = stride;
+    a.cap = cap;
+    a.n = (uint32_t) n;
+    a.out_size = out_sizes;
+    a.status = statuses;
+    a.fr = fr.data();
+    a.blk = blk.data();
+    a.flag = flag.data();
+    a.seqbase = seqbase.data();
+    a.seq_alloc = &seq_alloc;
+    a.lit = (uint8_t *) ((((uintptr_t) lit.data() + 15) & ~(uintptr_t) 15));
+    a.lit_stride = lit_stride;
+    a.seq = seq.data();
+    a.seq_cap = seq_cap;
+    a.predef = predef;
+    a.huftab = huftab.data();
+    a.fsetab = fsetab.data();
+
+    const unsigned ngroups = ((unsigned) n + ZP_G - 1) / ZP_G;
+
+    emu::launch(dim3(((unsigned) n + 31) / 32), dim3(32), 0, [&]() {
+        const uint32_t f = blockIdx.x * 32 + threadIdx.x;
+        if (f < a.n)
+            zp_stage1(a, f);
+    });
+    emu::launch(dim3((unsigned) n * ZP_MAXB), dim3(128), 0, [&]() {
+        zp_stage0(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, threadIdx.x, 128);
+    });
+    emu::launch(dim3((unsigned) n * ZP_MAXB / ZP2A_WARPS), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, w = blockIdx.x * ZP2A_WARPS + warp;
+        zp_stage2a(a, w / ZP_MAXB, w % ZP_MAXB, CRYO_SMEM_BASE() + warp * ZP2A_PER_WARP, lane);
+    });
+    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP2B_SMEM, [&]() {
+        zp_stage2b(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    });
+    emu::launch(dim3((unsigned) n * ZP_MAXB / ZP3A_WARPS), dim3(32 * ZP3A_WARPS), ZP3A_SMEM, [&]() {
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, w = blockIdx.x * ZP3A_WARPS + warp;
+        zp_stage3a(a, w / ZP_MAXB, w % ZP_MAXB, CRYO_SMEM_BASE() + warp * ZP3A_PER_WARP, lane);
+    });
+    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP_G * ZP3B_SMALL * 4, [&]() {
+        zp_stage3b<ZP3B_SMALL, 0>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    });
+    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP_G * ZP3B_LARGE * 4, [&]() {
+        zp_stage3b<ZP3B_LARGE, ZP3B_SMALL>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    });
+    emu::launch(dim3(((unsigned) n + ZP4_WARPS - 1) / ZP4_WARPS), dim3(ZP4_THREADS), ZP4_SMEM, [&]() {
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        zp_stage4(a, blockIdx.x * ZP4_WARPS + warp, CRYO_SMEM_BASE() + warp * ZP4_PER_WARP, lane);
+    });
+    if (getenv("ZP_DEBUG"))
+        for (int i = 0; i < n; i++)
+            for (uint32_t j = 0; j < fr[(size_t) i * ZP_FF]; j++)
+            {
+                const uint32_t *b = &blk[((size_t) i * ZP_MAXB + j) * ZP_BF];
+                if ((b[ZPB_KIND] & 3) == 2)
+                    fprintf(stderr, "frame %d block %u: lit_type %u regen %u huf_log %u nseq %u logs ll %u of %u ml %u\n", i, j,
+                            (b[ZPB_KIND] >> 2) & 3, b[ZPB_REGEN], b[ZPB_HINFO] & 0xFF, b[ZPB_NSEQ], b[ZPB_SLOGS] & 0xFF,
+                            (b[ZPB_SLOGS] >> 8) & 0xFF, (b[ZPB_SLOGS] >> 16) & 0x7F);
+            }
+    for (int i = 0; i < n; i++)
+    {
+        flags[i] = flag[i];
+        if (!flag[i])
+            continue;
+        emu::launch(dim3(1), dim3(32), ZSW_PER_WARP, [&]() {
+            zstdw_decode_frame(ib + off[i], csizes[i], o + i * (size_t) stride, cap, out_sizes + i, statuses + i,
+                               sc, predef, CRYO_SMEM_BASE(), threadIdx.x);
+        });
+    }
+    for (int i = 0; i < n; i++)
+        memcpy(dsts[i], o + i * (size_t) stride, cap);
+    for (int i = 1; i <= 64; i++)
+        if (o[-i] != 0xAA)
+            return -100;
+    return 0;
 }

@@ -142,3 +142,82 @@ def test_emulated_group_decoder_diverging_frames(oracle_ref):
             assert st[i] != 0
         else:
             assert st[i] == 0 and osz[i] == MiB and np.array_equal(outs[i], blocks[i]), i
+
+
+# ---- phase-split pipeline (zstd_decode_p.cuh): stages 1-4 + fallback -------------------------
+
+def _pipeline_lib():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
+    L = C.CDLL(os.path.join(HERE, "emu", "libcryoemu.so"))
+    L.emu_zstdp_decode_multi.restype = C.c_int
+    return L
+
+
+def _run_pipeline(L, comp, cap=MiB, shift=0):
+    n = len(comp)
+    comp = [np.ascontiguousarray(c, dtype=np.uint8) for c in comp]
+    outs = [np.zeros(cap, dtype=np.uint8) for _ in range(n)]
+    srcs = (C.c_void_p * n)(*[c.ctypes.data if c.size else None for c in comp])
+    dsts = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+    csz = (C.c_uint32 * n)(*[c.size for c in comp])
+    osz = (C.c_uint32 * n)()
+    st = (C.c_int32 * n)(*([-1] * n))
+    fl = (C.c_uint32 * n)()
+    rc = L.emu_zstdp_decode_multi(n, srcs, csz, dsts, cap, shift, osz, st, fl)
+    assert rc == 0, rc
+    return list(st), list(osz), outs, list(fl)
+
+
+def test_emulated_pipeline_mixed_frames(oracle_ref):
+    """Eleven different frames through the phase-split pipeline in one batch: two entropy groups,
+    lanes of one warp on different tables / streams / sequence counts; a truncated frame must
+    fail alone (through the fallback), everything libzstd wrote at levels -5..3 must be decoded
+    by the pipeline itself (flag 0)."""
+    L = _pipeline_lib()
+    blocks = [bg.make_block("S", "hex", 31), np.zeros(MiB, dtype=np.uint8), bg.make_block("S", "lowcard", 32),
+              bg.make_block("D", "random", 33), bg.regression_block(291, 500), bg.make_block("S", "hex", 34),
+              bg.make_block("M", "hex", 35), bg.make_block("S", "random", 36), bg.make_block("S", "hex", 37),
+              bg.make_block("M", "lowcard", 38), bg.regression_block(1, 290)]
+    levels = [1, 1, 3, 1, -5, 1, 1, 2, -1, 1, 1]
+    comp = [oracle_ref.compress(1, lv, b)[0][0] for lv, b in zip(levels, blocks)]
+    comp[5] = comp[5][:-37].copy()
+    st, osz, outs, fl = _run_pipeline(L, comp, shift=5)
+    for i in range(len(comp)):
+        if i == 5:
+            assert st[i] != 0 and fl[i] != 0
+        else:
+            assert st[i] == 0 and osz[i] == MiB and np.array_equal(outs[i], blocks[i]), i
+            assert fl[i] == 0, (i, "decoded by the fallback, not by the pipeline")
+
+
+def test_emulated_pipeline_conformance_and_fallback(oracle_ref):
+    """Hand-crafted conformance frames and high-level frames (Repeat_Mode tables, single-stream
+    literals): right bytes whichever path takes them; malformed inputs get the warp decoder's verdict."""
+    L = _pipeline_lib()
+    frames = conformance_frames()
+    st, osz, outs, fl = _run_pipeline(L, [f for _, f, _ in frames], cap=4096, shift=1)
+    for (name, _, expect), s, z, o in zip(frames, st, osz, outs):
+        assert s == 0 and z == len(expect) and bytes(o[: len(expect)]) == expect, name
+    blk = bg.make_block("S", "lowcard", 3)
+    hi = [oracle_ref.compress(1, lv, blk)[0][0] for lv in (9, 19)]
+    st, osz, outs, fl = _run_pipeline(L, hi)
+    for s, z, o in zip(st, osz, outs):
+        assert s == 0 and z == MiB and np.array_equal(o, blk)
+    z = oracle_ref.compress(1, 1, bg.make_block("S", "hex", 5))[0][0]
+    bad = z.copy()
+    bad[0] ^= 0xFF
+    two = np.concatenate([z, z])
+    flip = z.copy()
+    flip[len(z) // 2] ^= 0x55
+    st, osz, outs, fl = _run_pipeline(L, [z[:-100], bad, two, flip, z])
+    assert st[0] != 0 and st[1] != 0 and st[2] != 0 and st[4] == 0 and fl[4] == 0
+    st2, _, _, _ = _run_pipeline(L, [z], cap=MiB - 16)
+    assert st2[0] != 0
+    # the flipped byte: whatever the verdict, it must be the warp-per-frame decoder's own
+    one = np.zeros(MiB, dtype=np.uint8)
+    sz = C.c_uint32(0)
+    L.emu_zstdw_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint, C.POINTER(C.c_uint32)]
+    ref_st = L.emu_zstdw_decode(flip.ctypes.data, flip.size, one.ctypes.data, MiB, 0, C.byref(sz))
+    assert (st[3] == 0) == (ref_st == 0)
+    if ref_st == 0:
+        assert np.array_equal(outs[3][: sz.value], one[: sz.value])
