@@ -138,65 +138,110 @@ k_zstd_decode_g(const int32_t *methods, const uint8_t *src, const uint64_t *src_
                               CRYO_SMEM_BASE() + grp * ZSW_PER_WARP, g);
 }
 
+/* development aid (-DZP_TIMELINE): every pipeline kernel records the first CTA start and the last CTA
+ * end on the GPU's global timer, printed by cryogpu_decompress_device when CRYOGPU_ZP_TIMELINE is set */
+#ifdef ZP_TIMELINE
+__device__ unsigned long long zp_tl[32];
+#define ZP_TL_BEGIN(k)                                                                  \
+    if (threadIdx.x == 0)                                                               \
+    {                                                                                   \
+        unsigned long long t_;                                                          \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                          \
+        atomicMin(&zp_tl[2 * (k)], t_);                                                 \
+    }
+#define ZP_TL_END(k)                                                                    \
+    __syncthreads();                                                                    \
+    if (threadIdx.x == 0)                                                               \
+    {                                                                                   \
+        unsigned long long t_;                                                          \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                          \
+        atomicMax(&zp_tl[2 * (k) + 1], t_);                                             \
+    }
+#else
+#define ZP_TL_BEGIN(k)
+#define ZP_TL_END(k)
+#endif
+
 /* phase-split pipeline (default zstd path): zstd_decode_p.cuh */
 __global__ void __launch_bounds__(32)
 k_zp_parse(const ZpArgs a)
 {
+    ZP_TL_BEGIN(0)
     const uint32_t f = blockIdx.x * 32u + threadIdx.x;
 
     if (f < a.n)
         zp_stage1(a, f);
+    ZP_TL_END(0)
 }
 
 __global__ void __launch_bounds__(256)
 k_zp_prefill(const ZpArgs a)
 {
-    zp_stage0(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, threadIdx.x, 256);
+    ZP_TL_BEGIN(1)
+    /* persistent: HBM-bound stores need few warps, and the SM's warp slots are left to the
+     * latency-bound stages that run beside this one */
+    const uint32_t count = *a.pf_count;
+
+    for (uint32_t w = blockIdx.x; w < count; w += gridDim.x)
+        zp_stage0(a, a.pf_list[w], threadIdx.x, 256);
+    ZP_TL_END(1)
 }
 
 __global__ void __launch_bounds__(32 * ZP2A_WARPS)
 k_zp_huftab(const ZpArgs a)
 {
+    ZP_TL_BEGIN(2)
     /* CTA = the same block index of 8 consecutive frames: its warps have work together or not at all */
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     zp_stage2a(a, (blockIdx.x / ZP_MAXB) * ZP2A_WARPS + warp, blockIdx.x % ZP_MAXB,
                CRYO_SMEM_BASE() + warp * ZP2A_PER_WARP, lane);
+    ZP_TL_END(2)
 }
 
 __global__ void __launch_bounds__(32)
 k_zp_literals(const ZpArgs a)
 {
+    ZP_TL_BEGIN(3)
     zp_stage2b(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    ZP_TL_END(3)
 }
 
 __global__ void __launch_bounds__(32 * ZP3A_WARPS)
 k_zp_fsetab(const ZpArgs a)
 {
+    ZP_TL_BEGIN(4)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     zp_stage3a(a, (blockIdx.x / ZP_MAXB) * ZP3A_WARPS + warp, blockIdx.x % ZP_MAXB,
                CRYO_SMEM_BASE() + warp * ZP3A_PER_WARP, lane);
+    ZP_TL_END(4)
 }
 
 __global__ void __launch_bounds__(32)
 k_zp_sequences_small(const ZpArgs a)
 {
+    ZP_TL_BEGIN(5)
     zp_stage3b<ZP3B_SMALL, 0>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    ZP_TL_END(5)
 }
 
 __global__ void __launch_bounds__(32)
 k_zp_sequences_large(const ZpArgs a)
 {
+    ZP_TL_BEGIN(6)
     zp_stage3b<ZP3B_LARGE, ZP3B_SMALL>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    ZP_TL_END(6)
 }
 
 __global__ void __launch_bounds__(ZP4_THREADS)
 k_zp_execute(const ZpArgs a)
 {
+    ZP_TL_BEGIN(7)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     zp_stage4(a, blockIdx.x * ZP4_WARPS + warp, CRYO_SMEM_BASE() + warp * ZP4_PER_WARP, lane);
+    ZP_TL_END(7)
 }
 
 /* the three predefined FSE tables of RFC 8878 3.1.1.3.2.2, built once per context */
@@ -380,7 +425,7 @@ zp_al(size_t v)
 static size_t
 zp_bytes(size_t n, uint32_t cap)
 {
-    return zp_al(n * ZP_FF * 4) + zp_al(n * 4) + zp_al(n * 8) + 256 + zp_al(n * ZP_MAXB * ZP_BF * 4) +
+    return zp_al(n * ZP_FF * 4) + zp_al(n * 4) + zp_al(n * 8) + 256 + zp_al(n * ZP_MAXB * 4) + zp_al(n * ZP_MAXB * ZP_BF * 4) +
            zp_al(n * zp_lit_stride(cap)) + zp_al(zp_seq_cap(n, cap) * 8) + zp_al(n * ZP_MAXB * 4096) +
            zp_al(n * ZP_MAXB * ZP3_CELLS * 4);
 }
@@ -397,7 +442,10 @@ zp_carve(ZpArgs &a, void *base, size_t n, uint32_t cap)
     a.seqbase = (uint64_t *) p;
     p += zp_al(n * 8);
     a.seq_alloc = (unsigned long long *) p;
+    a.pf_count = (unsigned int *) (p + 8);
     p += 256;
+    a.pf_list = (uint32_t *) p;
+    p += zp_al(n * ZP_MAXB * 4);
     a.blk = (uint32_t *) p;
     p += zp_al(n * ZP_MAXB * ZP_BF * 4);
     a.lit = p;
@@ -416,7 +464,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
                    const uint64_t *src_off, const uint32_t *src_size, uint8_t *dst,
                    uint64_t dst_stride, uint32_t cap, uint32_t *out_size, int32_t *status,
                    uint8_t *scratch, const uint32_t *predef, void *zpbuf, cudaStream_t *aux,
-                   cudaEvent_t *ev)
+                   cudaEvent_t *ev, int sm_count)
 {
     const int variant = zstd_kernel_variant();
 
@@ -449,7 +497,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         a.status = status;
         a.predef = predef;
         zp_carve(a, zpbuf, n, cap);
-        cudaMemsetAsync(a.seq_alloc, 0, 8, st);
+        cudaMemsetAsync(a.seq_alloc, 0, 16, st);
         k_zp_parse<<<(unsigned) ((n + 31) / 32), 32, 0, st>>>(a);
         /* literals (st), sequences (aux 0) and the raw / RLE blocks (aux 1) are independent of
          * each other: the first two are bound by latency, the third by HBM */
@@ -457,10 +505,20 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         cudaStreamWaitEvent(aux[0], ev[0], 0);
         cudaStreamWaitEvent(aux[1], ev[0], 0);
         k_zp_fsetab<<<(unsigned) ((n + ZP3A_WARPS - 1) / ZP3A_WARPS) * ZP_MAXB, 32 * ZP3A_WARPS, ZP3A_SMEM, aux[0]>>>(a);
-        k_zp_sequences_small<<<ngroups * ZP_MAXB, 32, ZP_G * ZP3B_SMALL * 4, aux[0]>>>(a);
-        k_zp_sequences_large<<<ngroups * ZP_MAXB, 32, ZP_G * ZP3B_LARGE * 4, aux[0]>>>(a);
+        k_zp_sequences_small<<<ngroups * ZP_MAXB, 32, ZP3B_SMEM(ZP3B_SMALL), aux[0]>>>(a);
+        k_zp_sequences_large<<<ngroups * ZP_MAXB, 32, ZP3B_SMEM(ZP3B_LARGE), aux[0]>>>(a);
         cudaEventRecord(ev[1], aux[0]);
-        k_zp_prefill<<<(unsigned) n * ZP_MAXB, 256, 0, aux[1]>>>(a);
+        static int pf_ctas = -1, pf_late = -1;     /* tuning knobs (development) */
+        if (pf_ctas < 0)
+        {
+            const char *e = getenv("CRYOGPU_ZP_PREFILL_CTAS"), *l = getenv("CRYOGPU_ZP_PREFILL_LATE");
+
+            pf_ctas = e ? atoi(e) : 2;
+            pf_late = l ? atoi(l) : 0;
+        }
+        if (pf_late)
+            cudaStreamWaitEvent(aux[1], ev[1], 0);      /* start the HBM-bound stage after the sequence stage */
+        k_zp_prefill<<<(unsigned) std::min<size_t>(n * ZP_MAXB, (size_t) pf_ctas * sm_count), 256, 0, aux[1]>>>(a);
         cudaEventRecord(ev[2], aux[1]);
         k_zp_huftab<<<(unsigned) ((n + ZP2A_WARPS - 1) / ZP2A_WARPS) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
         k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
@@ -631,6 +689,18 @@ set_kernel_attrs(cryogpu_ctx *ctx)
     CU(cudaFuncSetAttribute(k_zstd_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSTDD_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSW_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode_g, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSG_SMEM));
+    CU(cudaFuncSetAttribute(k_zp_sequences_large, cudaFuncAttributeMaxDynamicSharedMemorySize, ZP3B_SMEM(ZP3B_LARGE)));
+    /* the pipeline's kernels run side by side on one SM (zstd_decode_p.cuh): give them all the same
+     * shared-memory carve-out, because an SM has to drain before it can change its L1 / shared split */
+    {
+        const void *zp_kernels[] = {(const void *) k_zp_parse, (const void *) k_zp_prefill, (const void *) k_zp_huftab,
+                                    (const void *) k_zp_literals, (const void *) k_zp_fsetab,
+                                    (const void *) k_zp_sequences_small, (const void *) k_zp_sequences_large,
+                                    (const void *) k_zp_execute, (const void *) k_zstd_decode_w};
+
+        for (const void *k : zp_kernels)
+            CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    }
     CU(cudaMalloc(&ctx->predef, ZSW_PREDEF_CELLS * sizeof(uint32_t)));
     k_zstd_build_predef<<<1, 32, 0, ctx->stream>>>(ctx->predef);
     CU(cudaGetLastError());
@@ -843,7 +913,7 @@ cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
         return fail(CRYOGPU_E_ARG, "NULL device pointer");
     if (((uintptr_t) d_dst & 15) || (dst_stride & 15) || dst_stride < block_size)
         return fail(CRYOGPU_E_ARG, "d_dst and dst_stride must be multiples of 16, stride >= block_size");
-    if (block_size == 0 || block_size > (1u << 27) || n > 0x7fffffffu)
+    if (block_size == 0 || block_size > (1u << 27) || n > 0xffffffu)
         return fail(CRYOGPU_E_ARG, "block_size or n out of range");
     cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
 
@@ -863,7 +933,7 @@ cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
                       d_out_size, d_status);
     launch_zstd_decode(st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
                        d_out_size, d_status, (uint8_t *) ctx->scratch.p, ctx->predef, ctx->zp[0].p, ctx->zaux[0],
-                       ctx->zev[0]);
+                       ctx->zev[0], ctx->sm_count);
     CU(cudaGetLastError());
     return CRYOGPU_OK;
 }
@@ -1192,7 +1262,7 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
                            (uint64_t *) dm, (uint32_t *) (dm + cnt * 8),
                            (uint8_t *) ctx->d_out[lane].p, stride, block_size,
                            (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20), scr,
-                           ctx->predef, ctx->zp[lane].p, ctx->zaux[lane], ctx->zev[lane]);
+                           ctx->predef, ctx->zp[lane].p, ctx->zaux[lane], ctx->zev[lane], ctx->sm_count);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(hm + cnt * 16, dm + cnt * 16, cnt * 8, cudaMemcpyDeviceToHost, st));
         d2h += cnt * 8;
@@ -1401,3 +1471,23 @@ cryogpu_compress_host_multi(cryogpu_ctx *const *ctxs, int nctx, size_t n, int me
                                      dst + lo, dst_cap, dst_size + lo, status + lo);
     });
 }
+
+#ifdef ZP_TIMELINE
+/* development aid: read (and optionally reset) the pipeline timeline; not part of include/cryogpu.h */
+extern "C" int
+cryogpu_debug_timeline(unsigned long long *out32, int reset)
+{
+    unsigned long long init[32];
+
+    cudaDeviceSynchronize();
+    if (out32)
+        cudaMemcpyFromSymbol(out32, zp_tl, sizeof(init));
+    if (reset)
+    {
+        for (int i = 0; i < 32; i++)
+            init[i] = (i & 1) ? 0ull : ~0ull;
+        cudaMemcpyToSymbol(zp_tl, init, sizeof(init));
+    }
+    return 0;
+}
+#endif

@@ -76,6 +76,8 @@ struct ZpArgs
     uint32_t       *flag;       /* n; non-zero: frame goes to the warp-per-frame decoder */
     uint64_t       *seqbase;    /* n; first entry of the frame in seq[] */
     unsigned long long *seq_alloc;
+    unsigned int   *pf_count;   /* entries in pf_list; zeroed with seq_alloc (adjacent) before stage 1 */
+    uint32_t       *pf_list;    /* raw / RLE blocks for stage 0: frame << 8 | block index */
     uint8_t        *lit;        /* n x lit_stride: Huffman-decoded literals */
     uint64_t        lit_stride; /* multiple of 16, >= cap + 16 * ZP_MAXB */
     uint64_t       *seq;        /* ll | ml << 17 | offset_value << 35 */
@@ -334,6 +336,23 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
             ok = false;
         a.seqbase[f] = base;
     }
+    if (ok)
+    {
+        /* work list of stage 0 */
+        const uint32_t *blk = a.blk + (size_t) f * ZP_MAXB * ZP_BF;
+        uint32_t cnt = 0;
+
+        for (uint32_t j = 0; j < fr[0]; j++)
+            cnt += blk[j * ZP_BF + ZPB_SPECPOS] != ~0u;
+        if (cnt)
+        {
+            uint32_t at = atomicAdd(a.pf_count, cnt);
+
+            for (uint32_t j = 0; j < fr[0]; j++)
+                if (blk[j * ZP_BF + ZPB_SPECPOS] != ~0u)
+                    a.pf_list[at++] = (f << 8) | j;
+        }
+    }
     if (!ok)
     {
         fr[0] = 0;
@@ -349,19 +368,14 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
  * writes those blocks at the assumed position while stages 2 and 3 run (they are bound by
  * latency, this is bound by HBM); stage 4 skips a block when it arrives at exactly that
  * position and writes it itself otherwise (anything stage 0 wrote is then overwritten).
- * One CTA per (frame, block index).
+ * A few persistent CTAs per SM walk the work list stage 1 wrote (frames with f < 2^24).
  */
-CRYO_DEV void zp_stage0(const ZpArgs &a, uint32_t f, uint32_t j, uint32_t tid, uint32_t nthr)
+CRYO_DEV void zp_stage0(const ZpArgs &a, uint32_t item, uint32_t tid, uint32_t nthr)
 {
-    if (f >= a.n || a.fr[(size_t) f * ZP_FF] <= j)
-        return;
+    const uint32_t f = item >> 8, j = item & 0xFFu;
     const uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
-    const uint32_t spec = b[ZPB_SPECPOS];
-
-    if ((b[ZPB_KIND] & 3u) >= 2u || spec == ~0u)
-        return;
     const uint8_t *in = a.src + a.src_off[f] + b[ZPB_OFF];
-    uint8_t *dst = a.dst + (size_t) f * a.dst_stride + spec;
+    uint8_t *dst = a.dst + (size_t) f * a.dst_stride + b[ZPB_SPECPOS];
 
     if ((b[ZPB_KIND] & 3u) == 0)
         team_copy(dst, in, b[ZPB_BSIZE], tid, nthr);
@@ -379,7 +393,8 @@ CRYO_DEV void zp_stage0(const ZpArgs &a, uint32_t f, uint32_t j, uint32_t tid, u
  *     through L1.  No shared memory: the stage co-resides with anything.
  */
 #define ZP2A_WARPS      8u
-#define ZP2A_PER_WARP   (704u + 512u + 128u)    /* weights work | symstart u16[256] | rankc u32[32] */
+#define ZP2A_DESC       176u                    /* staged tree description: 129 bytes at most + alignment slack */
+#define ZP2A_PER_WARP   (704u + 512u + 128u + ZP2A_DESC)    /* weights work | symstart u16[256] | rankc u32[32] | description */
 #define ZP2A_SMEM       (ZP2A_WARPS * ZP2A_PER_WARP)
 
 /* Huffman weights of one tree description, one lane (RFC 8878 4.2.1).  Bytes used or 0. */
@@ -464,9 +479,18 @@ CRYO_DEV void zp_stage2a(const ZpArgs &a, uint32_t f, uint32_t j, uint8_t *smem,
         return;                                 /* treeless blocks use the slot of the block that defined the tree */
     uint32_t used = 0, nw = 0;
     int32_t  log = 0;
+    /* the description (129 bytes at most) -> shared memory in one round trip: lane 0 then reads it
+     * byte by byte and backwards without waiting on HBM, which other stages keep busy meanwhile */
+    const uint8_t *gd = a.src + a.src_off[f] + b[ZPB_HDOFF];
+    const uint32_t dleft = b[ZPB_HDLEFT] < 130u ? b[ZPB_HDLEFT] : 130u;
+    const uint32_t dd = (uint32_t) ((uintptr_t) gd & 15u);
+    uint8_t *sd = smem + 704u + 512u + 128u;
 
+    if (16u * lane < dd + dleft)
+        st16(sd + 16u * lane, ld16(gd - dd + 16u * lane));
+    __syncwarp();
     if (lane == 0)
-        used = zp_huf_weights(a.src + a.src_off[f] + b[ZPB_HDOFF], b[ZPB_HDLEFT], smem,
+        used = zp_huf_weights(sd + dd, dleft, smem,
                               reinterpret_cast<uint32_t *>(smem + 256), reinterpret_cast<int16_t *>(smem + 512),
                               reinterpret_cast<uint16_t *>(smem + 544), &nw);
     used = __shfl_sync(CRYO_FULL, used, 0);
@@ -486,8 +510,22 @@ CRYO_DEV void zp_stage2a(const ZpArgs &a, uint32_t f, uint32_t j, uint8_t *smem,
     }
 }
 
-/* stage 2b body: one warp, block index j of frames [g * ZP_G, g * ZP_G + ZP_G) */
-#define ZP2B_SMEM       (ZP_G * 4096u)
+/*
+ * stage 2b body: one warp, block index j of frames [g * ZP_G, g * ZP_G + ZP_G); lane = 4 *
+ * frame + stream.
+ *
+ * The 32 streams are decoded in lockstep, and the loop is written for that: the scoreboard
+ * tracks registers per warp, so a load issued by one lane under a divergent branch delays the
+ * next use of that register by every other lane.  Hence no branch and no global load in the
+ * symbol loop: each lane's stream is staged through a 256-byte window in shared memory
+ * (refilled by all lanes together when any lane runs low), the refill of the bit accumulator
+ * is predicated, and the window word for the next refill is fetched right after the current
+ * one so that its latency is covered by two symbol decodes.
+ */
+#define ZP2B_WIN        256u                    /* bytes of stream per lane window */
+#define ZP2B_WSTRIDE    (ZP2B_WIN / 4u + 1u)    /* words; odd stride: conflict-free when lanes read the same offset */
+#define ZP2B_OFF_WIN    (ZP_G * 4096u)
+#define ZP2B_SMEM       (ZP2B_OFF_WIN + 32u * ZP2B_WSTRIDE * 4u)
 
 CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem, uint32_t lane)
 {
@@ -527,46 +565,232 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
             for (uint32_t k = 16u * s; k < bytes; k += 64u)
                 st16(st + k, ld16(gt + k));
     }
-    __syncwarp();
-    if (!valid)
-        return;
-    const int32_t  tlog = (int32_t) (hinfo & 0xFFu);
-    const uint32_t own = lt == 2u ? hinfo >> 8 : 0u;
-    const uint8_t *p = a.src + a.src_off[tf] + b[ZPB_OFF] + b[ZPB_LHDR] + own;
-    const uint32_t left = b[ZPB_LCSIZE] - own, regen = b[ZPB_REGEN];
-    uint8_t *dst = a.lit + (size_t) tf * a.lit_stride + b[ZPB_LITPOS];
-    const uint16_t *huf = reinterpret_cast<const uint16_t *>(smem + ti * 4096u);
-    bool ok = true;
+    /* this lane's stream: src[0, sn) -> cnt symbols at dst */
+    const uint8_t *src = nullptr;
+    uint8_t  *dst = nullptr;
+    uint32_t  sn = 0, cnt = 0;
+    int32_t   tlog = 1;
+    bool      ok = true, act = false;
 
-    if (tlog == 0)
-        ok = false;                             /* the tree's own stage-2a warp flagged the frame */
-    else if (!((kind >> 4) & 1u))
+    if (valid)
     {
-        if (s == 0)
-            ok = zsw_huf_stream(huf, tlog, p, left, dst, regen);
-    }
-    else if (left < 6)
-        ok = false;
-    else
-    {
-        const uint32_t s1 = p[0] | ((uint32_t) p[1] << 8);
-        const uint32_t s2 = p[2] | ((uint32_t) p[3] << 8);
-        const uint32_t s3 = p[4] | ((uint32_t) p[5] << 8);
-        const uint32_t seg = (regen + 3) / 4;
+        tlog = (int32_t) (hinfo & 0xFFu);
+        const uint32_t own = lt == 2u ? hinfo >> 8 : 0u;
+        const uint8_t *p = a.src + a.src_off[tf] + b[ZPB_OFF] + b[ZPB_LHDR] + own;
+        const uint32_t left = b[ZPB_LCSIZE] - own, regen = b[ZPB_REGEN];
+        uint8_t *d0 = a.lit + (size_t) tf * a.lit_stride + b[ZPB_LITPOS];
 
-        if (6 + s1 + s2 + s3 > left || seg * 3 > regen)
+        if (tlog == 0)
+        {
+            ok = false;                         /* the tree's own stage-2a warp flagged the frame */
+            tlog = 1;
+        }
+        else if (!((kind >> 4) & 1u))
+        {
+            if (s == 0)
+            {
+                src = p;
+                sn = left;
+                dst = d0;
+                cnt = regen;
+                act = true;
+            }
+        }
+        else if (left < 6)
             ok = false;
         else
         {
-            const uint32_t s4 = left - 6 - s1 - s2 - s3;
-            const uint32_t so = s == 0 ? 0 : s == 1 ? s1 : s == 2 ? s1 + s2 : s1 + s2 + s3;
-            const uint32_t sn = s == 0 ? s1 : s == 1 ? s2 : s == 2 ? s3 : s4;
-            const uint32_t cnt = s < 3 ? seg : regen - 3 * seg;
+            const uint32_t s1 = p[0] | ((uint32_t) p[1] << 8);
+            const uint32_t s2 = p[2] | ((uint32_t) p[3] << 8);
+            const uint32_t s3 = p[4] | ((uint32_t) p[5] << 8);
+            const uint32_t seg = (regen + 3) / 4;
 
-            ok = zsw_huf_stream(huf, tlog, p + 6 + so, sn, dst + s * seg, cnt);
+            if (6 + s1 + s2 + s3 > left || seg * 3 > regen)
+                ok = false;
+            else
+            {
+                const uint32_t s4 = left - 6 - s1 - s2 - s3;
+                const uint32_t so = s == 0 ? 0 : s == 1 ? s1 : s == 2 ? s1 + s2 : s1 + s2 + s3;
+
+                src = p + 6 + so;
+                sn = s == 0 ? s1 : s == 1 ? s2 : s == 2 ? s3 : s4;
+                dst = d0 + s * seg;
+                cnt = s < 3 ? seg : regen - 3 * seg;
+                act = true;
+            }
+        }
+        if (act && sn == 0)
+        {
+            ok = false;
+            act = false;
         }
     }
-    if (!ok)
+    /*
+     * positions are byte offsets from abase = src rounded down to 16 (so they can go below zero:
+     * words in front of the stream read as zero, a valid stream never consumes them and a
+     * corrupt one fails the final bit count)
+     */
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem + ZP2B_OFF_WIN) + lane * ZP2B_WSTRIDE;
+    const uint8_t *abase = src - ((uintptr_t) src & 15u);
+    const int32_t  delta = (int32_t) ((uintptr_t) src & 15u);
+    int32_t  npos = act ? (int32_t) ((delta + sn - 1u) & ~3u) : 0;      /* offset of the next word to hand out */
+    int32_t  g0 = 0;                            /* offset of the window's first byte, multiple of 16 */
+
+#define ZP2B_FILL()                                                          \
+    {                                                                        \
+        __syncwarp();                                                        \
+        g0 = (npos & ~15) - (int32_t) (ZP2B_WIN - 16u);                      \
+        _Pragma("unroll") for (int r_ = 0; r_ < 4; r_++)                     \
+        {                                                                    \
+            uint4 v_[4];                                                     \
+            _Pragma("unroll") for (int k_ = 0; k_ < 4; k_++)                 \
+            {                                                                \
+                const int32_t o_ = g0 + 16 * (4 * r_ + k_);                  \
+                v_[k_] = (act && o_ >= 0) ? ld16(abase + o_) : make_uint4(0, 0, 0, 0); \
+            }                                                                \
+            _Pragma("unroll") for (int k_ = 0; k_ < 4; k_++)                 \
+            {                                                                \
+                uint32_t *w_ = win + 4 * (4 * r_ + k_);                      \
+                w_[0] = v_[k_].x;                                            \
+                w_[1] = v_[k_].y;                                            \
+                w_[2] = v_[k_].z;                                            \
+                w_[3] = v_[k_].w;                                            \
+            }                                                                \
+        }                                                                    \
+        __syncwarp();                                                        \
+    }
+    ZP2B_FILL();
+    /* the word holding the last byte: end mark, first bits */
+    uint32_t hi = 0, lo = 0, cand = 0;
+    int32_t  avail = 0, used = 0, total = 0;
+
+    if (act)
+    {
+        uint32_t w = win[(npos - g0) >> 2];
+        const uint32_t keep = delta + sn - (uint32_t) npos;     /* 1..4 valid low bytes */
+
+        if (keep < 4)
+            w &= (1u << (8u * keep)) - 1u;
+        if (npos < delta)
+            w &= ~0u << (8u * (uint32_t) (delta - npos));
+        if ((w >> (8u * (keep - 1u))) == 0)
+        {
+            ok = false;                         /* no end mark in the last byte */
+            act = false;
+        }
+        else
+        {
+            const int hbit = zs_highbit(w);
+
+            hi = hbit ? w << (32 - hbit) : 0u;
+            avail = hbit;
+            total = (int32_t) ((sn - 1u) * 8u) + (hbit - 8 * (int) (keep - 1u));
+            npos -= 4;
+            cand = win[(npos - g0) >> 2];
+        }
+    }
+    if (!act)
+        cnt = 0;
+    const uint16_t *huf = reinterpret_cast<const uint16_t *>(smem + ti * 4096u);
+    const uint32_t sh = 32u - (uint32_t) tlog;
+
+#ifdef CRYO_EMU
+#define ZP_SHR_C(x, s) ((s) >= 32 ? 0u : (x) >> (s))
+#define ZP_SHL_C(x, s) ((s) >= 32 ? 0u : (x) << (s))
+#else
+#define ZP_SHR_C(x, s) __funnelshift_rc((x), 0u, (uint32_t) (s))
+#define ZP_SHL_C(x, s) __funnelshift_lc(0u, (x), (uint32_t) (s))
+#endif
+/* predicated refill: on = this lane still decodes */
+#define ZP2B_REFILL(on)                                                      \
+    {                                                                        \
+        const bool p_ = (on) && avail <= 32;                                 \
+        hi |= p_ ? ZP_SHR_C(cand, avail) : 0u;                               \
+        lo = p_ ? ZP_SHL_C(cand, 32 - avail) : lo;                           \
+        avail += p_ ? 32 : 0;                                                \
+        npos -= p_ ? 4 : 0;                                                  \
+        cand = win[(npos - g0) >> 2];                                        \
+    }
+#define ZP2B_DEC(sym, on)                                                    \
+    {                                                                        \
+        const uint32_t ent_ = huf[hi >> sh];                                 \
+        const uint32_t nb_ = (on) ? ent_ >> 8 : 0u;                          \
+        sym = ent_ & 0xFFu;                                                  \
+        hi = __funnelshift_l(lo, hi, nb_);                                   \
+        lo <<= nb_;                                                          \
+        avail -= (int32_t) nb_;                                              \
+        used += (int32_t) nb_;                                               \
+    }
+/* the window must hold the words of the next four symbols (at most two) and the fetch after them */
+#define ZP2B_ENSURE(on)                                                      \
+    if (__any_sync(CRYO_FULL, (on) && npos - g0 < 8))                        \
+    {                                                                        \
+        ZP2B_FILL();                                                         \
+        cand = win[(npos - g0) >> 2];                                        \
+    }
+    /* head: single symbols until dst + i is 4-byte aligned */
+    const uint32_t head = act ? min((uint32_t) ((4u - ((uintptr_t) dst & 3u)) & 3u), cnt) : 0u;
+    uint32_t i = 0;
+
+    ZP2B_ENSURE(act);
+#pragma unroll 1
+    for (uint32_t k = 0; k < 3; k++)
+    {
+        const bool on = k < head;
+        uint32_t   sy;
+
+        ZP2B_REFILL(on);
+        ZP2B_DEC(sy, on);
+        if (on)
+            dst[i++] = (uint8_t) sy;
+    }
+    /* quads, four symbols per 32-bit store; every lane runs the warp's longest count */
+    const uint32_t quads = (cnt - i) >> 2;
+    const uint32_t maxq = __reduce_max_sync(CRYO_FULL, quads);
+    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + i);
+
+#pragma unroll 1
+    for (uint32_t q = 0; q < maxq; q++)
+    {
+        const bool on = q < quads;
+        uint32_t   s0, s1, s2, s3;
+
+        ZP2B_ENSURE(on);
+        ZP2B_REFILL(on);
+        ZP2B_DEC(s0, on);
+        ZP2B_DEC(s1, on);
+        ZP2B_REFILL(on);
+        ZP2B_DEC(s2, on);
+        ZP2B_DEC(s3, on);
+        if (on)
+            d4[q] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+    }
+    i += quads << 2;
+    /* tail */
+    const uint32_t tail = cnt - i;
+
+    ZP2B_ENSURE(tail != 0);
+#pragma unroll 1
+    for (uint32_t k = 0; k < 3; k++)
+    {
+        const bool on = k < tail;
+        uint32_t   sy;
+
+        ZP2B_REFILL(on);
+        ZP2B_DEC(sy, on);
+        if (on)
+            dst[i++] = (uint8_t) sy;
+    }
+#undef ZP2B_FILL
+#undef ZP2B_REFILL
+#undef ZP2B_DEC
+#undef ZP2B_ENSURE
+#undef ZP_SHR_C
+#undef ZP_SHL_C
+    /* every bit under the end mark consumed, no more, no less */
+    if (act && used != total)
+        ok = false;
+    if (valid && !ok)
         a.flag[tf] = 1;
 }
 
@@ -582,7 +806,8 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
  */
 #define ZP3_CELLS       1280u                   /* u32 cells per block slot */
 #define ZP3A_WARPS      8u
-#define ZP3A_PER_WARP   (ZP3_CELLS * 4u + 128u + 128u + 144u)   /* cells | counts i16[64] | next u16[64] | cum u16[66] */
+#define ZP3A_DESC       272u                    /* staged table descriptions */
+#define ZP3A_PER_WARP   (ZP3_CELLS * 4u + 128u + 128u + 144u + ZP3A_DESC)   /* cells | counts i16[64] | next u16[64] | cum u16[66] | descriptions */
 #define ZP3A_SMEM       (ZP3A_WARPS * ZP3A_PER_WARP)
 
 /* stage 3a body: one warp, block j of frame f */
@@ -595,8 +820,19 @@ CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t f, uint32_t j, uint8_t *smem,
 
     if ((kind & 3u) != 2u || b[ZPB_NSEQ] == 0)
         return;
-    const uint8_t *p = a.src + a.src_off[f] + b[ZPB_OFF] + b[ZPB_SEQOFF];
-    uint32_t left = b[ZPB_BSIZE] - b[ZPB_SEQOFF], logs = 0;
+    /* the table descriptions (three FSE headers: well under 256 bytes) -> shared memory in one
+     * round trip; what follows them is the bitstream, which stage 3b reads */
+    const uint8_t *gd = a.src + a.src_off[f] + b[ZPB_OFF] + b[ZPB_SEQOFF];
+    const uint32_t full = b[ZPB_BSIZE] - b[ZPB_SEQOFF];
+    const uint32_t dd = (uint32_t) ((uintptr_t) gd & 15u);
+    uint8_t *sd = smem + ZP3_CELLS * 4u + 128u + 128u + 144u;
+    uint32_t left = full < 256u - 16u ? full : 256u - 16u, logs = 0;
+    const uint32_t staged = left;
+
+    if (16u * lane < dd + left && lane < 16u)
+        st16(sd + 16u * lane, ld16(gd - dd + 16u * lane));
+    __syncwarp();
+    const uint8_t *p = sd + dd;
     uint32_t *cells = reinterpret_cast<uint32_t *>(smem);
     int16_t  *counts = reinterpret_cast<int16_t *>(smem + ZP3_CELLS * 4u);
     uint16_t *next = reinterpret_cast<uint16_t *>(smem + ZP3_CELLS * 4u + 128u);
@@ -682,65 +918,9 @@ CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t f, uint32_t j, uint8_t *smem,
     if (lane == 0)
     {
         b[ZPB_SLOGS] = logs | 0x80000000u;
-        b[ZPB_BITOFF] = b[ZPB_BSIZE] - left;
+        b[ZPB_BITOFF] = b[ZPB_SEQOFF] + (staged - left);
     }
     __syncwarp();
-}
-
-/* one lane walks one block's sequence bitstream (RFC 8878 3.1.1.3.2.1.2) */
-CRYO_DEV bool zp_seq_walk(const uint32_t *llt, const uint32_t *oft, const uint32_t *mlt, uint32_t ll_log,
-                          uint32_t of_log, uint32_t ml_log, const uint8_t *p, uint32_t n, uint32_t nseq,
-                          uint64_t *out)
-{
-    BitsBack bb;
-
-    if (!bb_init(bb, p, n))
-        return false;
-    bb_refill(bb);
-    uint32_t sl = bb_read(bb, ll_log);
-    uint32_t so = bb_read(bb, of_log);
-    uint32_t sm = bb_read(bb, ml_log);
-
-    if (bb.remaining < 0)
-        return false;
-#ifndef CRYO_EMU
-    /* L1 fills by 32-byte sector and a miss stalls every lane of the warp: ask for the sector
-     * three below the read position once per sequence */
-    if (bb.cur >= bb.start + 32)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(bb.cur - 32));
-    if (bb.cur >= bb.start + 64)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(bb.cur - 64));
-#endif
-    for (uint32_t i = 0; i < nseq; i++)
-    {
-#ifndef CRYO_EMU
-        if (bb.cur >= bb.start + 96)
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(bb.cur - 96));
-#endif
-        const uint32_t cl = llt[sl], co = oft[so], cm = mlt[sm];
-        const uint32_t xo = co >> 26, xm = cm >> 26, xl = cl >> 26;
-
-        if (xo > 27)
-            return false;                       /* beyond any window ZSTD_decompress accepts */
-        bb_refill(bb);
-        const uint32_t ov = (1u << xo) + bb_read(bb, xo);
-
-        bb_refill(bb);
-        const uint32_t ml = (CRYO_GLD(ZS_ML_PACK[cm & 0xFFu]) & 0xFFFFFFu) + bb_read(bb, xm);
-        const uint32_t ll = (CRYO_GLD(ZS_LL_PACK[cl & 0xFFu]) & 0xFFFFFFu) + bb_read(bb, xl);
-
-        if (i + 1 < nseq)
-        {
-            bb_refill(bb);
-            sl = ((cl >> 16) & 0x3FFu) + bb_read(bb, (cl >> 8) & 0xFFu);
-            sm = ((cm >> 16) & 0x3FFu) + bb_read(bb, (cm >> 8) & 0xFFu);
-            so = ((co >> 16) & 0x3FFu) + bb_read(bb, (co >> 8) & 0xFFu);
-        }
-        if (bb.remaining < 0)
-            return false;
-        out[i] = (uint64_t) ll | ((uint64_t) ml << 17) | ((uint64_t) ov << 35);
-    }
-    return bb.remaining == 0;
 }
 
 /*
@@ -750,9 +930,17 @@ CRYO_DEV bool zp_seq_walk(const uint32_t *llt, const uint32_t *oft, const uint32
  * what libzstd emits for sparse blocks, 6/6/7-bit tables; large: the 9/8/9-bit maximum) and a
  * warp runs in the smallest class that holds all its blocks, so the small class keeps many
  * groups resident per SM.
+ *
+ * Like stage 2b the walk is written for lockstep: the bitstream of every lane is staged
+ * through a 256-byte shared-memory window, refills of the 64-bit accumulator are predicated,
+ * the next window word is fetched one refill ahead, and there is no branch or global load
+ * inside a sequence (the 8-byte result store aside).
  */
 #define ZP3B_SMALL      320u
 #define ZP3B_LARGE      ZP3_CELLS
+#define ZP3B_WIN        256u
+#define ZP3B_WSTRIDE    (ZP3B_WIN / 4u + 1u)
+#define ZP3B_SMEM(cells) (ZP_G * (cells) * 4u + 32u * ZP3B_WSTRIDE * 4u)
 
 template <uint32_t CELLS, uint32_t BELOW>      /* this launch takes groups needing > BELOW and <= CELLS cells */
 CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem, uint32_t lane)
@@ -760,7 +948,7 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
     const uint32_t f = g * ZP_G + lane;
     const uint32_t *b = nullptr;
     uint32_t logs = 0, nseq = 0, need = 0;
-    bool     valid = false, failed = false;
+    bool     act = false;
 
     if (lane < ZP_G && f < a.n && a.fr[(size_t) f * ZP_FF] > j && a.flag[f] == 0)
     {
@@ -769,18 +957,16 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         if ((b[ZPB_KIND] & 3u) == 2u && nseq != 0)
         {
             logs = b[ZPB_SLOGS];
-            valid = (logs & 0x80000000u) != 0;
-            failed = !valid;                    /* the block's stage-3a warp flagged the frame */
-            need = valid ? (1u << (logs & 0xFFu)) + (1u << ((logs >> 8) & 0xFFu)) + (1u << ((logs >> 16) & 0x7Fu)) : 0u;
+            act = (logs & 0x80000000u) != 0;    /* else: the block's stage-3a warp flagged the frame */
+            need = act ? (1u << (logs & 0xFFu)) + (1u << ((logs >> 8) & 0xFFu)) + (1u << ((logs >> 16) & 0x7Fu)) : 0u;
         }
     }
     const uint32_t gneed = __reduce_max_sync(CRYO_FULL, need);
 
     if (gneed == 0 || gneed > CELLS || gneed <= BELOW)
         return;
-    (void) failed;
     /* tables -> shared memory, the whole warp per block */
-    for (uint32_t m = __ballot_sync(CRYO_FULL, valid); m; m &= m - 1)
+    for (uint32_t m = __ballot_sync(CRYO_FULL, act); m; m &= m - 1)
     {
         const int      i = __ffs((int) m) - 1;
         const uint32_t li = __shfl_sync(CRYO_FULL, logs, i);
@@ -795,16 +981,178 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         for (uint32_t k = lane; k < nm; k += 32)
             cells[nl + no + k] = slot[768u + k];
     }
-    __syncwarp();
-    if (!valid)
-        return;
     const uint32_t ll_log = logs & 0xFFu, of_log = (logs >> 8) & 0xFFu, ml_log = (logs >> 16) & 0x7Fu;
-    const uint32_t *cells = reinterpret_cast<const uint32_t *>(smem) + lane * CELLS;
-    const uint32_t bitoff = b[ZPB_BITOFF];
+    const uint32_t *llt = reinterpret_cast<const uint32_t *>(smem) + (lane & (ZP_G - 1u)) * CELLS;
+    const uint32_t *oft = llt + (1u << ll_log), *mlt = oft + (1u << of_log);
+    /* this lane's bitstream src[0, sn); positions are byte offsets from abase = src rounded down to 16 */
+    const uint8_t *src = nullptr;
+    uint32_t  sn = 0;
+    bool      bad = false;
 
-    if (!zp_seq_walk(cells, cells + (1u << ll_log), cells + (1u << ll_log) + (1u << of_log), ll_log, of_log, ml_log,
-                     a.src + a.src_off[f] + b[ZPB_OFF] + bitoff, b[ZPB_BSIZE] - bitoff, nseq,
-                     a.seq + a.seqbase[f] + b[ZPB_SEQPOS]))
+    if (act)
+    {
+        const uint32_t bitoff = b[ZPB_BITOFF];
+
+        src = a.src + a.src_off[f] + b[ZPB_OFF] + bitoff;
+        sn = b[ZPB_BSIZE] - bitoff;
+        if (sn == 0)
+        {
+            bad = true;
+            act = false;
+        }
+    }
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem + ZP_G * CELLS * 4u) + lane * ZP3B_WSTRIDE;
+    const uint8_t *abase = src - ((uintptr_t) src & 15u);
+    const int32_t  delta = (int32_t) ((uintptr_t) src & 15u);
+    int32_t  npos = act ? (int32_t) ((delta + sn - 1u) & ~3u) : 0;
+    int32_t  g0 = 0;
+
+#define ZP3B_FILL()                                                          \
+    {                                                                        \
+        __syncwarp();                                                        \
+        g0 = (npos & ~15) - (int32_t) (ZP3B_WIN - 16u);                      \
+        _Pragma("unroll") for (int r_ = 0; r_ < 4; r_++)                     \
+        {                                                                    \
+            uint4 v_[4];                                                     \
+            _Pragma("unroll") for (int k_ = 0; k_ < 4; k_++)                 \
+            {                                                                \
+                const int32_t o_ = g0 + 16 * (4 * r_ + k_);                  \
+                v_[k_] = (act && o_ >= 0) ? ld16(abase + o_) : make_uint4(0, 0, 0, 0); \
+            }                                                                \
+            _Pragma("unroll") for (int k_ = 0; k_ < 4; k_++)                 \
+            {                                                                \
+                uint32_t *w_ = win + 4 * (4 * r_ + k_);                      \
+                w_[0] = v_[k_].x;                                            \
+                w_[1] = v_[k_].y;                                            \
+                w_[2] = v_[k_].z;                                            \
+                w_[3] = v_[k_].w;                                            \
+            }                                                                \
+        }                                                                    \
+        __syncwarp();                                                        \
+    }
+    ZP3B_FILL();
+    uint32_t ahi = 0, alo = 0, cand = 0;        /* accumulator: next bit to read is bit 31 of ahi */
+    int32_t  avail = 0, remaining = 0;
+
+    if (act)
+    {
+        uint32_t w = win[(npos - g0) >> 2];
+        const uint32_t keep = delta + sn - (uint32_t) npos;     /* 1..4 valid low bytes */
+
+        if (keep < 4)
+            w &= (1u << (8u * keep)) - 1u;
+        if (npos < delta)
+            w &= ~0u << (8u * (uint32_t) (delta - npos));
+        if ((w >> (8u * (keep - 1u))) == 0)
+        {
+            bad = true;                         /* no end mark in the last byte */
+            act = false;
+        }
+        else
+        {
+            const int hbit = zs_highbit(w);
+
+            ahi = hbit ? w << (32 - hbit) : 0u;
+            avail = hbit;
+            remaining = (int32_t) ((sn - 1u) * 8u) + (hbit - 8 * (int) (keep - 1u));
+            npos -= 4;
+            cand = win[(npos - g0) >> 2];
+        }
+    }
+    if (!act)
+        nseq = 0;
+#ifdef CRYO_EMU
+#define ZP_SHR_C(x, s) ((s) >= 32 ? 0u : (x) >> (s))
+#define ZP_SHL_C(x, s) ((s) >= 32 ? 0u : (x) << (s))
+#define ZP_FSHL_C(l, h, s) ((s) >= 32 ? (l) : __funnelshift_l((l), (h), (s)))
+#else
+#define ZP_FSHL_C(l, h, s) __funnelshift_lc((l), (h), (uint32_t) (s))
+#define ZP_SHR_C(x, s) __funnelshift_rc((x), 0u, (uint32_t) (s))
+#define ZP_SHL_C(x, s) __funnelshift_lc(0u, (x), (uint32_t) (s))
+#endif
+/* predicated refill to more than 32 valid bits */
+#define ZP3B_REFILL(on)                                                      \
+    {                                                                        \
+        const bool p_ = (on) && avail <= 32;                                 \
+        ahi |= p_ ? ZP_SHR_C(cand, avail) : 0u;                              \
+        alo = p_ ? ZP_SHL_C(cand, 32 - avail) : alo;                         \
+        avail += p_ ? 32 : 0;                                                \
+        npos -= p_ ? 4 : 0;                                                  \
+        cand = win[(npos - g0) >> 2];                                        \
+    }
+/* nb <= 32 bits out of the accumulator (nb == 0 reads nothing) */
+#define ZP3B_READ(dst, nb)                                                   \
+    {                                                                        \
+        const uint32_t n_ = (nb);                                            \
+        dst = ZP_SHR_C(ahi, 32u - n_);                                       \
+        ahi = ZP_FSHL_C(alo, ahi, n_);                                \
+        alo = ZP_SHL_C(alo, n_);                                             \
+        avail -= (int32_t) n_;                                               \
+        remaining -= (int32_t) n_;                                           \
+    }
+#define ZP3B_ENSURE(on)                                                      \
+    if (__any_sync(CRYO_FULL, (on) && npos - g0 < 12))                       \
+    {                                                                        \
+        ZP3B_FILL();                                                         \
+        cand = win[(npos - g0) >> 2];                                        \
+    }
+    uint32_t sl = 0, so = 0, sm = 0;
+
+    ZP3B_ENSURE(act);
+    ZP3B_REFILL(act);
+    ZP3B_READ(sl, act ? ll_log : 0u);
+    ZP3B_READ(so, act ? of_log : 0u);
+    ZP3B_READ(sm, act ? ml_log : 0u);
+    if (remaining < 0)
+        bad = true;
+    uint64_t *out = act ? a.seq + a.seqbase[f] + b[ZPB_SEQPOS] : nullptr;
+    const uint32_t maxseq = __reduce_max_sync(CRYO_FULL, nseq);
+
+#pragma unroll 1
+    for (uint32_t i = 0; i < maxseq; i++)
+    {
+        const bool on = i < nseq;
+        const bool more = i + 1 < nseq;
+
+        ZP3B_ENSURE(on);
+        const uint32_t cl = llt[sl], co = oft[so], cm = mlt[sm];
+        const uint32_t xo = co >> 26, xm = cm >> 26, xl = cl >> 26;
+        uint32_t ov, ml, ll, t;
+
+        if (on && xo > 27)
+            bad = true;                         /* beyond any window ZSTD_decompress accepts */
+        ZP3B_REFILL(on);
+        ZP3B_READ(ov, on ? (xo > 27 ? 27u : xo) : 0u);
+        ov += 1u << (xo & 31u);
+        ZP3B_REFILL(on);
+        ZP3B_READ(ml, on ? xm : 0u);
+        ml += CRYO_GLD(ZS_ML_PACK[cm & 0xFFu]) & 0xFFFFFFu;
+        ZP3B_READ(ll, on ? xl : 0u);
+        ll += CRYO_GLD(ZS_LL_PACK[cl & 0xFFu]) & 0xFFFFFFu;
+        ZP3B_REFILL(more);
+        ZP3B_READ(t, more ? (cl >> 8) & 0xFFu : 0u);
+        sl = more ? ((cl >> 16) & 0x3FFu) + t : sl;
+        ZP3B_READ(t, more ? (cm >> 8) & 0xFFu : 0u);
+        sm = more ? ((cm >> 16) & 0x3FFu) + t : sm;
+        ZP3B_READ(t, more ? (co >> 8) & 0xFFu : 0u);
+        so = more ? ((co >> 16) & 0x3FFu) + t : so;
+        if (on)
+        {
+            if (remaining < 0)
+                bad = true;
+            out[i] = (uint64_t) ll | ((uint64_t) ml << 17) | ((uint64_t) (ov & 0x1FFFFFFFu) << 35);
+        }
+    }
+#undef ZP3B_FILL
+#undef ZP3B_REFILL
+#undef ZP3B_READ
+#undef ZP3B_ENSURE
+#undef ZP_SHR_C
+#undef ZP_SHL_C
+#undef ZP_FSHL_C
+    if (act && remaining != 0)
+        bad = true;
+    if (bad)
         a.flag[f] = 1;
 }
 
@@ -812,8 +1160,13 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 
 #define ZP4_WARPS       8u
 #define ZP4_THREADS     (32u * ZP4_WARPS)
-#define ZP4_PER_WARP    (WX_RING + ZSW_LITWIN)
+#define ZP4_LITWIN      1024u                   /* literal window (the slow path uses its first ZSW_LITWIN bytes) */
+#define ZP4_PER_WARP    (WX_RING + ZP4_LITWIN)
 #define ZP4_SMEM        (ZP4_WARPS * ZP4_PER_WARP)
+#define ZP4_SPAN        1024u                   /* output bytes of one sub-batch: it is written ahead of o.pos in the ring */
+#define ZP4_BIG_LL      96u                     /* longer runs leave the batch path */
+#define ZP4_BIG_ML      256u
+#define ZP4_LANE_ML     48u                     /* independent matches up to this long are copied by one lane each */
 
 /* stage 4 body: one warp, frame f */
 CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lane)
@@ -877,6 +1230,16 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
             uint64_t nxt = lane < nseq ? sq[lane] : 0ull;
             uint32_t lpos = 0;
 
+            /*
+             * 32 sequences per load, lane k = sequence done + k.  Offsets (repeat codes), output
+             * and literal positions and the format checks are computed for the whole load first
+             * (a serial pass over the offset codes, two warp scans, one vote).  Then runs of
+             * ordinary sequences are executed as sub-batches written ahead of o.pos in the ring:
+             * every lane copies the literals of its own sequence (they come from one contiguous
+             * piece of the literal buffer, staged in the window), then the matches follow in
+             * order, each a warp-wide move.  Long runs, and anything that does not fit the ring,
+             * take the general executor one sequence at a time.
+             */
             for (uint32_t done = 0; done < nseq && err == ST_OK; done += 32)
             {
                 const uint32_t g = nseq - done < 32u ? nseq - done : 32u;
@@ -884,81 +1247,194 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
 
                 if (done + 32u + lane < nseq)
                     nxt = sq[done + 32u + lane];
-                const uint32_t my_ll = (uint32_t) cur & 0x1FFFFu, my_ml = (uint32_t) (cur >> 17) & 0x3FFFFu;
+                const bool     have = lane < g;
+                const uint32_t my_ll = have ? (uint32_t) cur & 0x1FFFFu : 0u;
+                const uint32_t my_ml = have ? (uint32_t) (cur >> 17) & 0x3FFFFu : 0u;
                 const uint32_t my_ov = (uint32_t) (cur >> 35);
+                uint32_t my_off = 0;
 
-                for (uint32_t k = 0; k < g; k++)
+                /* repeat offsets, in order (RFC 8878 3.1.1.5) */
                 {
-                    const uint32_t ov = __shfl_sync(CRYO_FULL, my_ov, (int) k);
-                    const uint32_t ml = __shfl_sync(CRYO_FULL, my_ml, (int) k);
-                    const uint32_t ll = __shfl_sync(CRYO_FULL, my_ll, (int) k);
-                    uint32_t moff;
+                    const uint32_t zmask = __ballot_sync(CRYO_FULL, my_ll == 0);
 
-                    if (ov > 3)
+                    for (uint32_t k = 0; k < g; k++)
                     {
-                        moff = ov - 3;
-                        rep2 = rep1;
-                        rep1 = rep0;
-                        rep0 = moff;
-                    }
-                    else
-                    {
-                        const uint32_t idx = ov - 1 + (ll == 0 ? 1u : 0u);
+                        const uint32_t ov = __shfl_sync(CRYO_FULL, my_ov, (int) k);
+                        uint32_t moff;
 
-                        if (idx == 0)
-                            moff = rep0;
-                        else
+                        if (ov > 3)
                         {
-                            moff = idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
-                            if (idx > 1)
-                                rep2 = rep1;
+                            moff = ov - 3;
+                            rep2 = rep1;
                             rep1 = rep0;
                             rep0 = moff;
                         }
-                    }
-                    const uint32_t mpos = o.pos + ll, epos = mpos + ml;     /* < 2^28: no wrap */
-
-                    if ((ll > regen - lpos) | (epos > cap) | (epos - block_start > ZS_MAXBLOCK) |
-                        (moff - 1u >= mpos))
-                    {
-                        err = ll > regen - lpos ? ST_FORMAT
-                              : epos > cap ? ST_OUTPUT
-                              : epos - block_start > ZS_MAXBLOCK ? ST_FORMAT : ST_OFFSET;
-                        break;
-                    }
-                    /* fast path: literal run and non-overlapping match of up to 64 bytes each,
-                     * literals in the window, match source in the ring */
-                    const uint32_t lip = L.delta + lpos;
-
-                    if (ll <= 64u && ml <= 64u && !L.rle && moff >= ml && moff <= WX_RING - 64u &&
-                        mpos - moff >= o.lo)
-                    {
-                        if (ll)
+                        else
                         {
-                            if (!L.wvalid || lip + ll > L.wbase + ZSW_LITWIN || lip < L.wbase)
-                                zsw_lits_fill(L, lip, lane);
-                            if (lane < ll)
-                                o.ring[(o.pos + lane) & WX_RMASK] = L.win[lip - L.wbase + lane];
-                            if (lane + 32u < ll)
-                                o.ring[(o.pos + lane + 32u) & WX_RMASK] = L.win[lip - L.wbase + lane + 32u];
-                            __syncwarp();
+                            const uint32_t idx = ov - 1 + ((zmask >> k) & 1u);
+
+                            if (idx == 0)
+                                moff = rep0;
+                            else
+                            {
+                                moff = idx == 1 ? rep1 : idx == 2 ? rep2 : rep0 - 1;
+                                if (idx > 1)
+                                    rep2 = rep1;
+                                rep1 = rep0;
+                                rep0 = moff;
+                            }
                         }
-                        if (lane < ml)
-                            o.ring[(mpos + lane) & WX_RMASK] = o.ring[(mpos - moff + lane) & WX_RMASK];
-                        if (lane + 32u < ml)
-                            o.ring[(mpos + lane + 32u) & WX_RMASK] = o.ring[(mpos - moff + lane + 32u) & WX_RMASK];
-                        o.pos = epos;
-                        lpos += ll;
-                        __syncwarp();
-                        if (o.pos - o.flushed >= WX_DRAIN)
-                            wx_drain(o, lane);
+                        if (lane == k)
+                            my_off = moff;
+                    }
+                }
+                /* positions: inclusive scans of ll + ml and of ll */
+                uint32_t cum = my_ll + my_ml, lcum = my_ll;
+
+#pragma unroll
+                for (uint32_t d = 1; d < 32; d <<= 1)
+                {
+                    const uint32_t c1 = __shfl_up_sync(CRYO_FULL, cum, d), c2 = __shfl_up_sync(CRYO_FULL, lcum, d);
+
+                    if (lane >= d)
+                    {
+                        cum += c1;
+                        lcum += c2;
+                    }
+                }
+                const uint32_t base_pos = o.pos, base_lit = lpos;
+                const uint32_t my_start = base_pos + cum - my_ll - my_ml, my_mpos = my_start + my_ll;
+                const uint32_t my_epos = base_pos + cum;                /* < 2^28: no wrap */
+                const uint32_t my_lit = base_lit + lcum - my_ll;        /* first literal of this sequence */
+
+                if (__any_sync(CRYO_FULL, have && ((base_lit + lcum > regen) | (my_epos > cap) |
+                                                   (my_epos - block_start > ZS_MAXBLOCK) |
+                                                   (my_off - 1u >= my_mpos))))
+                {
+                    err = ST_FORMAT;            /* which rule, and the status, are the fallback's to say */
+                    break;
+                }
+                const uint32_t bigmask = __ballot_sync(CRYO_FULL, !have || my_ll > ZP4_BIG_LL || my_ml > ZP4_BIG_ML);
+                uint32_t k0 = 0;
+
+                while (k0 < g)
+                {
+                    /* the longest run of ordinary sequences from k0 whose output fits the span and
+                     * whose literals fit the window */
+                    const uint32_t pos0 = __shfl_sync(CRYO_FULL, my_start, (int) k0);
+                    const uint32_t lit0 = __shfl_sync(CRYO_FULL, my_lit, (int) k0);
+                    const uint32_t lip0 = L.delta + lit0, wb = lip0 & ~15u;
+                    const bool     fits = my_epos - pos0 <= ZP4_SPAN && L.delta + my_lit + my_ll - wb <= ZP4_LITWIN;
+                    const uint32_t stop = (bigmask | __ballot_sync(CRYO_FULL, !fits)) & (~0u << k0);
+                    const uint32_t k1 = stop ? (uint32_t) __ffs((int) stop) - 1u : 32u;   /* first lane not in the run */
+
+                    if (k1 == k0 || L.rle || pos0 != o.pos)
+                    {
+                        /* one sequence through the general executor */
+                        const uint32_t ll = __shfl_sync(CRYO_FULL, my_ll, (int) k0);
+                        const uint32_t ml = __shfl_sync(CRYO_FULL, my_ml, (int) k0);
+                        const uint32_t moff = __shfl_sync(CRYO_FULL, my_off, (int) k0);
+
+                        L.pos = lit0;
+                        zsw_lits_emit(o, L, ll, lane);
+                        wx_match(o, moff, ml, lane);
+                        k0++;
                         continue;
                     }
-                    L.pos = lpos;
-                    zsw_lits_emit(o, L, ll, lane);
-                    lpos += ll;
-                    wx_match(o, moff, ml, lane);
+                    const bool     in = lane >= k0 && lane < k1;
+                    const uint32_t end = __shfl_sync(CRYO_FULL, my_epos, (int) (k1 - 1u));
+                    const uint32_t litend = __shfl_sync(CRYO_FULL, my_lit + my_ll, (int) (k1 - 1u));
+
+                    /* literals of the run -> window (coalesced), then every lane places its own */
+                    __syncwarp();
+                    for (uint32_t w = 16u * lane; wb + w < L.delta + litend; w += 512u)
+                        if (wb + w < L.lim)
+                            st16(L.win + w, ld16(L.abase + wb + w));
+                    L.wvalid = false;           /* the slow path's window bookkeeping no longer holds */
+                    __syncwarp();
+                    {
+                        const uint32_t maxll = __reduce_max_sync(CRYO_FULL, in ? my_ll : 0u);
+                        const uint8_t *ls = L.win + (L.delta + my_lit - wb);
+
+                        for (uint32_t i = 0; i < maxll; i++)
+                            if (in && i < my_ll)
+                                o.ring[(my_start + i) & WX_RMASK] = ls[i];
+                    }
+                    __syncwarp();
+                    /*
+                     * Matches.  A source byte is in the ring if it is at or above `floor` (everything
+                     * below o.flushed is in global memory, and floor < o.flushed).  A short match whose
+                     * source ends at or below the start of the run depends on nothing the run writes:
+                     * all of those go first, one per lane, with the global loads of a step issued
+                     * together (match-rich data takes most sources from far behind, and serving them
+                     * one after the other would cost an L2 round trip per sequence).  The others
+                     * follow in order, each a warp-wide move.
+                     */
+                    const uint32_t floor0 = end + 64u > WX_RING ? end + 64u - WX_RING : 0u;
+                    const uint32_t floor = floor0 > o.lo ? floor0 : o.lo;
+                    const uint32_t my_sp = my_mpos - my_off;
+                    const bool     indep = in && my_ml <= ZP4_LANE_ML && my_sp + my_ml <= pos0;
+                    {
+                        const uint32_t maxml = __reduce_max_sync(CRYO_FULL, indep ? my_ml : 0u);
+
+                        for (uint32_t i0 = 0; i0 < maxml; i0 += 16)
+                        {
+                            uint8_t v[16];
+
+#pragma unroll
+                            for (uint32_t q = 0; q < 16; q++)
+                            {
+                                const uint32_t x = my_sp + i0 + q;
+
+                                v[q] = (indep && i0 + q < my_ml) ? (x >= floor ? o.ring[x & WX_RMASK] : o.out[x]) : (uint8_t) 0;
+                            }
+#pragma unroll
+                            for (uint32_t q = 0; q < 16; q++)
+                                if (indep && i0 + q < my_ml)
+                                    o.ring[(my_mpos + i0 + q) & WX_RMASK] = v[q];
+                        }
+                    }
+                    __syncwarp();
+                    for (uint32_t dep = __ballot_sync(CRYO_FULL, in && !indep); dep; dep &= dep - 1)
+                    {
+                        const int      k = __ffs((int) dep) - 1;
+                        const uint32_t mpos = __shfl_sync(CRYO_FULL, my_mpos, k);
+                        const uint32_t moff = __shfl_sync(CRYO_FULL, my_off, k);
+                        const uint32_t ml = __shfl_sync(CRYO_FULL, my_ml, k);
+                        const uint32_t sp = mpos - moff;
+
+                        if (moff >= ml)
+                        {
+                            /* no overlap: up to ZP4_BIG_ML / 32 independent moves */
+                            for (uint32_t i = lane; i < ml; i += 32)
+                            {
+                                const uint32_t x = sp + i;
+
+                                o.ring[(mpos + i) & WX_RMASK] = x >= floor ? o.ring[x & WX_RMASK] : o.out[x];
+                            }
+                        }
+                        else
+                        {
+                            /* overlap: every byte is one of the moff bytes before mpos */
+                            uint32_t r = lane % moff;
+                            const uint32_t step = 32u % moff;
+
+                            for (uint32_t i = lane; i < ml; i += 32)
+                            {
+                                const uint32_t x = sp + r;
+
+                                o.ring[(mpos + i) & WX_RMASK] = x >= floor ? o.ring[x & WX_RMASK] : o.out[x];
+                                r += step;
+                                r = r >= moff ? r - moff : r;
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    o.pos = end;
+                    wx_drain(o, lane);
+                    k0 = k1;
                 }
+                lpos = base_lit + __shfl_sync(CRYO_FULL, lcum, 31);
             }
             L.pos = lpos;
             if (err != ST_OK)

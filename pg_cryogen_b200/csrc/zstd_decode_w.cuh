@@ -541,13 +541,6 @@ CRYO_DEV bool zsw_huf_stream(const uint16_t *huf, int log, const uint8_t *src, u
 
     wi--;
     nextw = wi >= 0 ? wb[wi] : 0u;
-#ifndef CRYO_EMU
-    /* the two sectors below the one just touched (see ZSW_HPREFETCH) */
-    if (wi >= 8)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + wi - 8));
-    if (wi >= 16)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + wi - 16));
-#endif
     const uint32_t sh = 32u - (uint32_t) log;
     uint32_t i = 0;
 
@@ -563,12 +556,7 @@ CRYO_DEV bool zsw_huf_stream(const uint16_t *huf, int log, const uint8_t *src, u
 #ifdef CRYO_EMU
 #define ZSW_HPREFETCH()
 #else
-/* L1 fills by 32-byte sector: ask for the sector three below at every refill (8 refills share a
- * sector), so the dependent word loads hit L1.  A miss stalls every lane of the warp, and with
- * one stream per lane (zstd_decode_p.cuh) the lanes would take their misses at different times. */
-#define ZSW_HPREFETCH()                                                      \
-    if (wi >= 24)                                                            \
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(wb + wi - 24));
+#define ZSW_HPREFETCH()
 #endif
 #define ZSW_HREFILL()                                                        \
     if (avail <= 32)                                                         \

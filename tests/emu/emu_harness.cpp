@@ -338,6 +338,8 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     std::vector<uint16_t> huftab((size_t) n * ZP_MAXB * 2048, 0x3333);
     std::vector<uint32_t> fsetab((size_t) n * ZP_MAXB * ZP3_CELLS, 0x44444444);
     unsigned long long    seq_alloc = 0;
+    unsigned int          pf_count[4] = {0, 0, 0, 0};
+    std::vector<uint32_t> pf_list((size_t) n * ZP_MAXB, 0xABABABAB);
     ZpArgs a;
 
     a.methods = methods.data();
@@ -355,6 +357,8 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     a.flag = flag.data();
     a.seqbase = seqbase.data();
     a.seq_alloc = &seq_alloc;
+    a.pf_count = &pf_count[2];
+    a.pf_list = pf_list.data();
     a.lit = (uint8_t *) ((((uintptr_t) lit.data() + 15) & ~(uintptr_t) 15));
     a.lit_stride = lit_stride;
     a.seq = seq.data();
@@ -370,8 +374,9 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
         if (f < a.n)
             zp_stage1(a, f);
     });
-    emu::launch(dim3((unsigned) n * ZP_MAXB), dim3(128), 0, [&]() {
-        zp_stage0(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, threadIdx.x, 128);
+    emu::launch(dim3(3), dim3(128), 0, [&]() {
+        for (uint32_t w = blockIdx.x; w < pf_count[2]; w += 3)
+            zp_stage0(a, pf_list[w], threadIdx.x, 128);
     });
     emu::launch(dim3((unsigned) n * ZP_MAXB / ZP2A_WARPS), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, w = blockIdx.x * ZP2A_WARPS + warp;
@@ -384,10 +389,10 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, w = blockIdx.x * ZP3A_WARPS + warp;
         zp_stage3a(a, w / ZP_MAXB, w % ZP_MAXB, CRYO_SMEM_BASE() + warp * ZP3A_PER_WARP, lane);
     });
-    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP_G * ZP3B_SMALL * 4, [&]() {
+    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP3B_SMEM(ZP3B_SMALL), [&]() {
         zp_stage3b<ZP3B_SMALL, 0>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
-    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP_G * ZP3B_LARGE * 4, [&]() {
+    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP3B_SMEM(ZP3B_LARGE), [&]() {
         zp_stage3b<ZP3B_LARGE, ZP3B_SMALL>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
     emu::launch(dim3(((unsigned) n + ZP4_WARPS - 1) / ZP4_WARPS), dim3(ZP4_THREADS), ZP4_SMEM, [&]() {

@@ -1,0 +1,44 @@
+"""dev tool (GPU box): build libcryogpu with -DZP_TIMELINE into a scratch .so, run the headline batch,
+print when each pipeline kernel started / ended (GPU global timer, microseconds from the first start)."""
+import ctypes as C, os, subprocess, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+so = os.path.join(ROOT, "gpurun_out", "libcryogpu_tl.so")
+os.makedirs(os.path.dirname(so), exist_ok=True)
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DZP_TIMELINE",
+                       "-Xcompiler", "-fPIC", "-diag-suppress", "550", "-shared", "-o", so,
+                       os.path.join(ROOT, "pg_cryogen_b200", "csrc", "cryogpu.cu")])
+import benchdata
+from pg_cryogen_b200 import CryoGPU, blockgen as bg, codec
+from pg_cryogen_b200.codec import pack_chunks
+codec.lib_path = lambda: so
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+kind, payload = (sys.argv[2], sys.argv[3]) if len(sys.argv) > 3 else ("S", "hex")
+nblk = bg.table_block_count(rows, kind)
+chunks, plain = benchdata.build_table(rows, kind, payload, 1, 1, threads=16)
+buf, offs, sizes = pack_chunks(chunks)
+gpu = CryoGPU(0)
+L = gpu.lib
+assert hasattr(L, "cryogpu_debug_timeline"), "timeline build not loaded"
+dev = torch.device("cuda:0")
+d_src = torch.from_numpy(buf).to(dev); d_off = torch.from_numpy(offs.view(np.int64)).to(dev)
+d_sz = torch.from_numpy(sizes.view(np.int32)).to(dev); d_me = torch.full((nblk,), 1, dtype=torch.int32, device=dev)
+d_dst = torch.empty((nblk, 1 << 20), dtype=torch.uint8, device=dev)
+d_osz = torch.zeros((nblk,), dtype=torch.int32, device=dev); d_st = torch.full((nblk,), -1, dtype=torch.int32, device=dev)
+s = torch.cuda.current_stream().cuda_stream
+names = ["parse", "prefill", "huftab", "literals", "fsetab", "seq_small", "seq_large", "execute"]
+for it in range(4):
+    L.cryogpu_debug_timeline(None, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gpu.decompress_device(d_me, d_src, d_off, d_sz, d_dst, 1 << 20, d_osz, d_st, nblk, stream=s)
+    e1.record(); torch.cuda.synchronize()
+    out = (C.c_ulonglong * 32)()
+    L.cryogpu_debug_timeline(out, 0)
+    t0 = min(out[2 * k] for k in range(8) if out[2 * k + 1])
+    print(f"iteration {it}: {e0.elapsed_time(e1) * 1e3:.0f} us by events")
+    for k, nm in enumerate(names):
+        if out[2 * k + 1]:
+            print(f"   {nm:10s} start {(out[2*k]-t0)/1e3:8.1f}  end {(out[2*k+1]-t0)/1e3:8.1f}  ({(out[2*k+1]-out[2*k])/1e3:7.1f} us)")
+assert bool((d_st == 0).all().item())
