@@ -174,16 +174,38 @@ k_zp_parse(const ZpArgs a)
     ZP_TL_END(0)
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 8)
 k_zp_prefill(const ZpArgs a)
 {
     ZP_TL_BEGIN(1)
-    /* persistent: HBM-bound stores need few warps, and the SM's warp slots are left to the
-     * latency-bound stages that run beside this one */
-    const uint32_t count = *a.pf_count;
+    /* persistent, few CTAs per SM: HBM-bound stores need few warps.  Frames are taken in index
+     * order, which is the order the executor's CTAs are dispatched in, so that a frame's blocks
+     * are there by the time its warp asks for them. */
+    __shared__ uint32_t spec[ZP_MAXB];
 
-    for (uint32_t w = blockIdx.x; w < count; w += gridDim.x)
-        zp_stage0(a, a.pf_list[w], threadIdx.x, 256);
+    for (uint32_t f = blockIdx.x; f < a.n; f += gridDim.x)
+    {
+        const uint32_t nb = a.fr[(size_t) f * ZP_FF];
+
+        __syncthreads();
+        if (threadIdx.x < ZP_MAXB)
+            spec[threadIdx.x] = threadIdx.x < nb ? a.blk[((size_t) f * ZP_MAXB + threadIdx.x) * ZP_BF + ZPB_SPECPOS] : ~0u;
+        __syncthreads();
+        uint32_t did = 0;
+
+        for (uint32_t j = 0; j < nb; j++)
+        {
+            if (spec[j] == ~0u)
+                continue;
+            zp_stage0(a, (f << 8) | j, threadIdx.x, 256);
+            did++;
+        }
+        /* one release per frame: every thread's stores, then the count */
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0 && did)
+            zp_stage0_done(a, f << 8, did);
+    }
     ZP_TL_END(1)
 }
 
@@ -234,7 +256,7 @@ k_zp_sequences_large(const ZpArgs a)
     ZP_TL_END(6)
 }
 
-__global__ void __launch_bounds__(ZP4_THREADS)
+__global__ void __maxnreg__(72)
 k_zp_execute(const ZpArgs a)
 {
     ZP_TL_BEGIN(7)
@@ -425,7 +447,7 @@ zp_al(size_t v)
 static size_t
 zp_bytes(size_t n, uint32_t cap)
 {
-    return zp_al(n * ZP_FF * 4) + zp_al(n * 4) + zp_al(n * 8) + 256 + zp_al(n * ZP_MAXB * 4) + zp_al(n * ZP_MAXB * ZP_BF * 4) +
+    return zp_al(n * ZP_FF * 4) + 2 * zp_al(n * 4) + zp_al(n * 8) + 256 + zp_al(n * ZP_MAXB * ZP_BF * 4) +
            zp_al(n * zp_lit_stride(cap)) + zp_al(zp_seq_cap(n, cap) * 8) + zp_al(n * ZP_MAXB * 4096) +
            zp_al(n * ZP_MAXB * ZP3_CELLS * 4);
 }
@@ -439,13 +461,12 @@ zp_carve(ZpArgs &a, void *base, size_t n, uint32_t cap)
     p += zp_al(n * ZP_FF * 4);
     a.flag = (uint32_t *) p;
     p += zp_al(n * 4);
+    a.pf_done = (uint32_t *) p;
+    p += zp_al(n * 4);
     a.seqbase = (uint64_t *) p;
     p += zp_al(n * 8);
     a.seq_alloc = (unsigned long long *) p;
-    a.pf_count = (unsigned int *) (p + 8);
     p += 256;
-    a.pf_list = (uint32_t *) p;
-    p += zp_al(n * ZP_MAXB * 4);
     a.blk = (uint32_t *) p;
     p += zp_al(n * ZP_MAXB * ZP_BF * 4);
     a.lit = p;
@@ -497,34 +518,54 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         a.status = status;
         a.predef = predef;
         zp_carve(a, zpbuf, n, cap);
-        cudaMemsetAsync(a.seq_alloc, 0, 16, st);
+        cudaMemsetAsync(a.seq_alloc, 0, 8, st);
         k_zp_parse<<<(unsigned) ((n + 31) / 32), 32, 0, st>>>(a);
-        /* literals (st), sequences (aux 0) and the raw / RLE blocks (aux 1) are independent of
-         * each other: the first two are bound by latency, the third by HBM */
+        /*
+         * literals (st) and sequences (aux 0) are independent of each other and bound by latency.
+         * The raw / RLE blocks (aux 1, one persistent CTA per SM) are bound by HBM and run beside
+         * the executor, which is bound by instruction issue and synchronises with them per frame
+         * through pf_done.  CRYOGPU_ZP_PREFILL_WITH=entropy runs them beside the entropy stages
+         * instead (measured slower on B200: a stage that saturates HBM stretches the memory
+         * latency the lockstep stages depend on; profiles/r01e_arrangements.txt).
+         */
+        static int pf_ctas = -1, pf_with_exec = 1;     /* tuning knobs */
+
+        if (pf_ctas < 0)
+        {
+            const char *e = getenv("CRYOGPU_ZP_PREFILL_CTAS"), *w = getenv("CRYOGPU_ZP_PREFILL_WITH");
+
+            pf_with_exec = !(w && strcmp(w, "entropy") == 0);
+            pf_ctas = e && atoi(e) > 0 ? atoi(e) : 1;
+        }
+        const unsigned pf_grid = (unsigned) std::min<size_t>(n, (size_t) pf_ctas * sm_count);
+
         cudaEventRecord(ev[0], st);
         cudaStreamWaitEvent(aux[0], ev[0], 0);
-        cudaStreamWaitEvent(aux[1], ev[0], 0);
         k_zp_fsetab<<<(unsigned) ((n + ZP3A_WARPS - 1) / ZP3A_WARPS) * ZP_MAXB, 32 * ZP3A_WARPS, ZP3A_SMEM, aux[0]>>>(a);
         k_zp_sequences_small<<<ngroups * ZP_MAXB, 32, ZP3B_SMEM(ZP3B_SMALL), aux[0]>>>(a);
         k_zp_sequences_large<<<ngroups * ZP_MAXB, 32, ZP3B_SMEM(ZP3B_LARGE), aux[0]>>>(a);
         cudaEventRecord(ev[1], aux[0]);
-        static int pf_ctas = -1, pf_late = -1;     /* tuning knobs (development) */
-        if (pf_ctas < 0)
+        if (!pf_with_exec)
         {
-            const char *e = getenv("CRYOGPU_ZP_PREFILL_CTAS"), *l = getenv("CRYOGPU_ZP_PREFILL_LATE");
-
-            pf_ctas = e ? atoi(e) : 2;
-            pf_late = l ? atoi(l) : 0;
+            cudaStreamWaitEvent(aux[1], ev[0], 0);
+            k_zp_prefill<<<pf_grid, 256, 0, aux[1]>>>(a);
+            cudaEventRecord(ev[2], aux[1]);
         }
-        if (pf_late)
-            cudaStreamWaitEvent(aux[1], ev[1], 0);      /* start the HBM-bound stage after the sequence stage */
-        k_zp_prefill<<<(unsigned) std::min<size_t>(n * ZP_MAXB, (size_t) pf_ctas * sm_count), 256, 0, aux[1]>>>(a);
-        cudaEventRecord(ev[2], aux[1]);
         k_zp_huftab<<<(unsigned) ((n + ZP2A_WARPS - 1) / ZP2A_WARPS) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
         k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
         cudaStreamWaitEvent(st, ev[1], 0);
-        cudaStreamWaitEvent(st, ev[2], 0);
+        if (pf_with_exec)
+        {
+            cudaEventRecord(ev[0], st);
+            cudaStreamWaitEvent(aux[1], ev[0], 0);
+            k_zp_prefill<<<pf_grid, 256, 0, aux[1]>>>(a);
+            cudaEventRecord(ev[2], aux[1]);
+        }
+        else
+            cudaStreamWaitEvent(st, ev[2], 0);
         k_zp_execute<<<(unsigned) ((n + ZP4_WARPS - 1) / ZP4_WARPS), ZP4_THREADS, ZP4_SMEM, st>>>(a);
+        if (pf_with_exec)
+            cudaStreamWaitEvent(st, ev[2], 0);
         /* frames the pipeline declined (flag set): decoded from scratch, one warp per frame */
         k_zstd_decode_w<<<(unsigned) ((n + ZSW_WARPS - 1) / ZSW_WARPS), ZSW_THREADS, ZSW_SMEM, st>>>(
             methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,

@@ -76,8 +76,7 @@ struct ZpArgs
     uint32_t       *flag;       /* n; non-zero: frame goes to the warp-per-frame decoder */
     uint64_t       *seqbase;    /* n; first entry of the frame in seq[] */
     unsigned long long *seq_alloc;
-    unsigned int   *pf_count;   /* entries in pf_list; zeroed with seq_alloc (adjacent) before stage 1 */
-    uint32_t       *pf_list;    /* raw / RLE blocks for stage 0: frame << 8 | block index */
+    uint32_t       *pf_done;    /* n; blocks of the frame stage 0 has finished (release / acquire with stage 4) */
     uint8_t        *lit;        /* n x lit_stride: Huffman-decoded literals */
     uint64_t        lit_stride; /* multiple of 16, >= cap + 16 * ZP_MAXB */
     uint64_t       *seq;        /* ll | ml << 17 | offset_value << 35 */
@@ -322,6 +321,7 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
 
     fr[0] = 0;
     a.flag[f] = 0;
+    a.pf_done[f] = 0;
     if (a.methods[f] != ZP_METHOD_ZSTD)
         return;
     uint32_t seq_total = 0;
@@ -336,23 +336,6 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
             ok = false;
         a.seqbase[f] = base;
     }
-    if (ok)
-    {
-        /* work list of stage 0 */
-        const uint32_t *blk = a.blk + (size_t) f * ZP_MAXB * ZP_BF;
-        uint32_t cnt = 0;
-
-        for (uint32_t j = 0; j < fr[0]; j++)
-            cnt += blk[j * ZP_BF + ZPB_SPECPOS] != ~0u;
-        if (cnt)
-        {
-            uint32_t at = atomicAdd(a.pf_count, cnt);
-
-            for (uint32_t j = 0; j < fr[0]; j++)
-                if (blk[j * ZP_BF + ZPB_SPECPOS] != ~0u)
-                    a.pf_list[at++] = (f << 8) | j;
-        }
-    }
     if (!ok)
     {
         fr[0] = 0;
@@ -365,10 +348,14 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
 /*
  * libzstd cuts a frame into full 128 KiB blocks (only the last one is short), so the output
  * position of a Raw or RLE block is known from the headers alone if that holds.  Stage 0
- * writes those blocks at the assumed position while stages 2 and 3 run (they are bound by
- * latency, this is bound by HBM); stage 4 skips a block when it arrives at exactly that
- * position and writes it itself otherwise (anything stage 0 wrote is then overwritten).
- * A few persistent CTAs per SM walk the work list stage 1 wrote (frames with f < 2^24).
+ * writes those blocks at the assumed position, at HBM speed, WHILE stage 4 runs (that one is
+ * bound by instruction issue).  Stage 4 skips a block when it arrives at exactly the assumed
+ * position (and writes it itself otherwise; anything stage 0 wrote is then overwritten).  It
+ * needs the bytes only when a later match may read them: before the next Compressed block of
+ * the frame it waits until pf_done[frame] says stage 0 has finished the blocks it skipped;
+ * should that take too long (stage 0 not scheduled yet) it writes them itself, which is
+ * idempotent, so no ordering between the two kernels is assumed.
+ * A few persistent CTAs per SM take the frames in index order (item = frame << 8 | block, f < 2^24).
  */
 CRYO_DEV void zp_stage0(const ZpArgs &a, uint32_t item, uint32_t tid, uint32_t nthr)
 {
@@ -381,6 +368,25 @@ CRYO_DEV void zp_stage0(const ZpArgs &a, uint32_t item, uint32_t tid, uint32_t n
         team_copy(dst, in, b[ZPB_BSIZE], tid, nthr);
     else
         team_fill_byte(dst, in[0], b[ZPB_BSIZE], tid, nthr);
+}
+
+/* after every thread of the CTA has finished (and fenced) `blocks` blocks of item's frame: one thread publishes them */
+CRYO_DEV void zp_stage0_done(const ZpArgs &a, uint32_t item, uint32_t blocks)
+{
+    __threadfence();
+    atomicAdd(a.pf_done + (item >> 8), blocks);
+}
+
+CRYO_DEV uint32_t zp_ld_acquire(const uint32_t *p)
+{
+#ifdef CRYO_EMU
+    return *reinterpret_cast<const volatile uint32_t *>(p);
+#else
+    uint32_t v;
+
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
 }
 
 /* --------------------------------------------------------------- stage 2: literals ---- */
@@ -1166,6 +1172,11 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 #define ZP4_SPAN        1024u                   /* output bytes of one sub-batch: it is written ahead of o.pos in the ring */
 #define ZP4_BIG_LL      96u                     /* longer runs leave the batch path */
 #define ZP4_BIG_ML      256u
+#ifdef CRYO_EMU
+#define ZP4_SPINS        4u
+#else
+#define ZP4_SPINS        8192u                  /* x 256 ns: about 2 ms, then stage 4 writes the blocks itself */
+#endif
 #define ZP4_LANE_ML     48u                     /* independent matches up to this long are copied by one lane each */
 
 /* stage 4 body: one warp, frame f */
@@ -1178,6 +1189,7 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
     WOut     o;
     int      err = ST_OK;
     uint32_t rep0 = 1, rep1 = 4, rep2 = 8;
+    uint32_t skipped = 0, confirmed = 0, skipmask = 0;     /* blocks left to stage 0 */
 
     wx_init(o, a.dst + (size_t) f * a.dst_stride, cap, smem);
     for (uint32_t j = 0; j < nb && err == ST_OK; j++)
@@ -1196,9 +1208,17 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                 continue;
             if (b[ZPB_SPECPOS] == o.pos)
             {
-                /* stage 0 wrote this block here already */
+                /* stage 0 writes this block here (it may not have yet): move on without touching
+                 * the output, the ring's tail comes from the block's own description */
                 wx_drain_all(o, lane);
-                wx_after_bulk(o, bsize, lane);
+                o.pos += bsize;
+                o.flushed = o.pos & ~15u;
+                o.lo = o.flushed;
+                if (lane < o.pos - o.flushed)
+                    o.ring[(o.flushed + lane) & WX_RMASK] = type == 0 ? in[off + bsize - (o.pos - o.flushed) + lane] : in[off];
+                __syncwarp();
+                skipped++;
+                skipmask |= 1u << j;
                 continue;
             }
             if (type == 0)
@@ -1206,6 +1226,38 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
             else
                 wx_fill_byte(o, in[off], bsize, lane);
             continue;
+        }
+        if (skipped > confirmed)
+        {
+            /* matches of this block may read what stage 0 writes: wait for it, or do it */
+            uint32_t seen = 0;
+
+            if (lane == 0)
+                for (uint32_t spin = 0; spin < ZP4_SPINS; spin++)
+                {
+                    seen = zp_ld_acquire(a.pf_done + f);
+                    if (seen >= skipped)
+                        break;
+                    __nanosleep(256);
+                }
+            seen = __shfl_sync(CRYO_FULL, seen, 0);
+            if (seen < skipped)
+            {
+                for (uint32_t jj = 0; jj < j; jj++)
+                {
+                    const uint32_t *bb = a.blk + ((size_t) f * ZP_MAXB + jj) * ZP_BF;
+
+                    if ((bb[ZPB_KIND] & 3u) < 2u && (skipmask >> jj) & 1u)
+                    {
+                        if ((bb[ZPB_KIND] & 3u) == 0)
+                            team_copy(o.out + bb[ZPB_SPECPOS], in + bb[ZPB_OFF], bb[ZPB_BSIZE], lane, 32);
+                        else
+                            team_fill_byte(o.out + bb[ZPB_SPECPOS], in[bb[ZPB_OFF]], bb[ZPB_BSIZE], lane, 32);
+                    }
+                }
+                __syncwarp();
+            }
+            confirmed = skipped;
         }
         const uint32_t lt = (kind >> 2) & 3u, regen = b[ZPB_REGEN], nseq = b[ZPB_NSEQ];
         const uint32_t block_start = o.pos;

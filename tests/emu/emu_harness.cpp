@@ -338,8 +338,7 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     std::vector<uint16_t> huftab((size_t) n * ZP_MAXB * 2048, 0x3333);
     std::vector<uint32_t> fsetab((size_t) n * ZP_MAXB * ZP3_CELLS, 0x44444444);
     unsigned long long    seq_alloc = 0;
-    unsigned int          pf_count[4] = {0, 0, 0, 0};
-    std::vector<uint32_t> pf_list((size_t) n * ZP_MAXB, 0xABABABAB);
+    std::vector<uint32_t> pf_done(n, 0xCDCDCDCD);
     ZpArgs a;
 
     a.methods = methods.data();
@@ -357,8 +356,7 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     a.flag = flag.data();
     a.seqbase = seqbase.data();
     a.seq_alloc = &seq_alloc;
-    a.pf_count = &pf_count[2];
-    a.pf_list = pf_list.data();
+    a.pf_done = pf_done.data();
     a.lit = (uint8_t *) ((((uintptr_t) lit.data() + 15) & ~(uintptr_t) 15));
     a.lit_stride = lit_stride;
     a.seq = seq.data();
@@ -374,10 +372,25 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
         if (f < a.n)
             zp_stage1(a, f);
     });
-    emu::launch(dim3(3), dim3(128), 0, [&]() {
-        for (uint32_t w = blockIdx.x; w < pf_count[2]; w += 3)
-            zp_stage0(a, pf_list[w], threadIdx.x, 128);
-    });
+    /* ZP_EMU_LATE_PREFILL: stage 0 runs after stage 4 (as if it were scheduled late), so stage 4
+     * times out waiting for it and writes the blocks it needs itself */
+    const bool late_prefill = getenv("ZP_EMU_LATE_PREFILL") != nullptr;
+    auto prefill = [&]() {
+        emu::launch(dim3(3), dim3(128), 0, [&]() {
+            for (uint32_t f = blockIdx.x; f < a.n; f += 3)
+                for (uint32_t j = 0; j < fr[(size_t) f * ZP_FF]; j++)
+                {
+                    if (blk[((size_t) f * ZP_MAXB + j) * ZP_BF + ZPB_SPECPOS] == ~0u)
+                        continue;
+                    zp_stage0(a, (f << 8) | j, threadIdx.x, 128);
+                    __syncthreads();
+                    if (threadIdx.x == 0)
+                        zp_stage0_done(a, (f << 8) | j, 1);
+                }
+        });
+    };
+    if (!late_prefill)
+        prefill();
     emu::launch(dim3((unsigned) n * ZP_MAXB / ZP2A_WARPS), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, w = blockIdx.x * ZP2A_WARPS + warp;
         zp_stage2a(a, w / ZP_MAXB, w % ZP_MAXB, CRYO_SMEM_BASE() + warp * ZP2A_PER_WARP, lane);
@@ -409,6 +422,8 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
                             (b[ZPB_KIND] >> 2) & 3, b[ZPB_REGEN], b[ZPB_HINFO] & 0xFF, b[ZPB_NSEQ], b[ZPB_SLOGS] & 0xFF,
                             (b[ZPB_SLOGS] >> 8) & 0xFF, (b[ZPB_SLOGS] >> 16) & 0x7F);
             }
+    if (late_prefill)
+        prefill();
     for (int i = 0; i < n; i++)
     {
         flags[i] = flag[i];

@@ -168,11 +168,15 @@ def _run_pipeline(L, comp, cap=MiB, shift=0):
     return list(st), list(osz), outs, list(fl)
 
 
-def test_emulated_pipeline_mixed_frames(oracle_ref):
+@pytest.mark.parametrize("late_prefill", [False, True])
+def test_emulated_pipeline_mixed_frames(oracle_ref, late_prefill, monkeypatch):
     """Eleven different frames through the phase-split pipeline in one batch: two entropy groups,
     lanes of one warp on different tables / streams / sequence counts; a truncated frame must
     fail alone (through the fallback), everything libzstd wrote at levels -5..3 must be decoded
-    by the pipeline itself (flag 0)."""
+    by the pipeline itself (flag 0).  late_prefill: the raw / RLE stage runs after the executor, which
+    must then time out waiting for it and write the blocks its matches read itself."""
+    if late_prefill:
+        monkeypatch.setenv("ZP_EMU_LATE_PREFILL", "1")
     L = _pipeline_lib()
     blocks = [bg.make_block("S", "hex", 31), np.zeros(MiB, dtype=np.uint8), bg.make_block("S", "lowcard", 32),
               bg.make_block("D", "random", 33), bg.regression_block(291, 500), bg.make_block("S", "hex", 34),
