@@ -147,6 +147,14 @@ int cryogpu_compress_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_a
 void cryogpu_last_transfer_bytes(const cryogpu_ctx *ctx, uint64_t *h2d, uint64_t *d2h);
 
 /*
+ * zstd frames of the last cryogpu_decompress_device call on this context: how many the
+ * phase-split pipeline was given, and how many of them it handed to the one-warp-per-frame
+ * decoder (irregular or malformed frames, see zstd_decode_p.cuh).  Waits for the device.
+ * Diagnostics for tests and benchmarks; the reference has no counterpart.
+ */
+int cryogpu_zstd_pipeline_stats(cryogpu_ctx *ctx, uint64_t *frames, uint64_t *fallback_frames);
+
+/*
  * Multi-GPU host variants: the batch is split into contiguous block ranges, one
  * per context (one host thread + stream per GPU, no collective).
  */

@@ -48,6 +48,7 @@ _PROTOS = {
                                           C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64,
                                           C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cryogpu_last_transfer_bytes": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "cryogpu_zstd_pipeline_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "cryogpu_decompress_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                           C.c_void_p]),
@@ -124,6 +125,15 @@ class CryoGPU:
         """(host->device, device->host) bytes of the last decompress_host call."""
         a, b = C.c_uint64(0), C.c_uint64(0)
         self.lib.cryogpu_last_transfer_bytes(self.handle, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
+    def zstd_pipeline_stats(self) -> tuple[int, int]:
+        """(zstd frames given to the phase-split pipeline, frames it handed to the fallback decoder)
+        of the last decompress_device call."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        rc = self.lib.cryogpu_zstd_pipeline_stats(self.handle, C.byref(a), C.byref(b))
+        if rc != 0:
+            raise CryoGPUError("cryogpu_zstd_pipeline_stats: " + self.lib.cryogpu_last_error().decode())
         return int(a.value), int(b.value)
 
     def close(self):

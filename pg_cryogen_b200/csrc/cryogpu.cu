@@ -688,6 +688,8 @@ struct cryogpu_ctx
     HostPool    *pool = nullptr;
     int          sparse = -1;           /* -1 unset, 0 off, 1 on (CRYOGPU_SPARSE_D2H) */
     uint64_t     last_h2d = 0, last_d2h = 0;
+    size_t       last_zp_n = 0;         /* frames of the last decompress_device call that took the pipeline */
+    uint32_t     last_zp_cap = 0;
 };
 
 static int
@@ -897,6 +899,37 @@ cryogpu_device(const cryogpu_ctx *ctx)
     return ctx ? ctx->device : -1;
 }
 
+extern "C" int
+cryogpu_zstd_pipeline_stats(cryogpu_ctx *ctx, uint64_t *frames, uint64_t *fallback_frames)
+{
+    if (!ctx)
+        return fail(CRYOGPU_E_ARG, "ctx is NULL");
+    uint64_t total = 0, fb = 0;
+
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    if (ctx->last_zp_n)
+    {
+        ZpArgs a;
+        std::vector<uint32_t> fr(ctx->last_zp_n * ZP_FF), flag(ctx->last_zp_n);
+
+        zp_carve(a, ctx->zp[0].p, ctx->last_zp_n, ctx->last_zp_cap);
+        CU(cudaMemcpy(fr.data(), a.fr, fr.size() * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(flag.data(), a.flag, flag.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < ctx->last_zp_n; i++)
+        {
+            /* a frame the pipeline kept has its block count in fr[0]; one it declined has the flag */
+            total += fr[i * ZP_FF] != 0 || flag[i] != 0;
+            fb += flag[i] != 0;
+        }
+    }
+    if (frames)
+        *frames = total;
+    if (fallback_frames)
+        *fallback_frames = fb;
+    return CRYOGPU_OK;
+}
+
 extern "C" void
 cryogpu_last_transfer_bytes(const cryogpu_ctx *ctx, uint64_t *h2d, uint64_t *d2h)
 {
@@ -972,6 +1005,8 @@ cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
                                                                          d_status);
     launch_lz4_decode(st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
                       d_out_size, d_status);
+    ctx->last_zp_n = zstd_kernel_variant() == 3 ? n : 0;
+    ctx->last_zp_cap = block_size;
     launch_zstd_decode(st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
                        d_out_size, d_status, (uint8_t *) ctx->scratch.p, ctx->predef, ctx->zp[0].p, ctx->zaux[0],
                        ctx->zev[0], ctx->sm_count);

@@ -190,3 +190,47 @@ def test_host_api_dense_batch_takes_the_plain_copy(gpu, oracle_ref):
     got, osz, st = gpu.decompress_host([1] * 6, comp)
     assert (st == 0).all() and np.array_equal(got, blocks)
     assert gpu.last_transfer_bytes()[1] >= blocks.size
+
+
+def test_zstd_pipeline_takes_what_libzstd_writes(gpu, oracle_ref):
+    """The phase-split pipeline (zstd_decode_p.cuh) must itself decode every frame libzstd writes
+    for cryo blocks at levels -5..3 (no hand-over to the one-warp-per-frame decoder), and hand
+    over exactly the frames it cannot take: Repeat_Mode tables (level 19 here), a truncated frame,
+    two concatenated frames.  Whatever path decodes a frame, bytes and status are the same."""
+    blocks, tags = _blocks()
+    chunks, want = [], []
+    for lv in (-5, -1, 1, 2, 3):
+        comp, _, _ = oracle_ref.compress(COMP_ZSTD, lv, blocks, nthreads=8)
+        chunks += comp
+        want += list(range(len(comp)))
+    out, osz, st = decode_device(gpu, COMP_ZSTD, chunks)
+    assert (st == 0).all() and (osz == CRYO_BLCKSZ).all()
+    for k in range(len(chunks)):
+        assert np.array_equal(out[k], blocks[want[k]]), k
+    frames, fallback = gpu.zstd_pipeline_stats()
+    assert frames == len(chunks) and fallback == 0, (frames, fallback)
+
+    z = oracle_ref.compress(COMP_ZSTD, 1, blocks[:1])[0][0]
+    hi = oracle_ref.compress(COMP_ZSTD, 19, bg.make_block("S", "lowcard", 3)[None, :])[0][0]
+    odd = [z, z[:-100].copy(), np.concatenate([z, z]), hi, z]
+    out, osz, st = decode_device(gpu, [COMP_ZSTD, COMP_ZSTD, COMP_ZSTD, COMP_ZSTD, COMP_LZ4], odd)
+    assert st[0] == 0 and st[1] != 0 and st[2] != 0 and st[3] == 0 and st[4] != 0
+    assert np.array_equal(out[0], blocks[0]) and np.array_equal(out[3], bg.make_block("S", "lowcard", 3))
+    frames, fallback = gpu.zstd_pipeline_stats()
+    assert frames == 4 and 2 <= fallback <= 3, (frames, fallback)
+
+
+def test_zstd_pipeline_large_batch_mixed_kinds(gpu, oracle_ref):
+    """A batch wide enough for several entropy groups per SM and for the raw / RLE stage to run
+    beside the executor: 600 frames cycling through every block kind and two levels."""
+    blocks, tags = _blocks()
+    comp1, _, _ = oracle_ref.compress(COMP_ZSTD, 1, blocks, nthreads=8)
+    comp3, _, _ = oracle_ref.compress(COMP_ZSTD, -3, blocks, nthreads=8)
+    pool = [(c, i) for i, c in enumerate(comp1)] + [(c, i) for i, c in enumerate(comp3)]
+    pick = [pool[(7 * k + k // 5) % len(pool)] for k in range(600)]
+    out, osz, st = decode_device(gpu, COMP_ZSTD, [c for c, _ in pick])
+    assert (st == 0).all() and (osz == CRYO_BLCKSZ).all()
+    for k, (_, i) in enumerate(pick):
+        assert np.array_equal(out[k], blocks[i]), (k, tags[i])
+    frames, fallback = gpu.zstd_pipeline_stats()
+    assert frames == 600 and fallback == 0
