@@ -213,11 +213,7 @@ __global__ void __launch_bounds__(32 * ZP2A_WARPS)
 k_zp_huftab(const ZpArgs a)
 {
     ZP_TL_BEGIN(2)
-    /* CTA = the same block index of 8 consecutive frames: its warps have work together or not at all */
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    zp_stage2a(a, (blockIdx.x / ZP_MAXB) * ZP2A_WARPS + warp, blockIdx.x % ZP_MAXB,
-               CRYO_SMEM_BASE() + warp * ZP2A_PER_WARP, lane);
+    zp_stage2a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     ZP_TL_END(2)
 }
 
@@ -233,10 +229,7 @@ __global__ void __launch_bounds__(32 * ZP3A_WARPS)
 k_zp_fsetab(const ZpArgs a)
 {
     ZP_TL_BEGIN(4)
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    zp_stage3a(a, (blockIdx.x / ZP_MAXB) * ZP3A_WARPS + warp, blockIdx.x % ZP_MAXB,
-               CRYO_SMEM_BASE() + warp * ZP3A_PER_WARP, lane);
+    zp_stage3a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     ZP_TL_END(4)
 }
 
@@ -244,7 +237,7 @@ __global__ void __launch_bounds__(32)
 k_zp_sequences_small(const ZpArgs a)
 {
     ZP_TL_BEGIN(5)
-    zp_stage3b<ZP3B_SMALL, 0>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    zp_stage3b<ZP3B_SMALL, 0, ZP3B_SMALL_LANES>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     ZP_TL_END(5)
 }
 
@@ -252,7 +245,7 @@ __global__ void __launch_bounds__(32)
 k_zp_sequences_large(const ZpArgs a)
 {
     ZP_TL_BEGIN(6)
-    zp_stage3b<ZP3B_LARGE, ZP3B_SMALL>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    zp_stage3b<ZP3B_LARGE, ZP3B_SMALL, ZP_G>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     ZP_TL_END(6)
 }
 
@@ -541,9 +534,10 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
 
         cudaEventRecord(ev[0], st);
         cudaStreamWaitEvent(aux[0], ev[0], 0);
-        k_zp_fsetab<<<(unsigned) ((n + ZP3A_WARPS - 1) / ZP3A_WARPS) * ZP_MAXB, 32 * ZP3A_WARPS, ZP3A_SMEM, aux[0]>>>(a);
-        k_zp_sequences_small<<<ngroups * ZP_MAXB, 32, ZP3B_SMEM(ZP3B_SMALL), aux[0]>>>(a);
-        k_zp_sequences_large<<<ngroups * ZP_MAXB, 32, ZP3B_SMEM(ZP3B_LARGE), aux[0]>>>(a);
+        k_zp_fsetab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP3A_WARPS, ZP3A_SMEM, aux[0]>>>(a);
+        k_zp_sequences_small<<<(unsigned) ((n + ZP3B_SMALL_LANES - 1) / ZP3B_SMALL_LANES) * ZP_MAXB, 32,
+                               ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), aux[0]>>>(a);
+        k_zp_sequences_large<<<ngroups * ZP_MAXB, 32, ZP3B_SMEM(ZP3B_LARGE, ZP_G), aux[0]>>>(a);
         cudaEventRecord(ev[1], aux[0]);
         if (!pf_with_exec)
         {
@@ -551,7 +545,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             k_zp_prefill<<<pf_grid, 256, 0, aux[1]>>>(a);
             cudaEventRecord(ev[2], aux[1]);
         }
-        k_zp_huftab<<<(unsigned) ((n + ZP2A_WARPS - 1) / ZP2A_WARPS) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
+        k_zp_huftab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
         k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
         cudaStreamWaitEvent(st, ev[1], 0);
         if (pf_with_exec)
@@ -732,7 +726,9 @@ set_kernel_attrs(cryogpu_ctx *ctx)
     CU(cudaFuncSetAttribute(k_zstd_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSTDD_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSW_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode_g, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSG_SMEM));
-    CU(cudaFuncSetAttribute(k_zp_sequences_large, cudaFuncAttributeMaxDynamicSharedMemorySize, ZP3B_SMEM(ZP3B_LARGE)));
+    CU(cudaFuncSetAttribute(k_zp_sequences_large, cudaFuncAttributeMaxDynamicSharedMemorySize, ZP3B_SMEM(ZP3B_LARGE, ZP_G)));
+    CU(cudaFuncSetAttribute(k_zp_sequences_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES)));
     /* the pipeline's kernels run side by side on one SM (zstd_decode_p.cuh): give them all the same
      * shared-memory carve-out, because an SM has to drain before it can change its L1 / shared split */
     {

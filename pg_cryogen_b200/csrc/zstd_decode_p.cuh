@@ -392,16 +392,19 @@ CRYO_DEV uint32_t zp_ld_acquire(const uint32_t *p)
 /* --------------------------------------------------------------- stage 2: literals ---- */
 
 /*
- * 2a: one warp per Huffman tree description: weights (lane 0), table filled by the warp
- *     straight into the block's slot of huftab (global, u16[2048] per slot); log and
- *     description length go into the block descriptor.
+ * 2a: one CTA per (32 frames x block index): the weights of the 32 trees decoded one lane per
+ *     tree, then each table filled by a warp straight into the block's slot of huftab (global,
+ *     u16[2048] per slot); log and description length go into the block descriptor.
  * 2b: one warp per (8 frames x block index), 32 lanes = 8 blocks x 4 streams, tables read
  *     through L1.  No shared memory: the stage co-resides with anything.
  */
 #define ZP2A_WARPS      8u
+#define ZP2A_LW         708u                    /* per tree: weights 256 | wfse 256 | wcounts 32 | wnext 128; odd word stride */
 #define ZP2A_DESC       176u                    /* staged tree description: 129 bytes at most + alignment slack */
-#define ZP2A_PER_WARP   (704u + 512u + 128u + ZP2A_DESC)    /* weights work | symstart u16[256] | rankc u32[32] | description */
-#define ZP2A_SMEM       (ZP2A_WARPS * ZP2A_PER_WARP)
+#define ZP2A_OFF_DESC   (32u * ZP2A_LW)         /* 22 656: multiple of 16 */
+#define ZP2A_OFF_WORK   (ZP2A_OFF_DESC + 32u * ZP2A_DESC)       /* per warp: symstart u16[256] | rankc u32[32] */
+#define ZP2A_OFF_META   (ZP2A_OFF_WORK + ZP2A_WARPS * 640u)
+#define ZP2A_SMEM       (ZP2A_OFF_META + 128u)
 
 /* Huffman weights of one tree description, one lane (RFC 8878 4.2.1).  Bytes used or 0. */
 CRYO_DEV uint32_t zp_huf_weights(const uint8_t *src, uint32_t n, uint8_t *weights, uint32_t *wfse,
@@ -473,46 +476,71 @@ CRYO_DEV uint32_t zp_huf_weights(const uint8_t *src, uint32_t n, uint8_t *weight
     return used;
 }
 
-/* stage 2a body: one warp, block j of frame f */
-CRYO_DEV void zp_stage2a(const ZpArgs &a, uint32_t f, uint32_t j, uint8_t *smem, uint32_t lane)
+/*
+ * stage 2a body: one CTA of ZP2A_WARPS warps, block index j of frames [g * 32, g * 32 + 32).
+ * Phase A, warp 0: lane i decodes the weights of frame g * 32 + i's tree (a serial chain per
+ * tree: 32 of them in lockstep instead of one per warp).  Phase B: the warps share out the 32
+ * tables, each filled by a whole warp straight into its global slot.
+ */
+CRYO_DEV void zp_stage2a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem, uint32_t tid)
 {
-    if (f >= a.n || a.fr[(size_t) f * ZP_FF] <= j)
-        return;
-    uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
-    const uint32_t kind = b[ZPB_KIND];
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
+    uint32_t *s_nw = reinterpret_cast<uint32_t *>(smem + ZP2A_OFF_META);        /* nw | used << 16, 0: nothing to build */
 
-    if ((kind & 3u) != 2u || ((kind >> 2) & 3u) != 2u)
-        return;                                 /* treeless blocks use the slot of the block that defined the tree */
-    uint32_t used = 0, nw = 0;
-    int32_t  log = 0;
-    /* the description (129 bytes at most) -> shared memory in one round trip: lane 0 then reads it
-     * byte by byte and backwards without waiting on HBM, which other stages keep busy meanwhile */
-    const uint8_t *gd = a.src + a.src_off[f] + b[ZPB_HDOFF];
-    const uint32_t dleft = b[ZPB_HDLEFT] < 130u ? b[ZPB_HDLEFT] : 130u;
-    const uint32_t dd = (uint32_t) ((uintptr_t) gd & 15u);
-    uint8_t *sd = smem + 704u + 512u + 128u;
-
-    if (16u * lane < dd + dleft)
-        st16(sd + 16u * lane, ld16(gd - dd + 16u * lane));
-    __syncwarp();
-    if (lane == 0)
-        used = zp_huf_weights(sd + dd, dleft, smem,
-                              reinterpret_cast<uint32_t *>(smem + 256), reinterpret_cast<int16_t *>(smem + 512),
-                              reinterpret_cast<uint16_t *>(smem + 544), &nw);
-    used = __shfl_sync(CRYO_FULL, used, 0);
-    nw = __shfl_sync(CRYO_FULL, nw, 0);
-    __syncwarp();
-    const bool ok = used != 0 &&
-                    zsw_huf_table(smem, nw, a.huftab + ((size_t) f * ZP_MAXB + j) * 2048u,
-                                  reinterpret_cast<uint16_t *>(smem + 704), reinterpret_cast<uint32_t *>(smem + 1216),
-                                  &log, lane);
-
-    if (lane == 0)
+    if (warp == 0)
     {
-        if (ok)
-            b[ZPB_HINFO] = (uint32_t) log | (used << 8);
-        else
-            a.flag[f] = 1;
+        const uint32_t f = g * 32u + lane;
+        uint32_t meta = 0;
+
+        if (f < a.n && a.fr[(size_t) f * ZP_FF] > j)
+        {
+            const uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
+            const uint32_t kind = b[ZPB_KIND];
+
+            /* treeless blocks use the slot of the block that defined the tree */
+            if ((kind & 3u) == 2u && ((kind >> 2) & 3u) == 2u)
+            {
+                /* the description (129 bytes at most) -> shared memory, then the serial part from there */
+                const uint8_t *gd = a.src + a.src_off[f] + b[ZPB_HDOFF];
+                const uint32_t dleft = b[ZPB_HDLEFT] < 130u ? b[ZPB_HDLEFT] : 130u;
+                const uint32_t dd = (uint32_t) ((uintptr_t) gd & 15u);
+                uint8_t *sd = smem + ZP2A_OFF_DESC + lane * ZP2A_DESC;
+                uint8_t *lw = smem + lane * ZP2A_LW;
+                uint32_t used, nw = 0;
+
+                for (uint32_t k = 0; k < dd + dleft; k += 16)
+                    st16(sd + k, ld16(gd - dd + k));
+                used = zp_huf_weights(sd + dd, dleft, lw, reinterpret_cast<uint32_t *>(lw + 256),
+                                      reinterpret_cast<int16_t *>(lw + 512), reinterpret_cast<uint16_t *>(lw + 544), &nw);
+                if (used == 0)
+                    a.flag[f] = 1;
+                else
+                    meta = nw | (used << 16);
+            }
+        }
+        s_nw[lane] = meta;
+    }
+    __syncthreads();
+    for (uint32_t t = warp; t < 32u; t += ZP2A_WARPS)
+    {
+        const uint32_t meta = s_nw[t];
+
+        if (meta == 0)
+            continue;
+        const uint32_t f = g * 32u + t;
+        int32_t    log = 0;
+        const bool ok = zsw_huf_table(smem + t * ZP2A_LW, meta & 0xFFFFu, a.huftab + ((size_t) f * ZP_MAXB + j) * 2048u,
+                                      reinterpret_cast<uint16_t *>(smem + ZP2A_OFF_WORK + warp * 640u),
+                                      reinterpret_cast<uint32_t *>(smem + ZP2A_OFF_WORK + warp * 640u + 512u), &log, lane);
+
+        if (lane == 0)
+        {
+            if (ok)
+                a.blk[((size_t) f * ZP_MAXB + j) * ZP_BF + ZPB_HINFO] = (uint32_t) log | ((meta >> 16) << 8);
+            else
+                a.flag[f] = 1;
+        }
+        __syncwarp();
     }
 }
 
@@ -803,56 +831,127 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 /* -------------------------------------------------------------- stage 3: sequences ---- */
 
 /*
- * 3a: one warp per block: the three table descriptions (lane 0 reads the counts), cells built
- *     by the warp in shared memory and copied to the block's slot of fsetab (global,
- *     LL u32[512] | OF u32[256] | ML u32[512]); logs and the bitstream offset go into the
- *     descriptor.
+ * 3a: one CTA per (32 frames x block index): the table descriptions of the 32 blocks read one
+ *     lane per block, then each table built by a warp in shared memory and copied to the
+ *     block's slot of fsetab (global, LL u32[512] | OF u32[256] | ML u32[512]); logs and the
+ *     bitstream offset go into the descriptor.
  * 3b: one LANE per block, 32 blocks (same block index of 32 frames) per warp, cells read
  *     through L1, (ll, ml, offset value) written to the frame's sequence area.
  */
 #define ZP3_CELLS       1280u                   /* u32 cells per block slot */
 #define ZP3A_WARPS      8u
-#define ZP3A_DESC       272u                    /* staged table descriptions */
-#define ZP3A_PER_WARP   (ZP3_CELLS * 4u + 128u + 128u + 144u + ZP3A_DESC)   /* cells | counts i16[64] | next u16[64] | cum u16[66] | descriptions */
-#define ZP3A_SMEM       (ZP3A_WARPS * ZP3A_PER_WARP)
+#define ZP3A_CNT        388u                    /* per block: counts i16[64] x 3; odd word stride */
+#define ZP3A_DESC       272u                    /* staged table descriptions per block */
+#define ZP3A_OFF_DESC   (32u * ZP3A_CNT)        /* 12 416: multiple of 16 */
+#define ZP3A_OFF_CELLS  (ZP3A_OFF_DESC + 32u * ZP3A_DESC)       /* per warp: u32[512], the table being built */
+#define ZP3A_OFF_WORK   (ZP3A_OFF_CELLS + ZP3A_WARPS * 2048u)   /* per warp: next u16[64] | cum u16[72] */
+#define ZP3A_OFF_META   (ZP3A_OFF_WORK + ZP3A_WARPS * 272u)
+#define ZP3A_SMEM       (ZP3A_OFF_META + 32u * 16u)
 
-/* stage 3a body: one warp, block j of frame f */
-CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t f, uint32_t j, uint8_t *smem, uint32_t lane)
+/*
+ * stage 3a body: one CTA of ZP3A_WARPS warps, block index j of frames [g * 32, g * 32 + 32).
+ * Phase A, warp 0: lane i reads the three table descriptions of frame g * 32 + i's block
+ * (serial bit parsing: 32 blocks in lockstep).  Phase B: the warps share out the 96 tables;
+ * each is built by a whole warp in shared memory and copied to the block's global slot.
+ */
+CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem, uint32_t tid)
 {
-    if (f >= a.n || a.fr[(size_t) f * ZP_FF] <= j)
-        return;
-    uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
-    const uint32_t kind = b[ZPB_KIND];
+    const uint32_t warp = tid >> 5, lane = tid & 31u;
+    uint32_t *s_meta = reinterpret_cast<uint32_t *>(smem + ZP3A_OFF_META);      /* per block: info[3] | bitoff */
 
-    if ((kind & 3u) != 2u || b[ZPB_NSEQ] == 0)
-        return;
-    /* the table descriptions (three FSE headers: well under 256 bytes) -> shared memory in one
-     * round trip; what follows them is the bitstream, which stage 3b reads */
-    const uint8_t *gd = a.src + a.src_off[f] + b[ZPB_OFF] + b[ZPB_SEQOFF];
-    const uint32_t full = b[ZPB_BSIZE] - b[ZPB_SEQOFF];
-    const uint32_t dd = (uint32_t) ((uintptr_t) gd & 15u);
-    uint8_t *sd = smem + ZP3_CELLS * 4u + 128u + 128u + 144u;
-    uint32_t left = full < 256u - 16u ? full : 256u - 16u, logs = 0;
-    const uint32_t staged = left;
-
-    if (16u * lane < dd + left && lane < 16u)
-        st16(sd + 16u * lane, ld16(gd - dd + 16u * lane));
-    __syncwarp();
-    const uint8_t *p = sd + dd;
-    uint32_t *cells = reinterpret_cast<uint32_t *>(smem);
-    int16_t  *counts = reinterpret_cast<int16_t *>(smem + ZP3_CELLS * 4u);
-    uint16_t *next = reinterpret_cast<uint16_t *>(smem + ZP3_CELLS * 4u + 128u);
-    uint16_t *cum = reinterpret_cast<uint16_t *>(smem + ZP3_CELLS * 4u + 256u);
-    bool      bad = false;
-
-#pragma unroll
-    for (int t = 0; t < 3; t++)
+    if (warp == 0)
     {
-        const uint32_t mode = (kind >> (14 - 2 * t)) & 3u;
-        const int max_log = t == 1 ? 8 : 9, max_sym = t == 0 ? 35 : t == 1 ? 31 : 52;
-        uint32_t *cell = cells + (t == 0 ? 0u : t == 1 ? 512u : 768u);
+        const uint32_t f = g * 32u + lane;
+        uint32_t info[3] = {0, 0, 0}, bitoff = 0;   /* info: 1 << 31 | mode << 24 | rle sym or (nsym << 8 | log) */
+
+        if (f < a.n && a.fr[(size_t) f * ZP_FF] > j)
+        {
+            const uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
+            const uint32_t kind = b[ZPB_KIND];
+
+            if ((kind & 3u) == 2u && b[ZPB_NSEQ] != 0)
+            {
+                /* the descriptions (three FSE headers: well under 256 bytes) -> shared memory; what
+                 * follows them is the bitstream, which stage 3b reads */
+                const uint8_t *gd = a.src + a.src_off[f] + b[ZPB_OFF] + b[ZPB_SEQOFF];
+                const uint32_t full = b[ZPB_BSIZE] - b[ZPB_SEQOFF];
+                const uint32_t dd = (uint32_t) ((uintptr_t) gd & 15u);
+                uint8_t *sd = smem + ZP3A_OFF_DESC + lane * ZP3A_DESC;
+                const uint32_t staged = full < ZP3A_DESC - 32u ? full : ZP3A_DESC - 32u;
+                uint32_t left = staged;
+                const uint8_t *p = sd + dd;
+                bool bad = false;
+
+                for (uint32_t k = 0; k < dd + staged; k += 16)
+                    st16(sd + k, ld16(gd - dd + k));
+#pragma unroll
+                for (int t = 0; t < 3; t++)
+                {
+                    const uint32_t mode = (kind >> (14 - 2 * t)) & 3u;
+                    const int max_log = t == 1 ? 8 : 9, max_sym = t == 0 ? 35 : t == 1 ? 31 : 52;
+
+                    if (bad)
+                        break;
+                    if (mode == 0)
+                        info[t] = 0x80000000u;
+                    else if (mode == 1)
+                    {
+                        if (left < 1 || p[0] > max_sym)
+                            bad = true;
+                        else
+                        {
+                            info[t] = 0x80000000u | (1u << 24) | p[0];
+                            p += 1;
+                            left -= 1;
+                        }
+                    }
+                    else
+                    {
+                        int32_t  nsym = 0, log = 0;
+                        const uint32_t used = fse_read_counts(p, left, max_log, max_sym,
+                                                              reinterpret_cast<int16_t *>(smem + lane * ZP3A_CNT + 128u * (uint32_t) t),
+                                                              &nsym, &log);
+
+                        if (used == 0)
+                            bad = true;
+                        else
+                        {
+                            info[t] = 0x80000000u | (2u << 24) | ((uint32_t) nsym << 8) | (uint32_t) log;
+                            p += used;
+                            left -= used;
+                        }
+                    }
+                }
+                if (bad)
+                {
+                    a.flag[f] = 1;
+                    info[0] = 0;
+                }
+                bitoff = b[ZPB_SEQOFF] + (staged - left);
+            }
+        }
+        s_meta[4 * lane + 0] = info[0];
+        s_meta[4 * lane + 1] = info[1];
+        s_meta[4 * lane + 2] = info[2];
+        s_meta[4 * lane + 3] = bitoff;
+    }
+    __syncthreads();
+    uint32_t *cell = reinterpret_cast<uint32_t *>(smem + ZP3A_OFF_CELLS + warp * 2048u);
+    uint16_t *next = reinterpret_cast<uint16_t *>(smem + ZP3A_OFF_WORK + warp * 272u);
+    uint16_t *cum = next + 64;
+
+    for (uint32_t w = warp; w < 96u; w += ZP3A_WARPS)
+    {
+        const uint32_t blkno = w / 3u, t = w % 3u;
+        const uint32_t info = s_meta[4 * blkno + t];
+
+        if (s_meta[4 * blkno] == 0)
+            continue;
+        const uint32_t mode = (info >> 24) & 3u;
+        const uint32_t f = g * 32u + blkno;
         int32_t   logv = 0;
 
+        __syncwarp();
         if (mode == 0)
         {
             const uint32_t n = t == 1 ? 32u : 64u, o = t == 0 ? 0u : t == 1 ? 64u : 96u;
@@ -863,75 +962,42 @@ CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t f, uint32_t j, uint8_t *smem,
         }
         else if (mode == 1)
         {
-            if (left < 1 || p[0] > max_sym)
-            {
-                bad = true;
-                break;
-            }
             if (lane == 0)
-                cell[0] = p[0];
-            p += 1;
-            left -= 1;
+                cell[0] = info & 0xFFu;
         }
         else
         {
-            int32_t  nsym = 0, log = 0;
-            uint32_t used = 0;
-
-            if (lane == 0)
-                used = fse_read_counts(p, left, max_log, max_sym, counts, &nsym, &log);
-            used = __shfl_sync(CRYO_FULL, used, 0);
-            nsym = __shfl_sync(CRYO_FULL, nsym, 0);
-            log = __shfl_sync(CRYO_FULL, log, 0);
-            if (used == 0)
-            {
-                bad = true;
-                break;
-            }
-            __syncwarp();
-            fse_build_table_warp(cell, counts, nsym, log, next, cum, lane);
-            logv = log;
-            p += used;
-            left -= used;
+            logv = (int32_t) (info & 0xFFu);
+            fse_build_table_warp(cell, reinterpret_cast<const int16_t *>(smem + blkno * ZP3A_CNT + 128u * t),
+                                 (int) ((info >> 8) & 0xFFu), logv, next, cum, lane);
         }
         __syncwarp();
-        /* extra-bit count of every cell's code into bits 26..30 (as zsw_seq_table) */
+        /* extra-bit count of every cell's code into bits 26..30 (as zsw_seq_table), and out to the slot */
+        uint32_t *slot = a.fsetab + ((size_t) f * ZP_MAXB + j) * ZP3_CELLS + (t == 0 ? 0u : t == 1 ? 512u : 768u);
+
         for (uint32_t k = lane; k < (1u << logv); k += 32)
         {
             const uint32_t c = cell[k], sym = c & 0xFFu;
             const uint32_t xb = t == 1 ? sym : (t == 0 ? CRYO_GLD(ZS_LL_PACK[sym]) : CRYO_GLD(ZS_ML_PACK[sym])) >> 24;
 
-            cell[k] = (c & 0x03FFFFFFu) | (xb << 26);
+            slot[k] = (c & 0x03FFFFFFu) | (xb << 26);
         }
-        __syncwarp();
-        logs |= (uint32_t) logv << (8 * t);
-    }
-    if (bad)
-    {
+        /* the logs: one word per block, assembled by whoever builds the block's tables (atomicOr: the
+         * three tables of a block may be built by different warps) */
         if (lane == 0)
-            a.flag[f] = 1;
-        return;
-    }
-    /* cells -> global slot (only the live part of each table) */
-    uint32_t *slot = a.fsetab + ((size_t) f * ZP_MAXB + j) * ZP3_CELLS;
+        {
+            uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
 
-    for (uint32_t k = lane; k < (1u << (logs & 0xFFu)); k += 32)
-        slot[k] = cells[k];
-    for (uint32_t k = lane; k < (1u << ((logs >> 8) & 0xFFu)); k += 32)
-        slot[512u + k] = cells[512u + k];
-    for (uint32_t k = lane; k < (1u << ((logs >> 16) & 0xFFu)); k += 32)
-        slot[768u + k] = cells[768u + k];
-    if (lane == 0)
-    {
-        b[ZPB_SLOGS] = logs | 0x80000000u;
-        b[ZPB_BITOFF] = b[ZPB_SEQOFF] + (staged - left);
+            atomicOr(&b[ZPB_SLOGS], ((uint32_t) logv << (8 * t)) | 0x80000000u);
+            if (t == 0)
+                b[ZPB_BITOFF] = s_meta[4 * blkno + 3];
+        }
     }
-    __syncwarp();
 }
 
 /*
- * stage 3b body: one warp, block index j of frames [g * ZP_G, g * ZP_G + ZP_G); lane i < ZP_G
- * walks frame g * ZP_G + i.  The live cells of the three tables are packed LL | OF | ML into
+ * stage 3b body: one warp, block index j of frames [g * LANES, g * LANES + LANES); lane i < LANES
+ * walks frame g * LANES + i (8 blocks per warp).  The live cells of the three tables are packed LL | OF | ML into
  * CELLS u32 of shared memory per block.  The kernel is launched once per size class (small:
  * what libzstd emits for sparse blocks, 6/6/7-bit tables; large: the 9/8/9-bit maximum) and a
  * warp runs in the smallest class that holds all its blocks, so the small class keeps many
@@ -946,17 +1012,18 @@ CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t f, uint32_t j, uint8_t *smem,
 #define ZP3B_LARGE      ZP3_CELLS
 #define ZP3B_WIN        256u
 #define ZP3B_WSTRIDE    (ZP3B_WIN / 4u + 1u)
-#define ZP3B_SMEM(cells) (ZP_G * (cells) * 4u + 32u * ZP3B_WSTRIDE * 4u)
+#define ZP3B_SMEM(cells, lanes) ((lanes) * (cells) * 4u + 32u * ZP3B_WSTRIDE * 4u)
+#define ZP3B_SMALL_LANES 8u                     /* blocks per warp in the small class (32 measured slower: 265 vs 221 us) */
 
-template <uint32_t CELLS, uint32_t BELOW>      /* this launch takes groups needing > BELOW and <= CELLS cells */
+template <uint32_t CELLS, uint32_t BELOW, uint32_t LANES>   /* groups of LANES frames needing > BELOW and <= CELLS cells */
 CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem, uint32_t lane)
 {
-    const uint32_t f = g * ZP_G + lane;
+    const uint32_t f = g * LANES + lane;
     const uint32_t *b = nullptr;
     uint32_t logs = 0, nseq = 0, need = 0;
     bool     act = false;
 
-    if (lane < ZP_G && f < a.n && a.fr[(size_t) f * ZP_FF] > j && a.flag[f] == 0)
+    if (lane < LANES && f < a.n && a.fr[(size_t) f * ZP_FF] > j && a.flag[f] == 0)
     {
         b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
         nseq = b[ZPB_NSEQ];
@@ -967,9 +1034,25 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
             need = act ? (1u << (logs & 0xFFu)) + (1u << ((logs >> 8) & 0xFFu)) + (1u << ((logs >> 16) & 0x7Fu)) : 0u;
         }
     }
-    const uint32_t gneed = __reduce_max_sync(CRYO_FULL, need);
+    /* the size class is decided for 32 consecutive frames (the small class's group), so that the
+     * two launches agree on who takes what */
+    uint32_t cneed = 0;
 
-    if (gneed == 0 || gneed > CELLS || gneed <= BELOW)
+    {
+        const uint32_t cf = (g * LANES / 32u) * 32u + lane;
+
+        if (cf < a.n && a.fr[(size_t) cf * ZP_FF] > j && a.flag[cf] == 0)
+        {
+            const uint32_t *cb = a.blk + ((size_t) cf * ZP_MAXB + j) * ZP_BF;
+            const uint32_t cl = cb[ZPB_SLOGS];
+
+            if ((cb[ZPB_KIND] & 3u) == 2u && cb[ZPB_NSEQ] != 0 && (cl & 0x80000000u))
+                cneed = (1u << (cl & 0xFFu)) + (1u << ((cl >> 8) & 0xFFu)) + (1u << ((cl >> 16) & 0x7Fu));
+        }
+    }
+    const uint32_t gneed = __reduce_max_sync(CRYO_FULL, cneed);
+
+    if (gneed == 0 || gneed > CELLS || gneed <= BELOW || __reduce_max_sync(CRYO_FULL, need) == 0)
         return;
     /* tables -> shared memory, the whole warp per block */
     for (uint32_t m = __ballot_sync(CRYO_FULL, act); m; m &= m - 1)
@@ -977,7 +1060,7 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         const int      i = __ffs((int) m) - 1;
         const uint32_t li = __shfl_sync(CRYO_FULL, logs, i);
         const uint32_t nl = 1u << (li & 0xFFu), no = 1u << ((li >> 8) & 0xFFu), nm = 1u << ((li >> 16) & 0x7Fu);
-        const uint32_t *slot = a.fsetab + ((size_t) (g * ZP_G + (uint32_t) i) * ZP_MAXB + j) * ZP3_CELLS;
+        const uint32_t *slot = a.fsetab + ((size_t) (g * LANES + (uint32_t) i) * ZP_MAXB + j) * ZP3_CELLS;
         uint32_t *cells = reinterpret_cast<uint32_t *>(smem) + (uint32_t) i * CELLS;
 
         for (uint32_t k = lane; k < nl; k += 32)
@@ -988,7 +1071,7 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
             cells[nl + no + k] = slot[768u + k];
     }
     const uint32_t ll_log = logs & 0xFFu, of_log = (logs >> 8) & 0xFFu, ml_log = (logs >> 16) & 0x7Fu;
-    const uint32_t *llt = reinterpret_cast<const uint32_t *>(smem) + (lane & (ZP_G - 1u)) * CELLS;
+    const uint32_t *llt = reinterpret_cast<const uint32_t *>(smem) + (lane & (LANES - 1u)) * CELLS;
     const uint32_t *oft = llt + (1u << ll_log), *mlt = oft + (1u << of_log);
     /* this lane's bitstream src[0, sn); positions are byte offsets from abase = src rounded down to 16 */
     const uint8_t *src = nullptr;
@@ -1007,7 +1090,7 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
             act = false;
         }
     }
-    uint32_t *win = reinterpret_cast<uint32_t *>(smem + ZP_G * CELLS * 4u) + lane * ZP3B_WSTRIDE;
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem + LANES * CELLS * 4u) + lane * ZP3B_WSTRIDE;
     const uint8_t *abase = src - ((uintptr_t) src & 15u);
     const int32_t  delta = (int32_t) ((uintptr_t) src & 15u);
     int32_t  npos = act ? (int32_t) ((delta + sn - 1u) & ~3u) : 0;

@@ -391,22 +391,21 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     };
     if (!late_prefill)
         prefill();
-    emu::launch(dim3((unsigned) n * ZP_MAXB / ZP2A_WARPS), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
-        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, w = blockIdx.x * ZP2A_WARPS + warp;
-        zp_stage2a(a, w / ZP_MAXB, w % ZP_MAXB, CRYO_SMEM_BASE() + warp * ZP2A_PER_WARP, lane);
+    emu::launch(dim3((((unsigned) n + 31) / 32) * ZP_MAXB), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
+        zp_stage2a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
     emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP2B_SMEM, [&]() {
         zp_stage2b(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
-    emu::launch(dim3((unsigned) n * ZP_MAXB / ZP3A_WARPS), dim3(32 * ZP3A_WARPS), ZP3A_SMEM, [&]() {
-        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, w = blockIdx.x * ZP3A_WARPS + warp;
-        zp_stage3a(a, w / ZP_MAXB, w % ZP_MAXB, CRYO_SMEM_BASE() + warp * ZP3A_PER_WARP, lane);
+    emu::launch(dim3((((unsigned) n + 31) / 32) * ZP_MAXB), dim3(32 * ZP3A_WARPS), ZP3A_SMEM, [&]() {
+        zp_stage3a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
-    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP3B_SMEM(ZP3B_SMALL), [&]() {
-        zp_stage3b<ZP3B_SMALL, 0>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    emu::launch(dim3((((unsigned) n + ZP3B_SMALL_LANES - 1) / ZP3B_SMALL_LANES) * ZP_MAXB), dim3(32),
+                ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), [&]() {
+        zp_stage3b<ZP3B_SMALL, 0, ZP3B_SMALL_LANES>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
-    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP3B_SMEM(ZP3B_LARGE), [&]() {
-        zp_stage3b<ZP3B_LARGE, ZP3B_SMALL>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP3B_SMEM(ZP3B_LARGE, ZP_G), [&]() {
+        zp_stage3b<ZP3B_LARGE, ZP3B_SMALL, ZP_G>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
     emu::launch(dim3(((unsigned) n + ZP4_WARPS - 1) / ZP4_WARPS), dim3(ZP4_THREADS), ZP4_SMEM, [&]() {
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
