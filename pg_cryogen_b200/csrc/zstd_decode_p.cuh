@@ -1012,7 +1012,7 @@ CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 #define ZP3B_LARGE      ZP3_CELLS
 #define ZP3B_WIN        256u
 #define ZP3B_WSTRIDE    (ZP3B_WIN / 4u + 1u)
-#define ZP3B_SMEM(cells, lanes) ((lanes) * (cells) * 4u + 32u * ZP3B_WSTRIDE * 4u)
+#define ZP3B_SMEM(cells, lanes) ((lanes) * (cells) * 4u + 32u * ZP3B_WSTRIDE * 4u + 96u * 4u)   /* cells | windows | LL, ML code tables */
 #define ZP3B_SMALL_LANES 8u                     /* blocks per warp in the small class (32 measured slower: 265 vs 221 us) */
 
 template <uint32_t CELLS, uint32_t BELOW, uint32_t LANES>   /* groups of LANES frames needing > BELOW and <= CELLS cells */
@@ -1177,7 +1177,6 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         ahi = ZP_FSHL_C(alo, ahi, n_);                                \
         alo = ZP_SHL_C(alo, n_);                                             \
         avail -= (int32_t) n_;                                               \
-        remaining -= (int32_t) n_;                                           \
     }
 #define ZP3B_ENSURE(on)                                                      \
     if (__any_sync(CRYO_FULL, (on) && npos - g0 < 12))                       \
@@ -1185,6 +1184,15 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         ZP3B_FILL();                                                         \
         cand = win[(npos - g0) >> 2];                                        \
     }
+    /* code -> baseline | extra bits << 24, from shared memory in the loop */
+    uint32_t *packs = reinterpret_cast<uint32_t *>(smem + LANES * CELLS * 4u + 32u * ZP3B_WSTRIDE * 4u);
+
+    for (uint32_t k = lane; k < 36u + 53u; k += 32)
+        packs[k] = k < 36u ? CRYO_GLD(ZS_LL_PACK[k]) : CRYO_GLD(ZS_ML_PACK[k - 36u]);
+    __syncwarp();
+    /* bits consumed are not counted per read: loaded bits minus what is left says it at the end
+     * (a walk that reads past the start of the stream never gets back to an exact balance) */
+    const int32_t total = remaining, loaded0 = avail, npos0 = npos;
     uint32_t sl = 0, so = 0, sm = 0;
 
     ZP3B_ENSURE(act);
@@ -1192,8 +1200,6 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
     ZP3B_READ(sl, act ? ll_log : 0u);
     ZP3B_READ(so, act ? of_log : 0u);
     ZP3B_READ(sm, act ? ml_log : 0u);
-    if (remaining < 0)
-        bad = true;
     uint64_t *out = act ? a.seq + a.seqbase[f] + b[ZPB_SEQPOS] : nullptr;
     const uint32_t maxseq = __reduce_max_sync(CRYO_FULL, nseq);
 
@@ -1206,32 +1212,33 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         ZP3B_ENSURE(on);
         const uint32_t cl = llt[sl], co = oft[so], cm = mlt[sm];
         const uint32_t xo = co >> 26, xm = cm >> 26, xl = cl >> 26;
-        uint32_t ov, ml, ll, t;
+        /* (a lane without work reads stale cells: keep its table indices in range) */
+        const uint32_t pl = packs[on ? cl & 0xFFu : 0u], pm = packs[36u + (on ? cm & 0xFFu : 0u)];
+        uint32_t ov, t;
 
         if (on && xo > 27)
             bad = true;                         /* beyond any window ZSTD_decompress accepts */
+        /* offset extra bits (up to 27) */
         ZP3B_REFILL(on);
         ZP3B_READ(ov, on ? (xo > 27 ? 27u : xo) : 0u);
         ov += 1u << (xo & 31u);
+        /* match-length then literal-length extra bits in one read (16 + 16 at most) */
         ZP3B_REFILL(on);
-        ZP3B_READ(ml, on ? xm : 0u);
-        ml += CRYO_GLD(ZS_ML_PACK[cm & 0xFFu]) & 0xFFFFFFu;
-        ZP3B_READ(ll, on ? xl : 0u);
-        ll += CRYO_GLD(ZS_LL_PACK[cl & 0xFFu]) & 0xFFFFFFu;
+        ZP3B_READ(t, on ? xm + xl : 0u);
+        const uint32_t ml = (pm & 0xFFFFFFu) + (t >> xl);
+        const uint32_t ll = (pl & 0xFFFFFFu) + (t & ((1u << xl) - 1u));
+        /* the three state updates in one read (9 + 9 + 8 bits at most): LL, ML, OF */
+        const uint32_t nbl = (cl >> 8) & 0xFFu, nbm = (cm >> 8) & 0xFFu, nbo = (co >> 8) & 0xFFu;
+
         ZP3B_REFILL(more);
-        ZP3B_READ(t, more ? (cl >> 8) & 0xFFu : 0u);
-        sl = more ? ((cl >> 16) & 0x3FFu) + t : sl;
-        ZP3B_READ(t, more ? (cm >> 8) & 0xFFu : 0u);
-        sm = more ? ((cm >> 16) & 0x3FFu) + t : sm;
-        ZP3B_READ(t, more ? (co >> 8) & 0xFFu : 0u);
-        so = more ? ((co >> 16) & 0x3FFu) + t : so;
+        ZP3B_READ(t, more ? nbl + nbm + nbo : 0u);
+        sl = more ? ((cl >> 16) & 0x3FFu) + (t >> (nbm + nbo)) : sl;
+        sm = more ? ((cm >> 16) & 0x3FFu) + ((t >> nbo) & ((1u << nbm) - 1u)) : sm;
+        so = more ? ((co >> 16) & 0x3FFu) + (t & ((1u << nbo) - 1u)) : so;
         if (on)
-        {
-            if (remaining < 0)
-                bad = true;
             out[i] = (uint64_t) ll | ((uint64_t) ml << 17) | ((uint64_t) (ov & 0x1FFFFFFFu) << 35);
-        }
     }
+    remaining = total - (loaded0 + 8 * (npos0 - npos) - avail);
 #undef ZP3B_FILL
 #undef ZP3B_REFILL
 #undef ZP3B_READ
