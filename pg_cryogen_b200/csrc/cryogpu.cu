@@ -527,7 +527,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         {
             const char *e = getenv("CRYOGPU_ZP_PREFILL_CTAS"), *w = getenv("CRYOGPU_ZP_PREFILL_WITH");
 
-            pf_with_exec = !(w && strcmp(w, "entropy") == 0);
+            pf_with_exec = (w && strcmp(w, "entropy") == 0) ? 0 : (w && strcmp(w, "all") == 0) ? 2 : 1;
             pf_ctas = e && atoi(e) > 0 ? atoi(e) : 1;
         }
         const unsigned pf_grid = (unsigned) std::min<size_t>(n, (size_t) pf_ctas * sm_count);
@@ -539,8 +539,10 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
                                ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), aux[0]>>>(a);
         k_zp_sequences_large<<<ngroups * ZP_MAXB, 32, ZP3B_SMEM(ZP3B_LARGE, ZP_G), aux[0]>>>(a);
         cudaEventRecord(ev[1], aux[0]);
-        if (!pf_with_exec)
+        if (pf_with_exec != 1)
         {
+            /* 0: beside the entropy stages, the executor waits for it; 2: started here, the executor
+             * does not wait for the whole of it (pf_done) */
             cudaStreamWaitEvent(aux[1], ev[0], 0);
             k_zp_prefill<<<pf_grid, 256, 0, aux[1]>>>(a);
             cudaEventRecord(ev[2], aux[1]);
@@ -548,14 +550,14 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         k_zp_huftab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
         k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
         cudaStreamWaitEvent(st, ev[1], 0);
-        if (pf_with_exec)
+        if (pf_with_exec == 1)
         {
             cudaEventRecord(ev[0], st);
             cudaStreamWaitEvent(aux[1], ev[0], 0);
             k_zp_prefill<<<pf_grid, 256, 0, aux[1]>>>(a);
             cudaEventRecord(ev[2], aux[1]);
         }
-        else
+        else if (pf_with_exec == 0)
             cudaStreamWaitEvent(st, ev[2], 0);
         k_zp_execute<<<(unsigned) ((n + ZP4_WARPS - 1) / ZP4_WARPS), ZP4_THREADS, ZP4_SMEM, st>>>(a);
         if (pf_with_exec)

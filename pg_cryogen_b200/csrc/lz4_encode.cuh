@@ -222,6 +222,31 @@ CRYO_DEV void lz4e_segment(const uint8_t *in, uint32_t len, uint32_t hist, int a
                 if (ne == 0)
                 {
                     ml += 32;
+                    /* long runs (the ~1 MB zero run of a sparse cryo block): 512 bytes per step, the
+                     * loads of a step issued together; stops at the first 128-byte group with a
+                     * mismatch or within 8 bytes of the limit, the bytewise step above finishes */
+                    for (bool stop = false; !stop;)
+                    {
+                        uint32_t x[4];
+
+#pragma unroll
+                        for (uint32_t u = 0; u < 4; u++)
+                        {
+                            const uint32_t i4 = mpos + ml + 128u * u + 4u * lane;
+
+                            x[u] = i4 + 8u <= matchlimit ? (lz4e_ld4(in + i4) ^ lz4e_ld4(in + i4 - off)) : 1u;
+                        }
+#pragma unroll
+                        for (uint32_t u = 0; u < 4; u++)
+                        {
+                            if (stop)
+                                break;
+                            if (__ballot_sync(CRYO_FULL, x[u] != 0) != 0)
+                                stop = true;
+                            else
+                                ml += 128u;
+                        }
+                    }
                     continue;
                 }
                 ml += (uint32_t) __ffs((int) ne) - 1u;

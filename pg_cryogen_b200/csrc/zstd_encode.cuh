@@ -410,6 +410,44 @@ CRYO_DEV uint32_t zse_fse_step(uint32_t &X, uint32_t s, const uint16_t *enc, con
 
 /* ---- match finder ------------------------------------------------------------ */
 
+/*
+ * Long runs: 512 bytes per step (4 groups of 4 bytes per lane, the 16 loads of a step issued
+ * together), used once a match has already run for a full 32-byte step.  The zero run of a
+ * sparse cryo block is ~1 MB: bytewise steps of 32 made it one dependent L2 round trip per
+ * 32 bytes, with the rest of the CTA waiting at the next barrier.  Stops at the first
+ * 128-byte group that holds a mismatch or reaches within 8 bytes of `len` (the unaligned
+ * 4-byte loads read up to the next aligned word); the caller's bytewise loop finishes.
+ */
+CRYO_DEV uint32_t zse_extend_wide(const uint8_t *in, uint32_t len, uint32_t pos, uint32_t off, uint32_t ml,
+                                  uint32_t lane)
+{
+    for (;;)
+    {
+        uint32_t x[4];
+        bool     stop = false;
+
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++)
+        {
+            const uint32_t idx = pos + ml + 128u * u + 4u * lane;
+
+            x[u] = idx + 8u <= len ? (zse_ld4(in + idx) ^ zse_ld4(in + idx - off)) : 1u;
+        }
+#pragma unroll
+        for (uint32_t u = 0; u < 4; u++)
+        {
+            if (stop)
+                break;
+            if (__ballot_sync(CRYO_FULL, x[u] != 0) != 0)
+                stop = true;
+            else
+                ml += 128u;
+        }
+        if (stop)
+            return ml;
+    }
+}
+
 /* warp-uniform forward extension of a match at (pos, pos - off): bytes beyond `have` */
 CRYO_DEV uint32_t zse_extend(const uint8_t *in, uint32_t len, uint32_t pos, uint32_t off, uint32_t have,
                              uint32_t lane)
@@ -425,6 +463,7 @@ CRYO_DEV uint32_t zse_extend(const uint8_t *in, uint32_t len, uint32_t pos, uint
         if (ne == 0)
         {
             ml += 32;
+            ml = zse_extend_wide(in, len, pos, off, ml, lane);
             continue;
         }
         return ml + (uint32_t) __ffs((int) ne) - 1u;
