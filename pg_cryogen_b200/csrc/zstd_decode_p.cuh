@@ -1498,9 +1498,15 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                         const uint32_t maxll = __reduce_max_sync(CRYO_FULL, in ? my_ll : 0u);
                         const uint8_t *ls = L.win + (L.delta + my_lit - wb);
 
-                        for (uint32_t i = 0; i < maxll; i++)
-                            if (in && i < my_ll)
-                                o.ring[(my_start + i) & WX_RMASK] = ls[i];
+                        const uint32_t nll = in ? my_ll : 0u;
+
+                        for (uint32_t i = 0; i < maxll; i += 4)
+                        {
+#pragma unroll
+                            for (uint32_t q = 0; q < 4; q++)
+                                if (i + q < nll)
+                                    o.ring[(my_start + i + q) & WX_RMASK] = ls[i + q];
+                        }
                     }
                     __syncwarp();
                     /*
@@ -1515,7 +1521,12 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                     const uint32_t floor0 = end + 64u > WX_RING ? end + 64u - WX_RING : 0u;
                     const uint32_t floor = floor0 > o.lo ? floor0 : o.lo;
                     const uint32_t my_sp = my_mpos - my_off;
-                    const bool     indep = in && my_ml <= ZP4_LANE_ML && my_sp + my_ml <= pos0;
+                    bool           indep = in && my_ml <= ZP4_LANE_ML && my_sp + my_ml <= pos0;
+
+                    /* worth a lane-per-sequence pass only if several lanes take part (the first match of
+                     * a run always qualifies) */
+                    if (__popc(__ballot_sync(CRYO_FULL, indep)) < 6)
+                        indep = false;
                     {
                         const uint32_t maxml = __reduce_max_sync(CRYO_FULL, indep ? my_ml : 0u);
 
