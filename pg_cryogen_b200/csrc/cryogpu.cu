@@ -174,18 +174,41 @@ k_zp_parse(const ZpArgs a)
     ZP_TL_END(0)
 }
 
-__global__ void __launch_bounds__(256, 8)
+/* bulk-copy engine (TMA) helpers for the raw / RLE stage: shared -> global, completion by bulk groups */
+#define ZP0_CHUNK 16384u
+
+__device__ __forceinline__ void
+zp0_bulk_store(uint8_t *dst, const uint8_t *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"((uint32_t) __cvta_generic_to_shared(smem_src)), "r"(bytes) : "memory");
+}
+
+#define ZP0_THREADS 128u                /* few registers beside the executor's three CTAs per SM */
+
+__global__ void __launch_bounds__(ZP0_THREADS)
 k_zp_prefill(const ZpArgs a)
 {
     ZP_TL_BEGIN(1)
-    /* persistent, few CTAs per SM: HBM-bound stores need few warps.  Frames are taken in index
-     * order, which is the order the executor's CTAs are dispatched in, so that a frame's blocks
-     * are there by the time its warp asks for them. */
+    /*
+     * Persistent, one CTA per SM.  Frames are taken in index order, which is the order the
+     * executor's CTAs are dispatched in.  RLE blocks (the zero runs of sparse cryo blocks: 73 % of
+     * the headline table's bytes) are written by the bulk-copy engine: a 16 KiB pattern in shared
+     * memory, one elected thread issuing cp.async.bulk stores of it, no LSU or register traffic on
+     * an SM that is executing sequences at the same time.  Two frames are kept in flight; a
+     * frame is published (pf_done) when its bulk group has completed.  Raw blocks and unaligned
+     * edges go through ordinary stores.
+     */
+    __shared__ __align__(128) uint8_t pat[ZP0_CHUNK];
     __shared__ uint32_t spec[ZP_MAXB];
+    int      cur = -1;                  /* byte the pattern holds */
+    uint32_t prev_f = ~0u, prev_did = 0;
 
     for (uint32_t f = blockIdx.x; f < a.n; f += gridDim.x)
     {
         const uint32_t nb = a.fr[(size_t) f * ZP_FF];
+        const uint8_t *in = a.src + a.src_off[f];
+        uint8_t *out = a.dst + (size_t) f * a.dst_stride;
 
         __syncthreads();
         if (threadIdx.x < ZP_MAXB)
@@ -197,14 +220,65 @@ k_zp_prefill(const ZpArgs a)
         {
             if (spec[j] == ~0u)
                 continue;
-            zp_stage0(a, (f << 8) | j, threadIdx.x, 256);
+            const uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
+            const uint32_t n = b[ZPB_BSIZE];
+            uint8_t *dst = out + spec[j];
+
             did++;
+            if ((b[ZPB_KIND] & 3u) == 0)
+            {
+                team_copy(dst, in + b[ZPB_OFF], n, threadIdx.x, ZP0_THREADS);
+                continue;
+            }
+            const int byte = in[b[ZPB_OFF]];
+
+            if (byte != cur)
+            {
+                /* new pattern: the engine must have read the old one out first */
+                if (threadIdx.x == 0)
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                __syncthreads();
+                const uint32_t w = (uint32_t) byte * 0x01010101u;
+
+                for (uint32_t k = threadIdx.x; k < ZP0_CHUNK / 16u; k += ZP0_THREADS)
+                    reinterpret_cast<uint4 *>(pat)[k] = make_uint4(w, w, w, w);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncthreads();
+                cur = byte;
+            }
+            /* edges by hand, the 16-byte aligned body by the engine */
+            const uint32_t head = (16u - (uint32_t) ((uintptr_t) dst & 15u)) & 15u;
+            const uint32_t h = head < n ? head : n, body = (n - h) & ~15u, tail = n - h - body;
+
+            if (threadIdx.x < h)
+                dst[threadIdx.x] = (uint8_t) byte;
+            if (threadIdx.x < tail)
+                dst[h + body + threadIdx.x] = (uint8_t) byte;
+            if (threadIdx.x == 0)
+                for (uint32_t o = 0; o < body; o += ZP0_CHUNK)
+                    zp0_bulk_store(dst + h + o, pat, body - o < ZP0_CHUNK ? body - o : ZP0_CHUNK);
         }
-        /* one release per frame: every thread's stores, then the count */
+        /* one bulk group per frame; publish the previous frame once at most this one is pending */
         __threadfence();
         __syncthreads();
-        if (threadIdx.x == 0 && did)
-            zp_stage0_done(a, f << 8, did);
+        if (threadIdx.x == 0)
+        {
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (prev_did)
+            {
+                asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                asm volatile("fence.proxy.async;" ::: "memory");
+                zp_stage0_done(a, prev_f << 8, prev_did);
+            }
+        }
+        prev_f = f;
+        prev_did = did;
+    }
+    if (threadIdx.x == 0 && prev_did)
+    {
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+        zp_stage0_done(a, prev_f << 8, prev_did);
     }
     ZP_TL_END(1)
 }
@@ -544,7 +618,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             /* 0: beside the entropy stages, the executor waits for it; 2: started here, the executor
              * does not wait for the whole of it (pf_done) */
             cudaStreamWaitEvent(aux[1], ev[0], 0);
-            k_zp_prefill<<<pf_grid, 256, 0, aux[1]>>>(a);
+            k_zp_prefill<<<pf_grid, ZP0_THREADS, 0, aux[1]>>>(a);
             cudaEventRecord(ev[2], aux[1]);
         }
         k_zp_huftab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
@@ -554,7 +628,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         {
             cudaEventRecord(ev[0], st);
             cudaStreamWaitEvent(aux[1], ev[0], 0);
-            k_zp_prefill<<<pf_grid, 256, 0, aux[1]>>>(a);
+            k_zp_prefill<<<pf_grid, ZP0_THREADS, 0, aux[1]>>>(a);
             cudaEventRecord(ev[2], aux[1]);
         }
         else if (pf_with_exec == 0)
