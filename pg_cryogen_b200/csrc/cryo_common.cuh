@@ -144,8 +144,16 @@ CRYO_DEV void team_fill_byte(uint8_t *dst, uint8_t b, uint32_t n, uint32_t tid, 
     uint32_t w = b * 0x01010101u;
     uint4 val = make_uint4(w, w, w, w);
 
-    for (uint32_t v = tid; v < nvec; v += nthr)
-        st16(d + 16 * (size_t) v, val);
+    if (n >= 8192u)
+    {
+        /* a long run streams through L2 (evict-first): what the same SMs are reading meanwhile
+         * (literals, sequences, match sources) should stay there */
+        for (uint32_t v = tid; v < nvec; v += nthr)
+            __stcs(reinterpret_cast<uint4 *>(d + 16 * (size_t) v), val);
+    }
+    else
+        for (uint32_t v = tid; v < nvec; v += nthr)
+            st16(d + 16 * (size_t) v, val);
     uint32_t done = head + (nvec << 4);
     if (tid < n - done)
         dst[done + tid] = b;

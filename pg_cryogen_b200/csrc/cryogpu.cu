@@ -162,6 +162,17 @@ __device__ unsigned long long zp_tl[32];
 #define ZP_TL_END(k)
 #endif
 
+/* defaults of the pipeline's knobs (each has an environment override, see launch_zstd_decode) */
+#ifndef ZP_HUF_X2_DEFAULT
+#define ZP_HUF_X2_DEFAULT 0
+#endif
+#ifndef ZP_L2HINT_DEFAULT
+#define ZP_L2HINT_DEFAULT 0
+#endif
+#ifndef ZP_EXEC_PREFETCH_DEFAULT
+#define ZP_EXEC_PREFETCH_DEFAULT 0
+#endif
+
 /* phase-split pipeline (default zstd path): zstd_decode_p.cuh */
 __global__ void __launch_bounds__(32)
 k_zp_parse(const ZpArgs a)
@@ -182,6 +193,15 @@ zp0_bulk_store(uint8_t *dst, const uint8_t *smem_src, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  ::"l"(dst), "r"((uint32_t) __cvta_generic_to_shared(smem_src)), "r"(bytes) : "memory");
+}
+
+/* the same with an L2 policy: the zero runs stream through, the literals and sequences the
+ * executor is reading at the same time should stay */
+__device__ __forceinline__ void
+zp0_bulk_store_hint(uint8_t *dst, const uint8_t *smem_src, uint32_t bytes, uint64_t policy)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 ::"l"(dst), "r"((uint32_t) __cvta_generic_to_shared(smem_src)), "r"(bytes), "l"(policy) : "memory");
 }
 
 #define ZP0_THREADS 128u                /* few registers beside the executor's three CTAs per SM */
@@ -255,8 +275,19 @@ k_zp_prefill(const ZpArgs a)
             if (threadIdx.x < tail)
                 dst[h + body + threadIdx.x] = (uint8_t) byte;
             if (threadIdx.x == 0)
-                for (uint32_t o = 0; o < body; o += ZP0_CHUNK)
-                    zp0_bulk_store(dst + h + o, pat, body - o < ZP0_CHUNK ? body - o : ZP0_CHUNK);
+            {
+                if (a.pf_hint & 1u)
+                {
+                    uint64_t policy;
+
+                    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+                    for (uint32_t o = 0; o < body; o += ZP0_CHUNK)
+                        zp0_bulk_store_hint(dst + h + o, pat, body - o < ZP0_CHUNK ? body - o : ZP0_CHUNK, policy);
+                }
+                else
+                    for (uint32_t o = 0; o < body; o += ZP0_CHUNK)
+                        zp0_bulk_store(dst + h + o, pat, body - o < ZP0_CHUNK ? body - o : ZP0_CHUNK);
+            }
         }
         /* one bulk group per frame; publish the previous frame once at most this one is pending */
         __threadfence();
@@ -295,7 +326,16 @@ __global__ void __launch_bounds__(32)
 k_zp_literals(const ZpArgs a)
 {
     ZP_TL_BEGIN(3)
-    zp_stage2b(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    zp_stage2b<false>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    ZP_TL_END(3)
+}
+
+/* two symbols per table lookup (zstd_decode_p.cuh, zp_stage2b<true>) */
+__global__ void __launch_bounds__(32)
+k_zp_literals_x2(const ZpArgs a)
+{
+    ZP_TL_BEGIN(3)
+    zp_stage2b<true>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     ZP_TL_END(3)
 }
 
@@ -585,6 +625,17 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         a.status = status;
         a.predef = predef;
         zp_carve(a, zpbuf, n, cap);
+        {
+            static int hint = -1;
+
+            if (hint < 0)
+            {
+                const char *e = getenv("CRYOGPU_ZP_PREFILL_L2HINT"), *x = getenv("CRYOGPU_ZP_EXEC_PREFETCH");
+
+                hint = (e ? atoi(e) != 0 : ZP_L2HINT_DEFAULT) | ((x ? atoi(x) != 0 : ZP_EXEC_PREFETCH_DEFAULT) << 1);
+            }
+            a.pf_hint = (uint32_t) hint;
+        }
         cudaMemsetAsync(a.seq_alloc, 0, 8, st);
         k_zp_parse<<<(unsigned) ((n + 31) / 32), 32, 0, st>>>(a);
         /*
@@ -622,7 +673,20 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             cudaEventRecord(ev[2], aux[1]);
         }
         k_zp_huftab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
-        k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
+        {
+            static int x2 = -1;                 /* CRYOGPU_ZP_HUF=x1 | x2: symbols per Huffman table lookup */
+
+            if (x2 < 0)
+            {
+                const char *e = getenv("CRYOGPU_ZP_HUF");
+
+                x2 = e ? strcmp(e, "x2") == 0 : ZP_HUF_X2_DEFAULT;
+            }
+            if (x2)
+                k_zp_literals_x2<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM_X(true), st>>>(a);
+            else
+                k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
+        }
         cudaStreamWaitEvent(st, ev[1], 0);
         if (pf_with_exec == 1)
         {
@@ -803,13 +867,14 @@ set_kernel_attrs(cryogpu_ctx *ctx)
     CU(cudaFuncSetAttribute(k_zstd_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSW_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode_g, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSG_SMEM));
     CU(cudaFuncSetAttribute(k_zp_sequences_large, cudaFuncAttributeMaxDynamicSharedMemorySize, ZP3B_SMEM(ZP3B_LARGE, ZP_G)));
+    CU(cudaFuncSetAttribute(k_zp_literals_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, ZP2B_SMEM_X(true)));
     CU(cudaFuncSetAttribute(k_zp_sequences_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES)));
     /* the pipeline's kernels run side by side on one SM (zstd_decode_p.cuh): give them all the same
      * shared-memory carve-out, because an SM has to drain before it can change its L1 / shared split */
     {
         const void *zp_kernels[] = {(const void *) k_zp_parse, (const void *) k_zp_prefill, (const void *) k_zp_huftab,
-                                    (const void *) k_zp_literals, (const void *) k_zp_fsetab,
+                                    (const void *) k_zp_literals, (const void *) k_zp_literals_x2, (const void *) k_zp_fsetab,
                                     (const void *) k_zp_sequences_small, (const void *) k_zp_sequences_large,
                                     (const void *) k_zp_execute, (const void *) k_zstd_decode_w};
 

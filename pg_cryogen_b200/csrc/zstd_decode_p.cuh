@@ -77,6 +77,8 @@ struct ZpArgs
     uint64_t       *seqbase;    /* n; first entry of the frame in seq[] */
     unsigned long long *seq_alloc;
     uint32_t       *pf_done;    /* n; blocks of the frame stage 0 has finished (release / acquire with stage 4) */
+    uint32_t        pf_hint;    /* bit 0: stage 0 bulk stores with the L2 evict_first policy; bit 1: stage 4 asks L2 for
+                                 * sequences and literals a few loads ahead */
     uint8_t        *lit;        /* n x lit_stride: Huffman-decoded literals */
     uint64_t        lit_stride; /* multiple of 16, >= cap + 16 * ZP_MAXB */
     uint64_t       *seq;        /* ll | ml << 17 | offset_value << 35 */
@@ -558,11 +560,22 @@ CRYO_DEV void zp_stage2a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
  */
 #define ZP2B_WIN        256u                    /* bytes of stream per lane window */
 #define ZP2B_WSTRIDE    (ZP2B_WIN / 4u + 1u)    /* words; odd stride: conflict-free when lanes read the same offset */
-#define ZP2B_OFF_WIN    (ZP_G * 4096u)
-#define ZP2B_SMEM       (ZP2B_OFF_WIN + 32u * ZP2B_WSTRIDE * 4u)
+#define ZP2B_TBYTES(x2) ((x2) ? 8192u : 4096u)  /* per table: u32[2048] two-symbol entries or u16[2048] */
+#define ZP2B_SMEM_X(x2) (ZP_G * ZP2B_TBYTES(x2) + 32u * ZP2B_WSTRIDE * 4u)
+#define ZP2B_SMEM       ZP2B_SMEM_X(false)
 
+/*
+ * X2: two symbols per lookup.  The table is rebuilt in shared memory from the one-symbol table
+ * stage 2a wrote: entry i = first symbol | second symbol << 8 | bits of the first << 16 | bits
+ * of both << 20 | (second symbol present) << 24, the second symbol being present when both
+ * codes fit the table's index bits.  Hex text and the like (4-5 bit codes, 11-bit tables) then
+ * takes two symbols per step of the serial chain.
+ */
+template <bool X2>
 CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem, uint32_t lane)
 {
+    constexpr uint32_t TB = ZP2B_TBYTES(X2), OFF_WIN = ZP_G * TB;
+
     const uint32_t ti = lane >> 2, tf = g * ZP_G + ti, s = lane & 3u;
     const uint32_t *b = nullptr;
     uint32_t kind = 0, lt = 0, hb = 0, hinfo = 0;
@@ -582,22 +595,42 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
     }
     if (__ballot_sync(CRYO_FULL, valid) == 0)
         return;
-    /* the group's tables -> shared memory: the 4 lanes of a table copy it, 16 bytes at a time */
+    /* the group's tables -> shared memory, by the 4 lanes of each table */
     if (valid && (hinfo & 0xFFu) != 0)
     {
-        const uint8_t *gt = reinterpret_cast<const uint8_t *>(a.huftab + ((size_t) tf * ZP_MAXB + hb) * 2048u);
-        uint8_t *st = smem + ti * 4096u;
-        const uint32_t bytes = 2u << (hinfo & 0xFFu);
+        const uint16_t *g1 = a.huftab + ((size_t) tf * ZP_MAXB + hb) * 2048u;
+        const uint32_t log1 = hinfo & 0xFFu, size1 = 1u << log1;
 
-        if (bytes < 16u)
+        if (X2)
         {
-            if (s == 0)
-                for (uint32_t k = 0; k < bytes; k += 2)
-                    *reinterpret_cast<uint16_t *>(st + k) = *reinterpret_cast<const uint16_t *>(gt + k);
+            uint32_t *x2 = reinterpret_cast<uint32_t *>(smem + ti * TB);
+
+            for (uint32_t k = s; k < size1; k += 4)
+            {
+                const uint32_t e0 = g1[k], nb0 = e0 >> 8;
+                const uint32_t e1 = g1[(k << nb0) & (size1 - 1u)], nb1 = e1 >> 8;
+                const bool     two = nb0 + nb1 <= log1;
+
+                x2[k] = (e0 & 0xFFu) | (two ? (e1 & 0xFFu) << 8 : 0u) | (nb0 << 16) |
+                        ((two ? nb0 + nb1 : nb0) << 20) | (two ? 1u << 24 : 0u);
+            }
         }
         else
-            for (uint32_t k = 16u * s; k < bytes; k += 64u)
-                st16(st + k, ld16(gt + k));
+        {
+            const uint8_t *gt = reinterpret_cast<const uint8_t *>(g1);
+            uint8_t *st = smem + ti * TB;
+            const uint32_t bytes = 2u * size1;
+
+            if (bytes < 16u)
+            {
+                if (s == 0)
+                    for (uint32_t k = 0; k < bytes; k += 2)
+                        *reinterpret_cast<uint16_t *>(st + k) = *reinterpret_cast<const uint16_t *>(gt + k);
+            }
+            else
+                for (uint32_t k = 16u * s; k < bytes; k += 64u)
+                    st16(st + k, ld16(gt + k));
+        }
     }
     /* this lane's stream: src[0, sn) -> cnt symbols at dst */
     const uint8_t *src = nullptr;
@@ -664,7 +697,7 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
      * words in front of the stream read as zero, a valid stream never consumes them and a
      * corrupt one fails the final bit count)
      */
-    uint32_t *win = reinterpret_cast<uint32_t *>(smem + ZP2B_OFF_WIN) + lane * ZP2B_WSTRIDE;
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem + OFF_WIN) + lane * ZP2B_WSTRIDE;
     const uint8_t *abase = src - ((uintptr_t) src & 15u);
     const int32_t  delta = (int32_t) ((uintptr_t) src & 15u);
     int32_t  npos = act ? (int32_t) ((delta + sn - 1u) & ~3u) : 0;      /* offset of the next word to hand out */
@@ -725,7 +758,8 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
     }
     if (!act)
         cnt = 0;
-    const uint16_t *huf = reinterpret_cast<const uint16_t *>(smem + ti * 4096u);
+    const uint16_t *huf = reinterpret_cast<const uint16_t *>(smem + ti * TB);
+    const uint32_t *huf2 = reinterpret_cast<const uint32_t *>(smem + ti * TB);
     const uint32_t sh = 32u - (uint32_t) tlog;
 
 #ifdef CRYO_EMU
@@ -762,58 +796,101 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         ZP2B_FILL();                                                         \
         cand = win[(npos - g0) >> 2];                                        \
     }
-    /* head: single symbols until dst + i is 4-byte aligned */
-    const uint32_t head = act ? min((uint32_t) ((4u - ((uintptr_t) dst & 3u)) & 3u), cnt) : 0u;
-    uint32_t i = 0;
-
-    ZP2B_ENSURE(act);
-#pragma unroll 1
-    for (uint32_t k = 0; k < 3; k++)
+    if (X2)
     {
-        const bool on = k < head;
-        uint32_t   sy;
-
-        ZP2B_REFILL(on);
-        ZP2B_DEC(sy, on);
-        if (on)
-            dst[i++] = (uint8_t) sy;
+        /*
+         * one or two symbols per step, four steps (at most 44 bits, two refills) per turn of the
+         * loop; every lane runs until the slowest lane of the warp is done.  Symbols go out as bytes:
+         * the second one of a step is written even when it turns out not to count (it is
+         * overwritten by the next step), except at the very end of the lane's output.
+         */
+#define ZP2B_DEC2(on)                                                        \
+    {                                                                        \
+        const uint32_t ent_ = huf2[hi >> sh];                                \
+        const bool on_ = (on) && i < cnt;                                    \
+        const bool two_ = on_ && (ent_ >> 24) != 0u && i + 1u < cnt;         \
+        const uint32_t nb_ = on_ ? (two_ ? (ent_ >> 20) & 15u : (ent_ >> 16) & 15u) : 0u; \
+        if (on_)                                                             \
+            dst[i] = (uint8_t) ent_;                                         \
+        if (two_)                                                            \
+            dst[i + 1u] = (uint8_t) (ent_ >> 8);                             \
+        i += on_ ? (two_ ? 2u : 1u) : 0u;                                    \
+        hi = __funnelshift_l(lo, hi, nb_);                                   \
+        lo <<= nb_;                                                          \
+        avail -= (int32_t) nb_;                                              \
+        used += (int32_t) nb_;                                               \
     }
-    /* quads, four symbols per 32-bit store; every lane runs the warp's longest count */
-    const uint32_t quads = (cnt - i) >> 2;
-    const uint32_t maxq = __reduce_max_sync(CRYO_FULL, quads);
-    uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + i);
+        uint32_t i = 0;
 
-#pragma unroll 1
-    for (uint32_t q = 0; q < maxq; q++)
-    {
-        const bool on = q < quads;
-        uint32_t   s0, s1, s2, s3;
+        while (__any_sync(CRYO_FULL, i < cnt))
+        {
+            const bool on = i < cnt;
 
-        ZP2B_ENSURE(on);
-        ZP2B_REFILL(on);
-        ZP2B_DEC(s0, on);
-        ZP2B_DEC(s1, on);
-        ZP2B_REFILL(on);
-        ZP2B_DEC(s2, on);
-        ZP2B_DEC(s3, on);
-        if (on)
-            d4[q] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+            ZP2B_ENSURE(on);
+            ZP2B_REFILL(on);
+            ZP2B_DEC2(on);
+            ZP2B_DEC2(on);
+            ZP2B_REFILL(on);
+            ZP2B_DEC2(on);
+            ZP2B_DEC2(on);
+        }
+#undef ZP2B_DEC2
     }
-    i += quads << 2;
-    /* tail */
-    const uint32_t tail = cnt - i;
-
-    ZP2B_ENSURE(tail != 0);
-#pragma unroll 1
-    for (uint32_t k = 0; k < 3; k++)
+    else
     {
-        const bool on = k < tail;
-        uint32_t   sy;
+        /* head: single symbols until dst + i is 4-byte aligned */
+        const uint32_t head = act ? min((uint32_t) ((4u - ((uintptr_t) dst & 3u)) & 3u), cnt) : 0u;
+        uint32_t i = 0;
 
-        ZP2B_REFILL(on);
-        ZP2B_DEC(sy, on);
-        if (on)
-            dst[i++] = (uint8_t) sy;
+        ZP2B_ENSURE(act);
+#pragma unroll 1
+        for (uint32_t k = 0; k < 3; k++)
+        {
+            const bool on = k < head;
+            uint32_t   sy;
+
+            ZP2B_REFILL(on);
+            ZP2B_DEC(sy, on);
+            if (on)
+                dst[i++] = (uint8_t) sy;
+        }
+        /* quads, four symbols per 32-bit store; every lane runs the warp's longest count */
+        const uint32_t quads = (cnt - i) >> 2;
+        const uint32_t maxq = __reduce_max_sync(CRYO_FULL, quads);
+        uint32_t *d4 = reinterpret_cast<uint32_t *>(dst + i);
+
+#pragma unroll 1
+        for (uint32_t q = 0; q < maxq; q++)
+        {
+            const bool on = q < quads;
+            uint32_t   s0, s1, s2, s3;
+
+            ZP2B_ENSURE(on);
+            ZP2B_REFILL(on);
+            ZP2B_DEC(s0, on);
+            ZP2B_DEC(s1, on);
+            ZP2B_REFILL(on);
+            ZP2B_DEC(s2, on);
+            ZP2B_DEC(s3, on);
+            if (on)
+                d4[q] = s0 | (s1 << 8) | (s2 << 16) | (s3 << 24);
+        }
+        i += quads << 2;
+        /* tail */
+        const uint32_t tail = cnt - i;
+
+        ZP2B_ENSURE(tail != 0);
+#pragma unroll 1
+        for (uint32_t k = 0; k < 3; k++)
+        {
+            const bool on = k < tail;
+            uint32_t   sy;
+
+            ZP2B_REFILL(on);
+            ZP2B_DEC(sy, on);
+            if (on)
+                dst[i++] = (uint8_t) sy;
+        }
     }
 #undef ZP2B_FILL
 #undef ZP2B_REFILL
@@ -1389,6 +1466,15 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
 
                 if (done + 32u + lane < nseq)
                     nxt = sq[done + 32u + lane];
+#ifndef CRYO_EMU
+                /* HBM is busy with the raw / RLE stage's stores while this runs, and a load that has to
+                 * go there is slow: ask L2 for the sequences and the literals a few loads ahead (one
+                 * 128-byte line per lane) */
+                if ((a.pf_hint & 2u) && done + 64u + 16u * lane < nseq)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(sq + done + 64u + 16u * lane));
+                if ((a.pf_hint & 2u) && lt != 1 && lpos + 1024u + 128u * lane < regen)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(lit_base + lpos + 1024u + 128u * lane));
+#endif
                 const bool     have = lane < g;
                 const uint32_t my_ll = have ? (uint32_t) cur & 0x1FFFFu : 0u;
                 const uint32_t my_ml = have ? (uint32_t) (cur >> 17) & 0x3FFFFu : 0u;

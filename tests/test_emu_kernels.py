@@ -225,3 +225,48 @@ def test_emulated_pipeline_conformance_and_fallback(oracle_ref):
     assert (st[3] == 0) == (ref_st == 0)
     if ref_st == 0:
         assert np.array_equal(outs[3][: sz.value], one[: sz.value])
+
+
+@pytest.mark.parametrize("huf_x2", [False, True])
+def test_emulated_pipeline_random_frames(oracle_port, huf_x2, monkeypatch):
+    """Forty frames of odd sizes and contents (text with repeats, random bytes, runs, mixtures),
+    written by libzstd at levels -5..6 into a 96 KiB capacity: several zstd blocks per frame,
+    raw / RLE / compressed blocks, treeless literals, all three sequence-table modes.  The
+    plain-C restatement of the format (oracle/) is the checker.  huf_x2: the literal stage with two
+    symbols per table lookup."""
+    import benchdata
+    if huf_x2:
+        monkeypatch.setenv("ZP_EMU_HUF_X2", "1")
+    L = _pipeline_lib()
+    _, zstd = benchdata._libs()
+    rng = np.random.default_rng(20260117)
+    words = [bytes(rng.integers(97, 123, size=int(rng.integers(2, 9)), dtype=np.uint8)) for _ in range(64)]
+    cap = 96 * 1024
+    plain, comp = [], []
+    for k in range(40):
+        n = int(rng.integers(1, cap + 1)) if k % 5 else cap
+        kind = k % 4
+        if kind == 0:
+            buf = b" ".join(words[int(i)] for i in rng.integers(0, 64, size=n // 3 + 1))[:n]
+        elif kind == 1:
+            buf = rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+        elif kind == 2:
+            buf = b"".join(bytes([int(rng.integers(0, 4))]) * int(rng.integers(1, 3000)) for _ in range(n // 500 + 1))[:n]
+        else:
+            half = n // 2
+            buf = rng.integers(0, 16, size=half, dtype=np.uint8).tobytes() + b"\0" * (n - half)
+        buf = buf.ljust(n, b"x")
+        src = np.frombuffer(buf, dtype=np.uint8).copy()
+        scratch = np.zeros(n + n // 128 + 256, dtype=np.uint8)
+        got = zstd.ZSTD_compress(scratch.ctypes.data, scratch.size, src.ctypes.data, src.size, int(rng.integers(-5, 7)))
+        assert 0 < got <= scratch.size
+        plain.append(src)
+        comp.append(scratch[:got].copy())
+    st, osz, outs, fl = _run_pipeline(L, comp, cap=cap, shift=3)
+    for k in range(len(comp)):
+        want_n, want = oracle_port.zstd_decode(comp[k], cap=cap)[:2]
+        assert want_n == plain[k].size and np.array_equal(want[:want_n], plain[k]), "oracle disagrees with libzstd"
+        assert st[k] == 0 and osz[k] == plain[k].size, (k, st[k], osz[k])
+        assert np.array_equal(outs[k][: osz[k]], plain[k]), k
+    # the pipeline itself should have taken nearly all of them (levels up to 6 rarely use Repeat_Mode)
+    assert sum(1 for f in fl if f == 0) >= 30, fl

@@ -234,3 +234,42 @@ def test_zstd_pipeline_large_batch_mixed_kinds(gpu, oracle_ref):
         assert np.array_equal(out[k], blocks[i]), (k, tags[i])
     frames, fallback = gpu.zstd_pipeline_stats()
     assert frames == 600 and fallback == 0
+
+
+def test_zstd_pipeline_random_frames_small_capacity(gpu, oracle_port):
+    """200 frames of odd sizes and contents at levels -5..6 in a 96 KiB capacity (block_size is a
+    run-time parameter of the library): several zstd blocks per frame, raw / RLE / compressed
+    blocks, treeless literals, all sequence-table modes; the plain-C restatement is the checker."""
+    import benchdata
+    _, zstd = benchdata._libs()
+    rng = np.random.default_rng(20260118)
+    words = [bytes(rng.integers(97, 123, size=int(rng.integers(2, 9)), dtype=np.uint8)) for _ in range(64)]
+    cap = 96 * 1024
+    plain, comp = [], []
+    for k in range(200):
+        n = int(rng.integers(1, cap + 1)) if k % 5 else cap
+        kind = k % 4
+        if kind == 0:
+            buf = b" ".join(words[int(i)] for i in rng.integers(0, 64, size=n // 3 + 1))[:n]
+        elif kind == 1:
+            buf = rng.integers(0, 256, size=n, dtype=np.uint8).tobytes()
+        elif kind == 2:
+            buf = b"".join(bytes([int(rng.integers(0, 4))]) * int(rng.integers(1, 3000)) for _ in range(n // 500 + 1))[:n]
+        else:
+            half = n // 2
+            buf = rng.integers(0, 16, size=half, dtype=np.uint8).tobytes() + b"\0" * (n - half)
+        src = np.frombuffer(buf.ljust(n, b"x"), dtype=np.uint8).copy()
+        scratch = np.zeros(n + n // 128 + 256, dtype=np.uint8)
+        got = zstd.ZSTD_compress(scratch.ctypes.data, scratch.size, src.ctypes.data, src.size, int(rng.integers(-5, 7)))
+        assert 0 < got <= scratch.size
+        plain.append(src)
+        comp.append(scratch[:got].copy())
+    out, osz, st = decode_device(gpu, COMP_ZSTD, comp, block_size=cap)
+    for k in range(len(comp)):
+        assert st[k] == 0 and osz[k] == plain[k].size, (k, st[k], osz[k])
+        assert np.array_equal(out[k][: osz[k]], plain[k]), k
+    for k in (0, 1, 2, 3, 7):
+        want_n, want = oracle_port.zstd_decode(comp[k], cap=cap)[:2]
+        assert want_n == plain[k].size and np.array_equal(want[:want_n], plain[k])
+    frames, fallback = gpu.zstd_pipeline_stats()
+    assert frames == len(comp) and fallback <= len(comp) // 4, (frames, fallback)
