@@ -163,11 +163,8 @@ __device__ unsigned long long zp_tl[32];
 #endif
 
 /* defaults of the pipeline's knobs (each has an environment override, see launch_zstd_decode) */
-#ifndef ZP_HUF_X2_DEFAULT
-#define ZP_HUF_X2_DEFAULT 0
-#endif
 #ifndef ZP_L2HINT_DEFAULT
-#define ZP_L2HINT_DEFAULT 0
+#define ZP_L2HINT_DEFAULT 1
 #endif
 #ifndef ZP_EXEC_PREFETCH_DEFAULT
 #define ZP_EXEC_PREFETCH_DEFAULT 0
@@ -326,16 +323,7 @@ __global__ void __launch_bounds__(32)
 k_zp_literals(const ZpArgs a)
 {
     ZP_TL_BEGIN(3)
-    zp_stage2b<false>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
-    ZP_TL_END(3)
-}
-
-/* two symbols per table lookup (zstd_decode_p.cuh, zp_stage2b<true>) */
-__global__ void __launch_bounds__(32)
-k_zp_literals_x2(const ZpArgs a)
-{
-    ZP_TL_BEGIN(3)
-    zp_stage2b<true>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    zp_stage2b(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     ZP_TL_END(3)
 }
 
@@ -673,20 +661,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             cudaEventRecord(ev[2], aux[1]);
         }
         k_zp_huftab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
-        {
-            static int x2 = -1;                 /* CRYOGPU_ZP_HUF=x1 | x2: symbols per Huffman table lookup */
-
-            if (x2 < 0)
-            {
-                const char *e = getenv("CRYOGPU_ZP_HUF");
-
-                x2 = e ? strcmp(e, "x2") == 0 : ZP_HUF_X2_DEFAULT;
-            }
-            if (x2)
-                k_zp_literals_x2<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM_X(true), st>>>(a);
-            else
-                k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
-        }
+        k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
         cudaStreamWaitEvent(st, ev[1], 0);
         if (pf_with_exec == 1)
         {
@@ -867,14 +842,13 @@ set_kernel_attrs(cryogpu_ctx *ctx)
     CU(cudaFuncSetAttribute(k_zstd_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSW_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode_g, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSG_SMEM));
     CU(cudaFuncSetAttribute(k_zp_sequences_large, cudaFuncAttributeMaxDynamicSharedMemorySize, ZP3B_SMEM(ZP3B_LARGE, ZP_G)));
-    CU(cudaFuncSetAttribute(k_zp_literals_x2, cudaFuncAttributeMaxDynamicSharedMemorySize, ZP2B_SMEM_X(true)));
     CU(cudaFuncSetAttribute(k_zp_sequences_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES)));
     /* the pipeline's kernels run side by side on one SM (zstd_decode_p.cuh): give them all the same
      * shared-memory carve-out, because an SM has to drain before it can change its L1 / shared split */
     {
         const void *zp_kernels[] = {(const void *) k_zp_parse, (const void *) k_zp_prefill, (const void *) k_zp_huftab,
-                                    (const void *) k_zp_literals, (const void *) k_zp_literals_x2, (const void *) k_zp_fsetab,
+                                    (const void *) k_zp_literals, (const void *) k_zp_fsetab,
                                     (const void *) k_zp_sequences_small, (const void *) k_zp_sequences_large,
                                     (const void *) k_zp_execute, (const void *) k_zstd_decode_w};
 

@@ -560,21 +560,14 @@ CRYO_DEV void zp_stage2a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
  */
 #define ZP2B_WIN        256u                    /* bytes of stream per lane window */
 #define ZP2B_WSTRIDE    (ZP2B_WIN / 4u + 1u)    /* words; odd stride: conflict-free when lanes read the same offset */
-#define ZP2B_TBYTES(x2) ((x2) ? 8192u : 4096u)  /* per table: u32[2048] two-symbol entries or u16[2048] */
-#define ZP2B_SMEM_X(x2) (ZP_G * ZP2B_TBYTES(x2) + 32u * ZP2B_WSTRIDE * 4u)
-#define ZP2B_SMEM       ZP2B_SMEM_X(false)
+#define ZP2B_SMEM       (ZP_G * 4096u + 32u * ZP2B_WSTRIDE * 4u)
 
-/*
- * X2: two symbols per lookup.  The table is rebuilt in shared memory from the one-symbol table
- * stage 2a wrote: entry i = first symbol | second symbol << 8 | bits of the first << 16 | bits
- * of both << 20 | (second symbol present) << 24, the second symbol being present when both
- * codes fit the table's index bits.  Hex text and the like (4-5 bit codes, 11-bit tables) then
- * takes two symbols per step of the serial chain.
- */
-template <bool X2>
+/* (two symbols per table lookup was tried here: u32 entries rebuilt from the one-symbol table,
+ * byte stores, data-dependent trip count.  On B200 it ran 2.5x slower than this loop on dense
+ * hex text, profiles/r01e_arrangements.txt, and was dropped.) */
 CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem, uint32_t lane)
 {
-    constexpr uint32_t TB = ZP2B_TBYTES(X2), OFF_WIN = ZP_G * TB;
+    constexpr uint32_t TB = 4096u, OFF_WIN = ZP_G * TB;
 
     const uint32_t ti = lane >> 2, tf = g * ZP_G + ti, s = lane & 3u;
     const uint32_t *b = nullptr;
@@ -601,21 +594,6 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         const uint16_t *g1 = a.huftab + ((size_t) tf * ZP_MAXB + hb) * 2048u;
         const uint32_t log1 = hinfo & 0xFFu, size1 = 1u << log1;
 
-        if (X2)
-        {
-            uint32_t *x2 = reinterpret_cast<uint32_t *>(smem + ti * TB);
-
-            for (uint32_t k = s; k < size1; k += 4)
-            {
-                const uint32_t e0 = g1[k], nb0 = e0 >> 8;
-                const uint32_t e1 = g1[(k << nb0) & (size1 - 1u)], nb1 = e1 >> 8;
-                const bool     two = nb0 + nb1 <= log1;
-
-                x2[k] = (e0 & 0xFFu) | (two ? (e1 & 0xFFu) << 8 : 0u) | (nb0 << 16) |
-                        ((two ? nb0 + nb1 : nb0) << 20) | (two ? 1u << 24 : 0u);
-            }
-        }
-        else
         {
             const uint8_t *gt = reinterpret_cast<const uint8_t *>(g1);
             uint8_t *st = smem + ti * TB;
@@ -759,7 +737,6 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
     if (!act)
         cnt = 0;
     const uint16_t *huf = reinterpret_cast<const uint16_t *>(smem + ti * TB);
-    const uint32_t *huf2 = reinterpret_cast<const uint32_t *>(smem + ti * TB);
     const uint32_t sh = 32u - (uint32_t) tlog;
 
 #ifdef CRYO_EMU
@@ -796,47 +773,6 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         ZP2B_FILL();                                                         \
         cand = win[(npos - g0) >> 2];                                        \
     }
-    if (X2)
-    {
-        /*
-         * one or two symbols per step, four steps (at most 44 bits, two refills) per turn of the
-         * loop; every lane runs until the slowest lane of the warp is done.  Symbols go out as bytes:
-         * the second one of a step is written even when it turns out not to count (it is
-         * overwritten by the next step), except at the very end of the lane's output.
-         */
-#define ZP2B_DEC2(on)                                                        \
-    {                                                                        \
-        const uint32_t ent_ = huf2[hi >> sh];                                \
-        const bool on_ = (on) && i < cnt;                                    \
-        const bool two_ = on_ && (ent_ >> 24) != 0u && i + 1u < cnt;         \
-        const uint32_t nb_ = on_ ? (two_ ? (ent_ >> 20) & 15u : (ent_ >> 16) & 15u) : 0u; \
-        if (on_)                                                             \
-            dst[i] = (uint8_t) ent_;                                         \
-        if (two_)                                                            \
-            dst[i + 1u] = (uint8_t) (ent_ >> 8);                             \
-        i += on_ ? (two_ ? 2u : 1u) : 0u;                                    \
-        hi = __funnelshift_l(lo, hi, nb_);                                   \
-        lo <<= nb_;                                                          \
-        avail -= (int32_t) nb_;                                              \
-        used += (int32_t) nb_;                                               \
-    }
-        uint32_t i = 0;
-
-        while (__any_sync(CRYO_FULL, i < cnt))
-        {
-            const bool on = i < cnt;
-
-            ZP2B_ENSURE(on);
-            ZP2B_REFILL(on);
-            ZP2B_DEC2(on);
-            ZP2B_DEC2(on);
-            ZP2B_REFILL(on);
-            ZP2B_DEC2(on);
-            ZP2B_DEC2(on);
-        }
-#undef ZP2B_DEC2
-    }
-    else
     {
         /* head: single symbols until dst + i is 4-byte aligned */
         const uint32_t head = act ? min((uint32_t) ((4u - ((uintptr_t) dst & 3u)) & 3u), cnt) : 0u;

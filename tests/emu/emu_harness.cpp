@@ -395,15 +395,9 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     emu::launch(dim3((((unsigned) n + 31) / 32) * ZP_MAXB), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
         zp_stage2a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
-    /* ZP_EMU_HUF_X2: the two-symbols-per-lookup variant of stage 2b */
-    if (getenv("ZP_EMU_HUF_X2"))
-        emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP2B_SMEM_X(true), [&]() {
-            zp_stage2b<true>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
-        });
-    else
-        emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP2B_SMEM, [&]() {
-            zp_stage2b<false>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
-        });
+    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP2B_SMEM, [&]() {
+        zp_stage2b(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    });
     emu::launch(dim3((((unsigned) n + 31) / 32) * ZP_MAXB), dim3(32 * ZP3A_WARPS), ZP3A_SMEM, [&]() {
         zp_stage3a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });

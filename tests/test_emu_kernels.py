@@ -227,16 +227,12 @@ def test_emulated_pipeline_conformance_and_fallback(oracle_ref):
         assert np.array_equal(outs[3][: sz.value], one[: sz.value])
 
 
-@pytest.mark.parametrize("huf_x2", [False, True])
-def test_emulated_pipeline_random_frames(oracle_port, huf_x2, monkeypatch):
+def test_emulated_pipeline_random_frames(oracle_port):
     """Forty frames of odd sizes and contents (text with repeats, random bytes, runs, mixtures),
     written by libzstd at levels -5..6 into a 96 KiB capacity: several zstd blocks per frame,
     raw / RLE / compressed blocks, treeless literals, all three sequence-table modes.  The
-    plain-C restatement of the format (oracle/) is the checker.  huf_x2: the literal stage with two
-    symbols per table lookup."""
+    plain-C restatement of the format (oracle/) is the checker."""
     import benchdata
-    if huf_x2:
-        monkeypatch.setenv("ZP_EMU_HUF_X2", "1")
     L = _pipeline_lib()
     _, zstd = benchdata._libs()
     rng = np.random.default_rng(20260117)
