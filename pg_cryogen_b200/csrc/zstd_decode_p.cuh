@@ -1282,17 +1282,60 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 #endif
 #define ZP4_LANE_ML     48u                     /* independent matches up to this long are copied by one lane each */
 
+/*
+ * Stage 4 reads what stage 0 writes only through match sources below `guard` (the end of the last
+ * block it skipped).  Before the first such read it waits until stage 0 has published the frame's
+ * blocks, or writes them itself if that takes too long (idempotent).  A frame whose matches never
+ * reach back into a skipped block never waits: the zero run that follows the RLE blocks of a
+ * sparse cryo block is recognised as a fill of the RLE byte (see rle_lo / rle_hi below).
+ */
+#define ZP4_CONFIRM()                                                                        \
+    if (skipped > confirmed)                                                                 \
+    {                                                                                        \
+        uint32_t seen_ = 0;                                                                  \
+                                                                                             \
+        if (lane == 0)                                                                       \
+            for (uint32_t spin_ = 0; spin_ < ZP4_SPINS; spin_++)                             \
+            {                                                                                \
+                seen_ = zp_ld_acquire(a.pf_done + f);                                        \
+                if (seen_ >= skipped)                                                        \
+                    break;                                                                   \
+                __nanosleep(256);                                                            \
+            }                                                                                \
+        seen_ = __shfl_sync(CRYO_FULL, seen_, 0);                                            \
+        if (seen_ < skipped)                                                                 \
+        {                                                                                    \
+            for (uint32_t jj_ = 0; jj_ < j; jj_++)                                           \
+            {                                                                                \
+                const uint32_t *bb_ = a.blk + ((size_t) f * ZP_MAXB + jj_) * ZP_BF;          \
+                                                                                             \
+                if ((bb_[ZPB_KIND] & 3u) < 2u && (skipmask >> jj_) & 1u)                     \
+                {                                                                            \
+                    if ((bb_[ZPB_KIND] & 3u) == 0)                                           \
+                        team_copy(o.out + bb_[ZPB_SPECPOS], fin + bb_[ZPB_OFF], bb_[ZPB_BSIZE], lane, 32); \
+                    else                                                                     \
+                        team_fill_byte(o.out + bb_[ZPB_SPECPOS], fin[bb_[ZPB_OFF]], bb_[ZPB_BSIZE], lane, 32); \
+                }                                                                            \
+            }                                                                                \
+            __syncwarp();                                                                    \
+        }                                                                                    \
+        confirmed = skipped;                                                                 \
+    }
+
 /* stage 4 body: one warp, frame f */
 CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lane)
 {
     if (f >= a.n || a.methods[f] != ZP_METHOD_ZSTD || a.flag[f] != 0)
         return;
     const uint32_t nb = a.fr[(size_t) f * ZP_FF], cap = a.cap;
-    const uint8_t *in = a.src + a.src_off[f];
+    const uint8_t *in = a.src + a.src_off[f], *fin = in;    /* fin: for ZP4_CONFIRM, where `in` is shadowed */
     WOut     o;
     int      err = ST_OK;
     uint32_t rep0 = 1, rep1 = 4, rep2 = 8;
     uint32_t skipped = 0, confirmed = 0, skipmask = 0;     /* blocks left to stage 0 */
+    uint32_t guard = 0;                                    /* positions below may not be written yet (see ZP4_CONFIRM) */
+    uint32_t rle_lo = 0, rle_hi = 0;                       /* [rle_lo, rle_hi): skipped RLE blocks, all bytes = rle_byte */
+    uint8_t  rle_byte = 0;
 
     wx_init(o, a.dst + (size_t) f * a.dst_stride, cap, smem);
     for (uint32_t j = 0; j < nb && err == ST_OK; j++)
@@ -1322,6 +1365,18 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                 __syncwarp();
                 skipped++;
                 skipmask |= 1u << j;
+                guard = o.pos;
+                /* consecutive RLE blocks of one byte form one range whose content is known */
+                if (type == 1 && rle_hi == o.pos - bsize && rle_byte == in[off] && rle_hi > rle_lo)
+                    rle_hi = o.pos;
+                else if (type == 1)
+                {
+                    rle_lo = o.pos - bsize;
+                    rle_hi = o.pos;
+                    rle_byte = in[off];
+                }
+                else
+                    rle_lo = rle_hi = 0;
                 continue;
             }
             if (type == 0)
@@ -1329,38 +1384,6 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
             else
                 wx_fill_byte(o, in[off], bsize, lane);
             continue;
-        }
-        if (skipped > confirmed)
-        {
-            /* matches of this block may read what stage 0 writes: wait for it, or do it */
-            uint32_t seen = 0;
-
-            if (lane == 0)
-                for (uint32_t spin = 0; spin < ZP4_SPINS; spin++)
-                {
-                    seen = zp_ld_acquire(a.pf_done + f);
-                    if (seen >= skipped)
-                        break;
-                    __nanosleep(256);
-                }
-            seen = __shfl_sync(CRYO_FULL, seen, 0);
-            if (seen < skipped)
-            {
-                for (uint32_t jj = 0; jj < j; jj++)
-                {
-                    const uint32_t *bb = a.blk + ((size_t) f * ZP_MAXB + jj) * ZP_BF;
-
-                    if ((bb[ZPB_KIND] & 3u) < 2u && (skipmask >> jj) & 1u)
-                    {
-                        if ((bb[ZPB_KIND] & 3u) == 0)
-                            team_copy(o.out + bb[ZPB_SPECPOS], in + bb[ZPB_OFF], bb[ZPB_BSIZE], lane, 32);
-                        else
-                            team_fill_byte(o.out + bb[ZPB_SPECPOS], in[bb[ZPB_OFF]], bb[ZPB_BSIZE], lane, 32);
-                    }
-                }
-                __syncwarp();
-            }
-            confirmed = skipped;
         }
         const uint32_t lt = (kind >> 2) & 3u, regen = b[ZPB_REGEN], nseq = b[ZPB_NSEQ];
         const uint32_t block_start = o.pos;
@@ -1501,7 +1524,18 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
 
                         L.pos = lit0;
                         zsw_lits_emit(o, L, ll, lane);
-                        wx_match(o, moff, ml, lane);
+                        {
+                            const uint32_t sp1 = o.pos - moff, need = ml < moff ? ml : moff;
+
+                            if (sp1 >= rle_lo && sp1 + need <= rle_hi)
+                                wx_fill_byte(o, rle_byte, ml, lane);    /* a copy of known bytes: no read */
+                            else
+                            {
+                                if (sp1 < guard)
+                                    ZP4_CONFIRM();
+                                wx_match(o, moff, ml, lane);
+                            }
+                        }
                         k0++;
                         continue;
                     }
@@ -1540,6 +1574,8 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                      * one after the other would cost an L2 round trip per sequence).  The others
                      * follow in order, each a warp-wide move.
                      */
+                    if (skipped > confirmed && __any_sync(CRYO_FULL, in && my_mpos - my_off < guard))
+                        ZP4_CONFIRM();
                     const uint32_t floor0 = end + 64u > WX_RING ? end + 64u - WX_RING : 0u;
                     const uint32_t floor = floor0 > o.lo ? floor0 : o.lo;
                     const uint32_t my_sp = my_mpos - my_off;
