@@ -1503,9 +1503,15 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                 }
                 const uint32_t bigmask = __ballot_sync(CRYO_FULL, !have || my_ll > ZP4_BIG_LL || my_ml > ZP4_BIG_ML);
                 uint32_t k0 = 0;
+                bool     need_confirm = false;
 
                 while (k0 < g)
                 {
+                    if (need_confirm)
+                    {
+                        ZP4_CONFIRM();          /* the only expansion: the sites below come back here */
+                        need_confirm = false;
+                    }
                     /* the longest run of ordinary sequences from k0 whose output fits the span and
                      * whose literals fit the window */
                     const uint32_t pos0 = __shfl_sync(CRYO_FULL, my_start, (int) k0);
@@ -1522,24 +1528,30 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                         const uint32_t ml = __shfl_sync(CRYO_FULL, my_ml, (int) k0);
                         const uint32_t moff = __shfl_sync(CRYO_FULL, my_off, (int) k0);
 
+                        const uint32_t sp1 = o.pos + ll - moff, need = ml < moff ? ml : moff;
+                        const bool     known = sp1 >= rle_lo && sp1 + need <= rle_hi;
+
+                        if (!known && sp1 < guard && skipped > confirmed)
+                        {
+                            need_confirm = true;
+                            continue;
+                        }
                         L.pos = lit0;
                         zsw_lits_emit(o, L, ll, lane);
-                        {
-                            const uint32_t sp1 = o.pos - moff, need = ml < moff ? ml : moff;
-
-                            if (sp1 >= rle_lo && sp1 + need <= rle_hi)
-                                wx_fill_byte(o, rle_byte, ml, lane);    /* a copy of known bytes: no read */
-                            else
-                            {
-                                if (sp1 < guard)
-                                    ZP4_CONFIRM();
-                                wx_match(o, moff, ml, lane);
-                            }
-                        }
+                        if (known)
+                            wx_fill_byte(o, rle_byte, ml, lane);        /* a copy of known bytes: no read */
+                        else
+                            wx_match(o, moff, ml, lane);
                         k0++;
                         continue;
                     }
                     const bool     in = lane >= k0 && lane < k1;
+
+                    if (skipped > confirmed && __any_sync(CRYO_FULL, in && my_mpos - my_off < guard))
+                    {
+                        need_confirm = true;
+                        continue;
+                    }
                     const uint32_t end = __shfl_sync(CRYO_FULL, my_epos, (int) (k1 - 1u));
                     const uint32_t litend = __shfl_sync(CRYO_FULL, my_lit + my_ll, (int) (k1 - 1u));
 
@@ -1574,8 +1586,6 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                      * one after the other would cost an L2 round trip per sequence).  The others
                      * follow in order, each a warp-wide move.
                      */
-                    if (skipped > confirmed && __any_sync(CRYO_FULL, in && my_mpos - my_off < guard))
-                        ZP4_CONFIRM();
                     const uint32_t floor0 = end + 64u > WX_RING ? end + 64u - WX_RING : 0u;
                     const uint32_t floor = floor0 > o.lo ? floor0 : o.lo;
                     const uint32_t my_sp = my_mpos - my_off;

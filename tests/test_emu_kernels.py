@@ -182,7 +182,11 @@ def test_emulated_pipeline_mixed_frames(oracle_ref, late_prefill, monkeypatch):
               bg.make_block("D", "random", 33), bg.regression_block(291, 500), bg.make_block("S", "hex", 34),
               bg.make_block("M", "hex", 35), bg.make_block("S", "random", 36), bg.make_block("S", "hex", 37),
               bg.make_block("M", "lowcard", 38), bg.regression_block(1, 290)]
-    levels = [1, 1, 3, 1, -5, 1, 1, 2, -1, 1, 1]
+    # 200 KB of random bytes repeated: a Raw block (written by the raw / RLE stage) that the matches of
+    # the Compressed blocks after it copy from, so the executor has to wait for it or write it itself
+    rnd = np.random.default_rng(7).integers(0, 256, size=200 * 1024, dtype=np.uint8)
+    blocks.append(np.tile(rnd, 6)[:MiB].copy())
+    levels = [1, 1, 3, 1, -5, 1, 1, 2, -1, 1, 1, 1]
     comp = [oracle_ref.compress(1, lv, b)[0][0] for lv, b in zip(levels, blocks)]
     comp[5] = comp[5][:-37].copy()
     st, osz, outs, fl = _run_pipeline(L, comp, shift=5)

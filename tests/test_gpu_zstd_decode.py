@@ -29,6 +29,11 @@ def _blocks():
     tags.append("regression-1")
     blocks.append(bg.regression_block(291, 500))
     tags.append("regression-2")
+    # 200 KB of random bytes repeated: Raw blocks whose bytes the matches of later blocks copy (the
+    # pipeline's executor then depends on its raw / RLE stage)
+    rnd = np.random.default_rng(7).integers(0, 256, size=200 * 1024, dtype=np.uint8)
+    blocks.append(np.tile(rnd, 6)[:CRYO_BLCKSZ].copy())
+    tags.append("random-repeated")
     return np.stack(blocks), tags
 
 
