@@ -582,7 +582,8 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
                    uint8_t *scratch, const uint32_t *predef, void *zpbuf, cudaStream_t *aux,
                    cudaEvent_t *ev, int sm_count)
 {
-    const int variant = zstd_kernel_variant();
+    /* no work area (allocation failed, or more frames than the pipeline indexes): one warp per frame */
+    const int variant = zstd_kernel_variant() == 3 && !zpbuf ? 2 : zstd_kernel_variant();
 
     if (variant == 1)
         k_zstd_decode<<<(unsigned) n, ZSTDD_THREADS, ZSTDD_SMEM, st>>>(
@@ -1098,9 +1099,10 @@ cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
         return fail(CRYOGPU_E_ARG, "NULL device pointer");
     if (((uintptr_t) d_dst & 15) || (dst_stride & 15) || dst_stride < block_size)
         return fail(CRYOGPU_E_ARG, "d_dst and dst_stride must be multiples of 16, stride >= block_size");
-    if (block_size == 0 || block_size > (1u << 27) || n > 0xffffffu)
+    if (block_size == 0 || block_size > (1u << 27) || n > 0x7fffffffu)
         return fail(CRYOGPU_E_ARG, "block_size or n out of range");
     cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
+    bool         use_zp = false;
 
     CU(cudaSetDevice(ctx->device));
     {
@@ -1109,17 +1111,39 @@ cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
 
         if (rc != CRYOGPU_OK)
             return rc;
-        if (zstd_kernel_variant() == 3 && (rc = dev_reserve(ctx->zp[0], zp_bytes(n, block_size))) != CRYOGPU_OK)
-            return rc;
+        /* the pipeline's work area (about 2.3 x the batch's output); without it the batch still
+         * decodes, one warp per frame */
+        use_zp = zstd_kernel_variant() == 3 && n <= 0xFFFFFFu;
+        if (use_zp && cudaSetDevice(ctx->device) == cudaSuccess)
+        {
+            DevBuf &zb = ctx->zp[0];
+            const size_t need = zp_bytes(n, block_size);
+
+            if (need > zb.cap)
+            {
+                if (zb.p)
+                    cudaFree(zb.p);
+                zb.p = nullptr;
+                zb.cap = 0;
+                if (cudaMalloc(&zb.p, need) == cudaSuccess)
+                    zb.cap = need;
+                else
+                {
+                    cudaGetLastError();         /* not an error of this call */
+                    zb.p = nullptr;
+                    use_zp = false;
+                }
+            }
+        }
     }
     k_flag_unknown_methods<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(d_methods, n, d_out_size,
                                                                          d_status);
     launch_lz4_decode(st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
                       d_out_size, d_status);
-    ctx->last_zp_n = zstd_kernel_variant() == 3 ? n : 0;
+    ctx->last_zp_n = use_zp ? n : 0;
     ctx->last_zp_cap = block_size;
     launch_zstd_decode(st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
-                       d_out_size, d_status, (uint8_t *) ctx->scratch.p, ctx->predef, ctx->zp[0].p, ctx->zaux[0],
+                       d_out_size, d_status, (uint8_t *) ctx->scratch.p, ctx->predef, use_zp ? ctx->zp[0].p : nullptr, ctx->zaux[0],
                        ctx->zev[0], ctx->sm_count);
     CU(cudaGetLastError());
     return CRYOGPU_OK;
