@@ -228,8 +228,8 @@ k_zp_prefill(const ZpArgs a)
         uint8_t *out = a.dst + (size_t) f * a.dst_stride;
 
         __syncthreads();
-        if (threadIdx.x < ZP_MAXB)
-            spec[threadIdx.x] = threadIdx.x < nb ? a.blk[((size_t) f * ZP_MAXB + threadIdx.x) * ZP_BF + ZPB_SPECPOS] : ~0u;
+        if (threadIdx.x == 0)
+            zp_frame_positions(a, f, spec);     /* exact: stage 3b has measured the Compressed blocks */
         __syncthreads();
         uint32_t did = 0;
 
@@ -629,19 +629,19 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         k_zp_parse<<<(unsigned) ((n + 31) / 32), 32, 0, st>>>(a);
         /*
          * literals (st) and sequences (aux 0) are independent of each other and bound by latency.
-         * The raw / RLE blocks (aux 1, one persistent CTA per SM) are bound by HBM and run beside
-         * the executor, which is bound by instruction issue and synchronises with them per frame
-         * through pf_done.  CRYOGPU_ZP_PREFILL_WITH=entropy runs them beside the entropy stages
-         * instead (measured slower on B200: a stage that saturates HBM stretches the memory
-         * latency the lockstep stages depend on; profiles/r01e_arrangements.txt).
+         * Once the sequences are walked the positions of the raw / RLE blocks are known (stage 3c);
+         * those blocks (aux 1, one persistent CTA per SM, bound by HBM) are then written beside the
+         * executor (st, bound by instruction issue), which synchronises with them per frame through
+         * pf_done.  Running them beside the entropy stages instead was measured slower (a stage that
+         * saturates HBM stretches the memory latency the lockstep stages depend on;
+         * profiles/r01e_arrangements.txt).
          */
-        static int pf_ctas = -1, pf_with_exec = 1;     /* tuning knobs */
+        static int pf_ctas = -1;                /* CTAs per SM of the raw / RLE stage (tuning knob) */
 
         if (pf_ctas < 0)
         {
-            const char *e = getenv("CRYOGPU_ZP_PREFILL_CTAS"), *w = getenv("CRYOGPU_ZP_PREFILL_WITH");
+            const char *e = getenv("CRYOGPU_ZP_PREFILL_CTAS");
 
-            pf_with_exec = (w && strcmp(w, "entropy") == 0) ? 0 : (w && strcmp(w, "all") == 0) ? 2 : 1;
             pf_ctas = e && atoi(e) > 0 ? atoi(e) : 1;
         }
         const unsigned pf_grid = (unsigned) std::min<size_t>(n, (size_t) pf_ctas * sm_count);
@@ -653,29 +653,15 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
                                ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), aux[0]>>>(a);
         k_zp_sequences_large<<<ngroups * ZP_MAXB, 32, ZP3B_SMEM(ZP3B_LARGE, ZP_G), aux[0]>>>(a);
         cudaEventRecord(ev[1], aux[0]);
-        if (pf_with_exec != 1)
-        {
-            /* 0: beside the entropy stages, the executor waits for it; 2: started here, the executor
-             * does not wait for the whole of it (pf_done) */
-            cudaStreamWaitEvent(aux[1], ev[0], 0);
-            k_zp_prefill<<<pf_grid, ZP0_THREADS, 0, aux[1]>>>(a);
-            cudaEventRecord(ev[2], aux[1]);
-        }
         k_zp_huftab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
         k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
         cudaStreamWaitEvent(st, ev[1], 0);
-        if (pf_with_exec == 1)
-        {
-            cudaEventRecord(ev[0], st);
-            cudaStreamWaitEvent(aux[1], ev[0], 0);
-            k_zp_prefill<<<pf_grid, ZP0_THREADS, 0, aux[1]>>>(a);
-            cudaEventRecord(ev[2], aux[1]);
-        }
-        else if (pf_with_exec == 0)
-            cudaStreamWaitEvent(st, ev[2], 0);
+        cudaEventRecord(ev[0], st);
+        cudaStreamWaitEvent(aux[1], ev[0], 0);
+        k_zp_prefill<<<pf_grid, ZP0_THREADS, 0, aux[1]>>>(a);
+        cudaEventRecord(ev[2], aux[1]);
         k_zp_execute<<<(unsigned) ((n + ZP4_WARPS - 1) / ZP4_WARPS), ZP4_THREADS, ZP4_SMEM, st>>>(a);
-        if (pf_with_exec)
-            cudaStreamWaitEvent(st, ev[2], 0);
+        cudaStreamWaitEvent(st, ev[2], 0);
         /* frames the pipeline declined (flag set): decoded from scratch, one warp per frame */
         k_zstd_decode_w<<<(unsigned) ((n + ZSW_WARPS - 1) / ZSW_WARPS), ZSW_THREADS, ZSW_SMEM, st>>>(
             methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,

@@ -34,7 +34,7 @@
 #define ZP_METHOD_ZSTD 1
 #define ZP_MAXB   16u           /* zstd blocks per frame the pipeline takes (1 MiB / 128 KiB = 8) */
 #define ZP_G      8u            /* frames per entropy warp */
-#define ZP_BF     18u           /* u32 fields per block descriptor */
+#define ZP_BF     19u           /* u32 fields per block descriptor */
 #define ZP_PREFILL_MIN 2048u     /* raw / RLE blocks at least this long are written ahead by stage 0 */
 #define ZP_FF     4u            /* u32 fields per frame descriptor: nblk, fcs, has_fcs, - */
 
@@ -52,11 +52,12 @@ enum
     ZPB_SEQOFF,                 /* block-relative offset of the first table description */
     ZPB_LITPOS,                 /* byte offset in the frame's literal area (multiple of 16) */
     ZPB_SEQPOS,                 /* entry offset in the frame's sequence area */
-    ZPB_SPECPOS,                /* raw / RLE: output position stage 0 assumed and wrote at, or ~0u */
+    ZPB_SPECPOS,                /* raw / RLE block that stage 0 is to write: 0, any other block: ~0u */
     ZPB_HDBLK,                  /* index of the block whose Huffman tree is in force */
     ZPB_HINFO,                  /* written by stage 2a: table log | description bytes << 8 (0: failed) */
     ZPB_SLOGS,                  /* written by stage 3a: ll_log | of_log << 8 | ml_log << 16 | 1 << 31 */
-    ZPB_BITOFF                  /* written by stage 3a: block-relative offset of the sequence bitstream */
+    ZPB_BITOFF,                 /* written by stage 3a: block-relative offset of the sequence bitstream */
+    ZPB_OUTSZ                   /* bytes the block regenerates: stage 1 (raw, RLE, no sequences) or stage 3b (literals + matches) */
 };
 
 struct ZpArgs
@@ -138,8 +139,6 @@ CRYO_DEV bool zp_parse(const uint8_t *in, uint32_t csize, uint32_t cap, uint64_t
         return false;
 
     uint32_t nb = 0, lit_total = 0, seq_total = 0, hd_off = 0, hd_left = 0, hd_blk = 0;
-    uint64_t spec = 0;                          /* output position if every earlier Compressed block is full */
-    const uint64_t spec_lim = fcs_bytes ? fcs : 0;
     bool     have_hd = false;
 
     for (;;)
@@ -156,8 +155,8 @@ CRYO_DEV bool zp_parse(const uint8_t *in, uint32_t csize, uint32_t cap, uint64_t
         b[ZPB_OFF] = ip;
         b[ZPB_BSIZE] = bsize;
         b[ZPB_KIND] = type;
-        b[ZPB_SPECPOS] = (type < 2 && bsize >= ZP_PREFILL_MIN && spec + bsize <= spec_lim) ? (uint32_t) spec : ~0u;
-        spec += type < 2 ? bsize : ZS_MAXBLOCK;
+        b[ZPB_SPECPOS] = (type < 2 && bsize >= ZP_PREFILL_MIN) ? 0u : ~0u;
+        b[ZPB_OUTSZ] = bsize;                   /* raw, RLE; Compressed: below and stage 3b */
         if (type == 0)
         {
             if (bsize > csize - ip)
@@ -286,6 +285,7 @@ CRYO_DEV bool zp_parse(const uint8_t *in, uint32_t csize, uint32_t cap, uint64_t
             b[ZPB_HINFO] = 0;
             b[ZPB_SLOGS] = 0;
             b[ZPB_BITOFF] = 0;
+            b[ZPB_OUTSZ] = regen;                /* + the match lengths, added by stage 3b */
             b[ZPB_NSEQ] = nseq;
             b[ZPB_SEQOFF] = sp;
             b[ZPB_LITPOS] = lit_total;
@@ -348,23 +348,48 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
 /* ------------------------------------------------- stage 0: raw / RLE blocks ahead ---- */
 
 /*
- * libzstd cuts a frame into full 128 KiB blocks (only the last one is short), so the output
- * position of a Raw or RLE block is known from the headers alone if that holds.  Stage 0
- * writes those blocks at the assumed position, at HBM speed, WHILE stage 4 runs (that one is
- * bound by instruction issue).  Stage 4 skips a block when it arrives at exactly the assumed
- * position (and writes it itself otherwise; anything stage 0 wrote is then overwritten).  It
+ * The output position of a Raw or RLE block is known once the blocks before it have been
+ * measured (stage 3b sums the match lengths of every Compressed block; zp_frame_positions).  Stage 0
+ * writes those blocks, at HBM speed, WHILE stage 4 runs (that one is
+ * bound by instruction issue).  Stage 4 skips a block when it arrives at exactly that
+ * position (and writes it itself otherwise).  It
  * needs the bytes only when a later match may read them: before the next Compressed block of
  * the frame it waits until pf_done[frame] says stage 0 has finished the blocks it skipped;
  * should that take too long (stage 0 not scheduled yet) it writes them itself, which is
  * idempotent, so no ordering between the two kernels is assumed.
  * A few persistent CTAs per SM take the frames in index order (item = frame << 8 | block, f < 2^24).
  */
-CRYO_DEV void zp_stage0(const ZpArgs &a, uint32_t item, uint32_t tid, uint32_t nthr)
+/*
+ * Output positions of frame f's blocks for stage 0, from the regenerated sizes (stage 1 for raw,
+ * RLE and sequence-less blocks, stage 3b for the others): pos[j] = position of block j if stage 0
+ * is to write it, ~0u otherwise (not a candidate, would not fit the capacity, frame flagged).
+ * Stage 4 arrives at the same positions by construction: it regenerates exactly those sizes.
+ */
+CRYO_DEV void zp_frame_positions(const ZpArgs &a, uint32_t f, uint32_t *pos)
+{
+    const uint32_t nb = a.fr[(size_t) f * ZP_FF];
+    const bool     live = a.flag[f] == 0;
+    uint64_t at = 0;
+
+    for (uint32_t j = 0; j < ZP_MAXB; j++)
+    {
+        const uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
+
+        pos[j] = ~0u;
+        if (j >= nb)
+            continue;
+        if (live && b[ZPB_SPECPOS] != ~0u && at + b[ZPB_BSIZE] <= a.cap)
+            pos[j] = (uint32_t) at;
+        at += b[ZPB_OUTSZ];
+    }
+}
+
+CRYO_DEV void zp_stage0(const ZpArgs &a, uint32_t item, uint32_t at, uint32_t tid, uint32_t nthr)
 {
     const uint32_t f = item >> 8, j = item & 0xFFu;
     const uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
     const uint8_t *in = a.src + a.src_off[f] + b[ZPB_OFF];
-    uint8_t *dst = a.dst + (size_t) f * a.dst_stride + b[ZPB_SPECPOS];
+    uint8_t *dst = a.dst + (size_t) f * a.dst_stride + at;
 
     if ((b[ZPB_KIND] & 3u) == 0)
         team_copy(dst, in, b[ZPB_BSIZE], tid, nthr);
@@ -1206,7 +1231,7 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
     /* bits consumed are not counted per read: loaded bits minus what is left says it at the end
      * (a walk that reads past the start of the stream never gets back to an exact balance) */
     const int32_t total = remaining, loaded0 = avail, npos0 = npos;
-    uint32_t sl = 0, so = 0, sm = 0;
+    uint32_t sl = 0, so = 0, sm = 0, mlsum = 0;
 
     ZP3B_ENSURE(act);
     ZP3B_REFILL(act);
@@ -1249,8 +1274,13 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         sm = more ? ((cm >> 16) & 0x3FFu) + ((t >> nbo) & ((1u << nbm) - 1u)) : sm;
         so = more ? ((co >> 16) & 0x3FFu) + (t & ((1u << nbo) - 1u)) : so;
         if (on)
+        {
             out[i] = (uint64_t) ll | ((uint64_t) ml << 17) | ((uint64_t) (ov & 0x1FFFFFFFu) << 35);
+            mlsum += ml;
+        }
     }
+    if (act)
+        a.blk[((size_t) f * ZP_MAXB + j) * ZP_BF + ZPB_OUTSZ] += mlsum;     /* regen + match bytes (< 2^32) */
     remaining = total - (loaded0 + 8 * (npos0 - npos) - avail);
 #undef ZP3B_FILL
 #undef ZP3B_REFILL
@@ -1305,17 +1335,20 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         seen_ = __shfl_sync(CRYO_FULL, seen_, 0);                                            \
         if (seen_ < skipped)                                                                 \
         {                                                                                    \
+            uint32_t at_ = 0;                                                                \
+                                                                                             \
             for (uint32_t jj_ = 0; jj_ < j; jj_++)                                           \
             {                                                                                \
                 const uint32_t *bb_ = a.blk + ((size_t) f * ZP_MAXB + jj_) * ZP_BF;          \
                                                                                              \
-                if ((bb_[ZPB_KIND] & 3u) < 2u && (skipmask >> jj_) & 1u)                     \
+                if ((skipmask >> jj_) & 1u)                                                  \
                 {                                                                            \
                     if ((bb_[ZPB_KIND] & 3u) == 0)                                           \
-                        team_copy(o.out + bb_[ZPB_SPECPOS], fin + bb_[ZPB_OFF], bb_[ZPB_BSIZE], lane, 32); \
+                        team_copy(o.out + at_, fin + bb_[ZPB_OFF], bb_[ZPB_BSIZE], lane, 32); \
                     else                                                                     \
-                        team_fill_byte(o.out + bb_[ZPB_SPECPOS], fin[bb_[ZPB_OFF]], bb_[ZPB_BSIZE], lane, 32); \
+                        team_fill_byte(o.out + at_, fin[bb_[ZPB_OFF]], bb_[ZPB_BSIZE], lane, 32); \
                 }                                                                            \
+                at_ += bb_[ZPB_OUTSZ];                                                       \
             }                                                                                \
             __syncwarp();                                                                    \
         }                                                                                    \
@@ -1352,7 +1385,7 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
             }
             if (bsize == 0)
                 continue;
-            if (b[ZPB_SPECPOS] == o.pos)
+            if (b[ZPB_SPECPOS] != ~0u)
             {
                 /* stage 0 writes this block here (it may not have yet): move on without touching
                  * the output, the ring's tail comes from the block's own description */

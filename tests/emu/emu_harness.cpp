@@ -377,21 +377,27 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
      * times out waiting for it and writes the blocks it needs itself */
     const bool late_prefill = getenv("ZP_EMU_LATE_PREFILL") != nullptr;
     auto prefill = [&]() {
-        emu::launch(dim3(3), dim3(128), 0, [&]() {
+        emu::launch(dim3(3), dim3(128), 64, [&]() {
+            uint32_t *pos = reinterpret_cast<uint32_t *>(CRYO_SMEM_BASE());
+
             for (uint32_t f = blockIdx.x; f < a.n; f += 3)
+            {
+                __syncthreads();
+                if (threadIdx.x == 0)
+                    zp_frame_positions(a, f, pos);
+                __syncthreads();
                 for (uint32_t j = 0; j < fr[(size_t) f * ZP_FF]; j++)
                 {
-                    if (blk[((size_t) f * ZP_MAXB + j) * ZP_BF + ZPB_SPECPOS] == ~0u)
+                    if (pos[j] == ~0u)
                         continue;
-                    zp_stage0(a, (f << 8) | j, threadIdx.x, 128);
+                    zp_stage0(a, (f << 8) | j, pos[j], threadIdx.x, 128);
                     __syncthreads();
                     if (threadIdx.x == 0)
                         zp_stage0_done(a, (f << 8) | j, 1);
                 }
+            }
         });
     };
-    if (!late_prefill)
-        prefill();
     emu::launch(dim3((((unsigned) n + 31) / 32) * ZP_MAXB), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
         zp_stage2a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
@@ -408,6 +414,8 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP3B_SMEM(ZP3B_LARGE, ZP_G), [&]() {
         zp_stage3b<ZP3B_LARGE, ZP3B_SMALL, ZP_G>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
+    if (!late_prefill)
+        prefill();
     emu::launch(dim3(((unsigned) n + ZP4_WARPS - 1) / ZP4_WARPS), dim3(ZP4_THREADS), ZP4_SMEM, [&]() {
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         zp_stage4(a, blockIdx.x * ZP4_WARPS + warp, CRYO_SMEM_BASE() + warp * ZP4_PER_WARP, lane);

@@ -270,3 +270,30 @@ def test_emulated_pipeline_random_frames(oracle_port):
         assert np.array_equal(outs[k][: osz[k]], plain[k]), k
     # the pipeline itself should have taken nearly all of them (levels up to 6 rarely use Repeat_Mode)
     assert sum(1 for f in fl if f == 0) >= 30, fl
+
+
+@pytest.mark.parametrize("late_prefill", [False, True])
+def test_emulated_pipeline_decodes_own_encoder_frames(oracle_ref, late_prefill, monkeypatch):
+    """Frames written by zstd_encode.cuh (64 KiB zstd blocks, RLE blocks for the zero interior of a
+    sparse cryo block): Compressed blocks that are not 128 KiB long in front of RLE blocks, so the
+    positions of the raw / RLE stage must come from measured block sizes, not from an assumed
+    block length."""
+    if late_prefill:
+        monkeypatch.setenv("ZP_EMU_LATE_PREFILL", "1")
+    L = _pipeline_lib()
+    L.emu_zstd_encode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]
+    L.emu_zstd_encode.restype = C.c_int
+    blocks = [bg.make_block("S", "hex", 41), bg.regression_block(1, 290), bg.make_block("M", "hex", 42)]
+    comp = []
+    for blk in blocks:
+        cap = blk.size + (blk.size >> 8) + 128
+        out = np.zeros(cap, dtype=np.uint8)
+        sz = C.c_uint32(0)
+        assert L.emu_zstd_encode(blk.ctypes.data, blk.size, out.ctypes.data, cap, 1, C.byref(sz)) == 0
+        comp.append(out[: sz.value].copy())
+        back, ok = oracle_ref.decompress_one(1, comp[-1])
+        assert ok and np.array_equal(back, blk)
+    st, osz, outs, fl = _run_pipeline(L, comp, shift=2)
+    for i, blk in enumerate(blocks):
+        assert st[i] == 0 and osz[i] == MiB and np.array_equal(outs[i], blk), i
+        assert fl[i] == 0, i

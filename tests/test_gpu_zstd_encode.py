@@ -106,3 +106,19 @@ def test_zstd_encode_large_batch_persistent_grid(gpu, oracle_ref):
         assert np.array_equal(comp[i], comp[i % 6]), i  # deterministic, no cross-block leakage
     back, ok, _ = oracle_ref.decompress([COMP_ZSTD] * 6, *oracle_ref.pack(comp[:6]))
     assert ok.all() and np.array_equal(back, uniq)
+
+
+def test_zstd_gpu_frames_through_the_gpu_pipeline_large_batch(gpu):
+    """400 sparse and medium blocks compressed on the GPU (64 KiB zstd blocks, RLE blocks behind
+    Compressed blocks that are not 128 KiB long) and decompressed on the GPU: the decode
+    pipeline's raw / RLE stage runs beside its executor, so its block positions must be exact
+    for frames libzstd did not write, too.  The pipeline itself must take them (no fallback)."""
+    kinds = [("S", "hex"), ("M", "hex"), ("S", "lowcard"), ("M", "lowcard")]
+    blocks = np.stack([bg.make_block(k, p, 100 + i) for i, (k, p) in enumerate(kinds * 100)])
+    comp, st = encode_device(gpu, COMP_ZSTD, 1, blocks)
+    assert (st == 0).all()
+    out, osz, dst = decode_device(gpu, COMP_ZSTD, comp)
+    assert (dst == 0).all() and (osz == CRYO_BLCKSZ).all()
+    assert np.array_equal(out, blocks)
+    frames, fallback = gpu.zstd_pipeline_stats()
+    assert frames == len(comp) and fallback == 0, (frames, fallback)
