@@ -629,7 +629,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         k_zp_parse<<<(unsigned) ((n + 31) / 32), 32, 0, st>>>(a);
         /*
          * literals (st) and sequences (aux 0) are independent of each other and bound by latency.
-         * Once the sequences are walked the positions of the raw / RLE blocks are known (stage 3c);
+         * Once the sequences are walked the positions of the raw / RLE blocks are known (zp_frame_positions);
          * those blocks (aux 1, one persistent CTA per SM, bound by HBM) are then written beside the
          * executor (st, bound by instruction issue), which synchronises with them per frame through
          * pf_done.  Running them beside the entropy stages instead was measured slower (a stage that

@@ -349,15 +349,14 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
 
 /*
  * The output position of a Raw or RLE block is known once the blocks before it have been
- * measured (stage 3b sums the match lengths of every Compressed block; zp_frame_positions).  Stage 0
- * writes those blocks, at HBM speed, WHILE stage 4 runs (that one is
- * bound by instruction issue).  Stage 4 skips a block when it arrives at exactly that
- * position (and writes it itself otherwise).  It
- * needs the bytes only when a later match may read them: before the next Compressed block of
- * the frame it waits until pf_done[frame] says stage 0 has finished the blocks it skipped;
- * should that take too long (stage 0 not scheduled yet) it writes them itself, which is
- * idempotent, so no ordering between the two kernels is assumed.
- * A few persistent CTAs per SM take the frames in index order (item = frame << 8 | block, f < 2^24).
+ * measured (stage 1 for raw, RLE and sequence-less blocks; stage 3b sums the match lengths of
+ * the others; zp_frame_positions).  Stage 0 writes those blocks, at HBM speed, WHILE stage 4
+ * runs (that one is bound by instruction issue); stage 4 steps over them.  It needs their bytes
+ * only when a later match reads them: before the first such read it waits until
+ * pf_done[frame] says stage 0 has published the frame's blocks; should that take too long
+ * (stage 0 not scheduled yet) it writes them itself, which is idempotent, so no ordering
+ * between the two kernels is assumed.  One persistent CTA per SM takes the frames in index
+ * order (item = frame << 8 | block).
  */
 /*
  * Output positions of frame f's blocks for stage 0, from the regenerated sizes (stage 1 for raw,
