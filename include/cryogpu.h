@@ -103,6 +103,12 @@ void        cryogpu_host_free(void *p);
  *   d_status[i]    CRYOGPU_ST_*
  *   stream         a cudaStream_t (NULL = the context's own stream); the call only
  *                  enqueues work, it does not synchronise
+ *
+ * Ordering: the kernels' work areas belong to the context, so the device-resident calls of ONE
+ * context execute one after the other on the device whatever streams they are given (each call's
+ * stream first waits for an event recorded at the end of the previous call).  Use one context per
+ * stream for calls that should overlap.  Work areas grow on demand (the first call of a given size
+ * allocates, which waits for the device); a steady-state call only enqueues.
  */
 int cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n,
                               const int32_t *d_methods,
@@ -153,6 +159,14 @@ void cryogpu_last_transfer_bytes(const cryogpu_ctx *ctx, uint64_t *h2d, uint64_t
  * Diagnostics for tests and benchmarks; the reference has no counterpart.
  */
 int cryogpu_zstd_pipeline_stats(cryogpu_ctx *ctx, uint64_t *frames, uint64_t *fallback_frames);
+
+/*
+ * LZ4 blocks of the last cryogpu_decompress_device call on this context when it was routed per block
+ * (batches of more than two blocks per SM): how many blocks the call had, and how many of them the
+ * router sent to the CTA-per-block decoder (lz4_decode_c.cuh: blocks with many sequences); smaller
+ * batches go to that decoder whole and report 0 / 0.  Waits for the device.  Diagnostics.
+ */
+int cryogpu_lz4_route_stats(cryogpu_ctx *ctx, uint64_t *blocks, uint64_t *cta_blocks);
 
 /*
  * Multi-GPU host variants: the batch is split into contiguous block ranges, one

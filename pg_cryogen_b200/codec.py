@@ -49,6 +49,7 @@ _PROTOS = {
                                           C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cryogpu_last_transfer_bytes": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "cryogpu_zstd_pipeline_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "cryogpu_lz4_route_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "cryogpu_decompress_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
                                           C.c_void_p]),
@@ -134,6 +135,14 @@ class CryoGPU:
         rc = self.lib.cryogpu_zstd_pipeline_stats(self.handle, C.byref(a), C.byref(b))
         if rc != 0:
             raise CryoGPUError("cryogpu_zstd_pipeline_stats: " + self.lib.cryogpu_last_error().decode())
+        return int(a.value), int(b.value)
+
+    def lz4_route_stats(self) -> tuple[int, int]:
+        """(blocks of the last routed decompress_device call, blocks the router gave to the CTA-per-block decoder)."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        rc = self.lib.cryogpu_lz4_route_stats(self.handle, C.byref(a), C.byref(b))
+        if rc != 0:
+            raise CryoGPUError("cryogpu_lz4_route_stats: " + self.lib.cryogpu_last_error().decode())
         return int(a.value), int(b.value)
 
     def close(self):

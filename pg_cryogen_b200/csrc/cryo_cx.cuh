@@ -1,0 +1,553 @@
+/*
+ * cryo_cx.cuh -- CTA-cooperative output executor ("one CTA owns one cryo block").
+ *
+ * The warp executor (cryo_wexec.cuh) walks the sequences of a block one after the other:
+ * fine when thousands of blocks are in flight, hopeless for the call the reference actually
+ * makes (one block per call, cache.c:178) and for match-rich blocks (120 K sequences at one
+ * L2 round trip each).  Here the whole CTA works on ONE block and the sequences themselves are
+ * the unit of parallelism:
+ *
+ *   - the front end (lz4_decode_c.cuh, zstd_decode_c.cuh) hands over CX_THREADS sequences at a
+ *     time, one per thread: literal length, match length, offset, where the literals are;
+ *   - output positions are a CTA-wide prefix sum, so every sequence knows where it writes
+ *     before any byte moves;
+ *   - literals depend on nothing: all threads place theirs at once (a lane for a short run,
+ *     the warp for a medium one);
+ *   - a match depends only on the matches that wrote its source bytes.  Which sequences those
+ *     are follows from the positions (a search in the prefix sums); every warp publishes a bit
+ *     mask of its finished sequences in shared memory, and a match is copied as soon as the bits
+ *     it needs are set.  Independent matches -- most of them -- move in the same round; chains of
+ *     dependent ones cost one round per link, not one per sequence;
+ *   - the most recent output lives in a CX_RING-byte ring in shared memory, so a match source
+ *     is a shared-memory read (LZ4's whole 64 KiB window fits); the ring drains to HBM as
+ *     aligned 16-byte vectors by all threads;
+ *   - runs of CX_BIG bytes or more (the ~1 MB zero run of a sparse block, RLE blocks, long
+ *     literal runs) bypass the ring: the whole CTA streams them to global memory, overlapping
+ *     matches as periodic fills, and the ring's history is reloaded afterwards.
+ *
+ * All functions are CTA-collective: every thread calls them, uniform arguments are marked.
+ */
+#pragma once
+#include "cryo_common.cuh"
+
+#ifndef CX_THREADS
+#define CX_THREADS 1024u
+#endif
+#define CX_WARPS   (CX_THREADS / 32u)
+#define CX_RING    131072u              /* power of two; >= CX_HIST + CX_SPAN + slack */
+#define CX_RMASK   (CX_RING - 1u)
+#define CX_SPAN    32768u               /* output bytes one chunk of sequences may cover */
+#define CX_BIG     8192u                /* runs at least this long are CTA-wide bulk operations (2 * CX_BIG <= CX_SPAN) */
+#define CX_LANE    32u                  /* runs up to this long are moved by the sequence's own lane */
+#define CX_HIST    65536u               /* history reloaded into the ring after a bulk operation (LZ4: offsets <= 65535) */
+#define CX_PAT     1024u                /* pattern staging for periodic fills (k * off >= 512, + 32) */
+
+#ifdef CRYO_EMU
+#define CX_LDCG(p) (*(p))
+#define CX_VLD(p) (*reinterpret_cast<const volatile uint32_t *>(p))
+#define CX_VST(p, v) (*reinterpret_cast<volatile uint32_t *>(p) = (v))
+#else
+#define CX_LDCG(p) __ldcg(p)
+#define CX_VLD(p) (*reinterpret_cast<const volatile uint32_t *>(p))
+#define CX_VST(p, v) (*reinterpret_cast<volatile uint32_t *>(p) = (v))
+#endif
+
+/* shared-memory control block of one CTA */
+struct CxSh
+{
+    uint32_t wsa[CX_WARPS + 1], wsb[CX_WARPS + 1];     /* scan scratch: per-warp sums, [CX_WARPS] = total */
+    uint32_t cut;                       /* first sequence of the chunk that is not executed in it */
+    uint32_t err;                       /* (sequence index << 8 | status) of the first failing sequence, ~0u: none */
+    uint32_t bcast[4];
+    uint32_t done[CX_WARPS];            /* per warp: bit l set = the match of the warp's sequence l is in the ring */
+    uint32_t pend[CX_THREADS];          /* end position of every sequence of the chunk (dependency search) */
+};
+
+/* per-thread view; every field is uniform over the CTA */
+struct Cx
+{
+    uint8_t    *out;                    /* global output block, 16-byte aligned */
+    uint8_t    *ring;                   /* shared, CX_RING bytes, 16-byte aligned */
+    uint8_t    *pat;                    /* shared, CX_PAT + 32 bytes, 16-byte aligned */
+    CxSh       *sh;
+    uint32_t    cap;
+    uint32_t    pos;                    /* next output byte */
+    uint32_t    flushed;                /* multiple of 16; out[0, flushed) is in global memory */
+    uint32_t    ring_lo;                /* the ring holds out[max(ring_lo, newest - CX_RING), pos) */
+    int         err;
+};
+
+CRYO_DEV void cx_init(Cx &cx, uint8_t *out, uint32_t cap, uint8_t *ring, uint8_t *pat, CxSh *sh)
+{
+    cx.out = out;
+    cx.cap = cap;
+    cx.ring = ring;
+    cx.pat = pat;
+    cx.sh = sh;
+    cx.pos = 0;
+    cx.flushed = 0;
+    cx.ring_lo = 0;
+    cx.err = ST_OK;
+}
+
+/*
+ * Inclusive prefix sums of two values over the CTA (thread order).  Totals are left in
+ * sh->wsa[CX_WARPS] / sh->wsb[CX_WARPS].  Two barriers; the caller keeps a barrier between two
+ * calls (every use below has one).
+ */
+CRYO_DEV void cx_scan2(CxSh *sh, uint32_t &a, uint32_t &b, uint32_t tid)
+{
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+
+#pragma unroll
+    for (uint32_t d = 1; d < 32; d <<= 1)
+    {
+        const uint32_t x = __shfl_up_sync(CRYO_FULL, a, d), y = __shfl_up_sync(CRYO_FULL, b, d);
+
+        if (lane >= d)
+        {
+            a += x;
+            b += y;
+        }
+    }
+    if (lane == 31)
+    {
+        sh->wsa[warp] = a;
+        sh->wsb[warp] = b;
+    }
+    __syncthreads();
+    if (warp == 0)
+    {
+        uint32_t x = lane < CX_WARPS ? sh->wsa[lane] : 0u, y = lane < CX_WARPS ? sh->wsb[lane] : 0u;
+        const uint32_t x0 = x, y0 = y;
+
+#pragma unroll
+        for (uint32_t d = 1; d < 32; d <<= 1)
+        {
+            const uint32_t p = __shfl_up_sync(CRYO_FULL, x, d), q = __shfl_up_sync(CRYO_FULL, y, d);
+
+            if (lane >= d)
+            {
+                x += p;
+                y += q;
+            }
+        }
+        if (lane < CX_WARPS)
+        {
+            sh->wsa[lane] = x - x0;     /* exclusive */
+            sh->wsb[lane] = y - y0;
+        }
+        if (lane == CX_WARPS - 1u)
+        {
+            sh->wsa[CX_WARPS] = x;
+            sh->wsb[CX_WARPS] = y;
+        }
+    }
+    __syncthreads();
+    a += sh->wsa[warp];
+    b += sh->wsb[warp];
+}
+
+/* one byte of already produced output: the ring when it is there, global memory otherwise */
+CRYO_DEV uint8_t cx_src(const Cx &cx, uint32_t x, uint32_t lo)
+{
+    return x >= lo ? cx.ring[x & CX_RMASK] : CX_LDCG(cx.out + x);
+}
+
+/* team copy of n bytes from src (global or shared) into the ring at output position p (split at the wrap) */
+CRYO_DEV void cx_ring_put(Cx &cx, uint32_t p, const uint8_t *src, uint32_t n, uint32_t tid, uint32_t nthr)
+{
+    const uint32_t a = p & CX_RMASK, first = CX_RING - a < n ? CX_RING - a : n;
+
+    team_copy(cx.ring + a, src, first, tid, nthr);
+    if (first < n)
+        team_copy(cx.ring, src + first, n - first, tid, nthr);
+}
+
+CRYO_DEV void cx_ring_fill(Cx &cx, uint32_t p, uint8_t b, uint32_t n, uint32_t tid, uint32_t nthr)
+{
+    const uint32_t a = p & CX_RMASK, first = CX_RING - a < n ? CX_RING - a : n;
+
+    team_fill_byte(cx.ring + a, b, first, tid, nthr);
+    if (first < n)
+        team_fill_byte(cx.ring, b, n - first, tid, nthr);
+}
+
+/* drain out[flushed, pos & ~15) from the ring, all threads; ring writes are behind a barrier */
+CRYO_DEV void cx_drain(Cx &cx, uint32_t tid)
+{
+    const uint32_t p0 = cx.pos & ~15u;
+
+    for (uint32_t a = cx.flushed + 16u * tid; a < p0; a += 16u * CX_THREADS)
+        st16(cx.out + a, ld16(cx.ring + (a & CX_RMASK)));
+    cx.flushed = p0;
+}
+
+/* the (< 16) bytes between flushed and pos, bytewise (end of block, before a bulk operation) */
+CRYO_DEV void cx_drain_tail(Cx &cx, uint32_t tid)
+{
+    if (tid < cx.pos - cx.flushed)
+        cx.out[cx.flushed + tid] = cx.ring[(cx.flushed + tid) & CX_RMASK];
+}
+
+/* after a bulk operation wrote out[.., pos) straight to global memory: reload the ring's history */
+CRYO_DEV void cx_reload(Cx &cx, uint32_t tid)
+{
+    const uint32_t lo = cx.pos > CX_HIST ? cx.pos - CX_HIST : 0u, a0 = lo & ~15u;
+
+    __syncthreads();                    /* the bulk stores of every thread */
+    for (uint32_t a = a0 + 16u * tid; a < cx.pos; a += 16u * CX_THREADS)
+    {
+        const uint4 v = CX_LDCG(reinterpret_cast<const uint4 *>(cx.out + a));
+
+        st16(cx.ring + (a & CX_RMASK), v);      /* may run up to 15 bytes past pos: those slots are rewritten later */
+    }
+    cx.flushed = cx.pos & ~15u;
+    cx.ring_lo = lo;
+    __syncthreads();
+}
+
+/* long match straight on global memory by the whole CTA; out[0, pos) is in global memory */
+CRYO_DEV void cx_bulk_match(Cx &cx, uint32_t off, uint32_t n, uint32_t tid)
+{
+    uint8_t *dst = cx.out + cx.pos;
+
+    if (off >= n)
+    {
+        team_copy(dst, dst - off, n, tid, CX_THREADS);
+        return;
+    }
+    if (off == 1)
+    {
+        team_fill_byte(dst, CX_LDCG(dst - 1), n, tid, CX_THREADS);
+        return;
+    }
+    if (off < 512u)
+    {
+        /* k whole periods (k * off >= 512) staged in shared memory, then a pattern fill */
+        const uint32_t k = (512u + off - 1u) / off, plen = k * off;
+        const uint8_t *src = dst - off;
+
+        for (uint32_t j = tid; j < plen + 32u; j += CX_THREADS)
+            cx.pat[j] = CX_LDCG(src + j % off);
+        __syncthreads();
+        team_fill_from_pattern(dst, cx.pat, plen, 0, n, tid, CX_THREADS);
+        return;
+    }
+    /* long period: every round copies the largest whole number of periods available */
+    uint32_t done = 0;
+
+    while (done < n)
+    {
+        const uint32_t avail = ((off + done) / off) * off;
+        const uint32_t m = n - done < avail ? n - done : avail;
+
+        team_copy(dst + done, dst + done - avail, m, tid, CX_THREADS);
+        done += m;
+        __syncthreads();
+    }
+}
+
+/*
+ * One sequence as a bulk operation (uniform arguments): ll literal bytes from lit (rle_byte >= 0:
+ * ll copies of that byte), then a match of ml bytes at distance off.  Bounds were checked.
+ */
+CRYO_DEV void cx_bulk(Cx &cx, uint32_t ll, const uint8_t *lit, int rle_byte, uint32_t ml, uint32_t off, uint32_t tid)
+{
+    __syncthreads();                    /* ring writes of the previous chunk */
+    cx_drain(cx, tid);
+    cx_drain_tail(cx, tid);
+    if (ll)
+    {
+        if (rle_byte >= 0)
+            team_fill_byte(cx.out + cx.pos, (uint8_t) rle_byte, ll, tid, CX_THREADS);
+        else
+            team_copy(cx.out + cx.pos, lit, ll, tid, CX_THREADS);
+        cx.pos += ll;
+    }
+    if (ml)
+    {
+        __syncthreads();                /* the match may read the literals and the drained tail */
+        cx_bulk_match(cx, off, ml, tid);
+        cx.pos += ml;
+    }
+    cx_reload(cx, tid);
+}
+
+/* lower bound in sh->pend[0, n): first index whose end position is > x */
+CRYO_DEV uint32_t cx_first_end_above(const CxSh *sh, uint32_t n, uint32_t x)
+{
+    uint32_t lo = 0, hi = n;
+
+    while (lo < hi)
+    {
+        const uint32_t mid = (lo + hi) >> 1;
+
+        if (sh->pend[mid] > x)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return lo;
+}
+
+/*
+ * Execute a chunk.  Thread t offers sequence t (valid: t < n, n <= CX_THREADS uniform):
+ *   ll, ml, off   literal length, match length (0: none -- the last sequence of an LZ4 block, or
+ *                 the literal tail of a zstd block), match distance
+ *   lit           where the ll literal bytes are (global or shared memory); rle_byte >= 0: the
+ *                 literals are ll copies of that byte
+ *   cum           inclusive prefix sum of ll + ml over the chunk (cx_scan2)
+ *   pre           a status the front end already found for this sequence (ST_OK: none)
+ * Returns how many sequences were executed (a prefix of the chunk; the caller offers the rest
+ * again), 0 when the block failed (cx.err).  A sequence with a run of CX_BIG bytes or more is
+ * executed alone, as a bulk operation.
+ */
+CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_t off, const uint8_t *lit,
+                           int rle_byte, uint32_t cum, int pre, uint32_t tid)
+{
+    CxSh *sh = cx.sh;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const bool     valid = tid < n;
+    const uint32_t pos0 = cx.pos;
+    const uint32_t end = pos0 + cum, start = end - ll - ml, mpos = start + ll;
+    const bool     big = valid && (ll >= CX_BIG || ml >= CX_BIG);
+
+    /* the prefix that is executed now: up to the first big sequence or the first one past the span */
+    if (tid == 0)
+    {
+        sh->cut = n;
+        sh->err = ~0u;
+    }
+    __syncthreads();
+    {
+        const uint32_t stop = __ballot_sync(CRYO_FULL, !valid || big || cum > CX_SPAN);
+
+        if (stop && lane == 0)
+            atomicMin(&sh->cut, (warp << 5) + (uint32_t) __ffs((int) stop) - 1u);
+    }
+    __syncthreads();
+    uint32_t       k = sh->cut;
+    const bool     alone = k == 0;      /* sequence 0 is big (n >= 1 and cum_0 < 2 * CX_BIG <= CX_SPAN otherwise) */
+
+    if (alone)
+        k = 1;
+    /* checks of the sequences that are executed now: the first failing one names the status */
+    {
+        int e = ST_OK;
+
+        if (tid < k)
+        {
+            if (pre != ST_OK)
+                e = pre;
+            else if (end > cx.cap || end < pos0)
+                e = ST_OUTPUT;
+            else if (ml && (off == 0 || off > mpos))
+                e = ST_OFFSET;
+        }
+        const uint32_t bad = __ballot_sync(CRYO_FULL, e != ST_OK);
+
+        if (bad && lane == (uint32_t) __ffs((int) bad) - 1u)
+            atomicMin(&sh->err, (tid << 8) | (uint32_t) e);
+    }
+    __syncthreads();
+    if (sh->err != ~0u)
+    {
+        cx.err = (int) (sh->err & 0xFFu);
+        return 0;
+    }
+    if (alone)
+    {
+        /* sequence 0 of thread 0 becomes uniform through shared memory */
+        unsigned long long *slot = reinterpret_cast<unsigned long long *>(sh->wsa);
+
+        if (tid == 0)
+        {
+            sh->bcast[0] = ll;
+            sh->bcast[1] = ml;
+            sh->bcast[2] = off;
+            sh->bcast[3] = (uint32_t) rle_byte;
+            slot[0] = (unsigned long long) (uintptr_t) lit;
+        }
+        __syncthreads();
+        const uint32_t ll0 = sh->bcast[0], ml0 = sh->bcast[1], off0 = sh->bcast[2];
+        const int      rb0 = (int) sh->bcast[3];
+        const uint8_t *lit0 = reinterpret_cast<const uint8_t *>((uintptr_t) slot[0]);
+
+        cx_bulk(cx, ll0, lit0, rb0, ml0, off0, tid);
+        return 1;
+    }
+    const bool mine = tid < k;
+    /* positions below lo are not in the ring any more (or never were, after a bulk operation) */
+    const uint32_t kend = pos0 + CX_SPAN;
+    const uint32_t lo = kend > CX_RING && kend - CX_RING > cx.ring_lo ? kend - CX_RING : cx.ring_lo;
+
+    /* ---- literals: no dependencies ---- */
+    if (mine)
+        sh->pend[tid] = end;
+    if (mine && ll && ll <= CX_LANE)
+    {
+        if (rle_byte >= 0)
+            for (uint32_t i = 0; i < ll; i++)
+                cx.ring[(start + i) & CX_RMASK] = (uint8_t) rle_byte;
+        else
+            for (uint32_t i = 0; i < ll; i++)
+                cx.ring[(start + i) & CX_RMASK] = lit[i];
+    }
+    for (uint32_t m = __ballot_sync(CRYO_FULL, mine && ll > CX_LANE); m; m &= m - 1)
+    {
+        const int      j = __ffs((int) m) - 1;
+        const uint32_t jl = __shfl_sync(CRYO_FULL, ll, j), js = __shfl_sync(CRYO_FULL, start, j);
+        const int      jr = __shfl_sync(CRYO_FULL, rle_byte, j);
+        const uint8_t *jp = reinterpret_cast<const uint8_t *>(
+            (uintptr_t) __shfl_sync(CRYO_FULL, (unsigned long long) (uintptr_t) lit, j));
+
+        if (jr >= 0)
+            cx_ring_fill(cx, js, (uint8_t) jr, jl, lane, 32);
+        else
+            cx_ring_put(cx, js, jp, jl, lane, 32);
+    }
+    /* ---- matches: every warp publishes the sequences it has finished ---- */
+    bool     pending = mine && ml != 0;
+    uint32_t mydone = __ballot_sync(CRYO_FULL, !pending);
+
+    if (lane == 0)
+        sh->done[warp] = mydone;
+    __syncthreads();                    /* literals, pend[], done[] */
+    /* which sequences wrote this match's source: [q_lo, q_hi], none when the source is older than the chunk
+     * or lies in the sequence's own literals */
+    uint32_t q_lo = 1, q_hi = 0;
+
+    if (pending)
+    {
+        const uint32_t s = mpos - off;
+        uint32_t       e = s + ml < mpos ? s + ml : mpos;   /* the part of the source that exists before the copy */
+
+        if (e > start)
+            e = start;                  /* own literals are in place */
+        if (e > pos0 && s < e)
+        {
+            q_lo = s > pos0 ? cx_first_end_above(sh, tid, s) : 0u;
+            q_hi = cx_first_end_above(sh, tid, e - 1u);
+            if (q_hi >= tid)
+                q_hi = tid - 1u;        /* (e <= start = pend[tid - 1]: cannot happen; keeps the masks sane) */
+        }
+    }
+    for (;;)
+    {
+        bool ready = false;
+
+        if (pending)
+        {
+            ready = true;
+            if (q_lo <= q_hi)
+                for (uint32_t w = q_lo >> 5; w <= (q_hi >> 5); w++)
+                {
+                    const uint32_t b0 = w == (q_lo >> 5) ? q_lo & 31u : 0u;
+                    const uint32_t b1 = w == (q_hi >> 5) ? q_hi & 31u : 31u;
+                    const uint32_t need = (b1 == 31u ? ~0u : (2u << b1) - 1u) & (~0u << b0);
+                    const uint32_t have = w == warp ? mydone : CX_VLD(&sh->done[w]);
+
+                    if ((have & need) != need)
+                    {
+                        ready = false;
+                        break;
+                    }
+                }
+        }
+        if (__any_sync(CRYO_FULL, ready))
+            __threadfence_block();      /* the flags were read before the bytes they stand for */
+        /* short matches: the sequence's own lane.  An overlapping match reads what it has just written. */
+        if (ready && ml <= CX_LANE)
+        {
+            const uint32_t s = mpos - off;
+
+            if (off >= ml)
+            {
+                for (uint32_t i0 = 0; i0 < ml; i0 += 8)
+                {
+                    uint8_t v[8];
+
+#pragma unroll
+                    for (uint32_t q = 0; q < 8; q++)
+                        v[q] = i0 + q < ml ? cx_src(cx, s + i0 + q, lo) : (uint8_t) 0;
+#pragma unroll
+                    for (uint32_t q = 0; q < 8; q++)
+                        if (i0 + q < ml)
+                            cx.ring[(mpos + i0 + q) & CX_RMASK] = v[q];
+                }
+            }
+            else
+                for (uint32_t i = 0; i < ml; i++)
+                {
+                    const uint32_t x = s + i;
+                    const uint8_t  b = x >= lo ? *reinterpret_cast<volatile uint8_t *>(cx.ring + (x & CX_RMASK))
+                                               : CX_LDCG(cx.out + x);
+
+                    *reinterpret_cast<volatile uint8_t *>(cx.ring + ((mpos + i) & CX_RMASK)) = b;
+                }
+        }
+        /* medium matches: the warp, one after the other */
+        for (uint32_t m = __ballot_sync(CRYO_FULL, ready && ml > CX_LANE); m; m &= m - 1)
+        {
+            const int      j = __ffs((int) m) - 1;
+            const uint32_t jm = __shfl_sync(CRYO_FULL, ml, j), jo = __shfl_sync(CRYO_FULL, off, j);
+            const uint32_t jp = __shfl_sync(CRYO_FULL, mpos, j), s = jp - jo;
+
+            if (jo >= jm || jo >= 32u)
+            {
+                for (uint32_t i0 = 0; i0 < jm; i0 += 32)
+                {
+                    const uint32_t i = i0 + lane;
+
+                    if (i < jm)
+                        cx.ring[(jp + i) & CX_RMASK] = cx_src(cx, s + i, lo);
+                    if (jo < jm)
+                        __syncwarp();   /* the next 32 bytes may read these */
+                }
+            }
+            else
+            {
+                /* period below 32: every byte is one of the jo bytes before the match */
+                uint32_t r = lane % jo;
+                const uint32_t step = 32u % jo;
+
+                for (uint32_t i = lane; i < jm; i += 32)
+                {
+                    cx.ring[(jp + i) & CX_RMASK] = cx_src(cx, s + r, lo);
+                    r += step;
+                    r = r >= jo ? r - jo : r;
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+        const uint32_t newly = __ballot_sync(CRYO_FULL, ready);
+
+        if (newly)
+        {
+            mydone |= newly;
+            __threadfence_block();      /* the bytes before the flag */
+            if (lane == 0)
+                CX_VST(&sh->done[warp], mydone);
+        }
+        pending = pending && !ready;
+        if (__ballot_sync(CRYO_FULL, pending) == 0)
+            break;
+        if (!newly)
+            __nanosleep(32);            /* every pending match of this warp waits for another warp */
+    }
+    __syncthreads();
+    cx.pos = sh->pend[k - 1];
+    cx_drain(cx, tid);
+    return k;
+}
+
+/* end of block: everything to global memory */
+CRYO_DEV void cx_finish(Cx &cx, uint32_t tid)
+{
+    __syncthreads();
+    cx_drain(cx, tid);
+    cx_drain_tail(cx, tid);
+    cx.flushed = cx.pos;
+}

@@ -8,8 +8,8 @@
  */
 #include "../../include/cryogpu.h"
 
-#include "lz4_decode.cuh"
 #include "lz4_decode_w.cuh"
+#include "lz4_decode_c.cuh"
 #include "zstd_decode.cuh"
 #include "zstd_decode_w.cuh"
 #include "zstd_decode_g.cuh"
@@ -62,29 +62,96 @@ fail(int code, const char *fmt, ...)
 
 /* ----------------------------------------------------------------- kernels */
 
-__global__ void __launch_bounds__(LZ4D_THREADS)
-k_lz4_decode(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
-             const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
-             uint32_t *out_size, int32_t *status)
-{
-    const uint32_t b = blockIdx.x;
+/*
+ * Which decoder takes an LZ4 block: the one-warp-per-block kernel (thousands of blocks in flight hide its
+ * serial chain) or the CTA-per-block kernel (lz4_decode_c.cuh), which a block with many sequences needs
+ * whatever the batch size.  The number of sequences is not in the format; it is estimated: eight lanes
+ * walk 64 tokens each from eight evenly spaced bytes of the stream (a walk that starts at a wrong byte
+ * falls in with the true chain after a few tokens), and the bytes per token of the later half of each
+ * walk scale to the stream.  route[b]: 0 = warp, 1 = CTA.
+ */
+#define LZ4R_CX_SEQS 4096u             /* estimated sequences from which the CTA kernel is the faster one */
 
-    if (methods[b] != CRYOGPU_LZ4)
+__global__ void __launch_bounds__(128)
+k_lz4_route(const int32_t *methods, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_size,
+            uint32_t *route, uint32_t n, uint32_t cap)
+{
+    const uint32_t b = blockIdx.x * 4u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+
+    if (b >= n)
         return;
-    lz4_decode_block(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
-                     status + b);
+    uint32_t est = 0;
+    const uint32_t csize = src_size[b];
+
+    if (methods[b] == CRYOGPU_LZ4 && csize >= 1024u && cap <= LZ4C_MAXCAP && lane < 8u)
+    {
+        const uint8_t *in = src + src_off[b];
+        const uint32_t part = csize / 8u, lim = lane == 7u ? csize : (lane + 1u) * part;
+        uint32_t p = lane * part, hops = 0, p16 = p;
+
+        while (hops < 64u && p + 3u <= lim)
+        {
+            const uint32_t tk = in[p];
+            uint32_t q = p + 1u, ll = tk >> 4, ml = tk & 15u;
+
+            if (ll == 15u)
+                for (uint32_t x = 255u; x == 255u && q < lim; ll += x)
+                    x = in[q++];
+            q += ll + 2u;
+            if (ml == 15u)
+                for (uint32_t x = 255u; x == 255u && q < lim; )
+                    x = in[q++];
+            p = q;
+            if (++hops == 16u)
+                p16 = p;
+        }
+        /* tokens of this eighth of the stream at the density of the walk's later part */
+        if (hops > 16u && p > p16)
+            est = (uint32_t) (((uint64_t) part * (hops - 16u)) / (p - p16));
+        else
+            est = hops;
+    }
+    est = __reduce_add_sync(0xffffffffu, est);
+    if (lane == 0)
+        route[b] = est >= LZ4R_CX_SEQS ? 1u : 0u;
+}
+
+/* latency path and match-rich blocks: one CTA per block, persistent CTAs take the routed blocks in order */
+__global__ void __launch_bounds__(CX_THREADS, 1)
+k_lz4_decode_c(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
+               const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
+               uint32_t *out_size, int32_t *status, uint32_t n, const uint32_t *route,
+               uint32_t *counter, unsigned long long *gseq)
+{
+    __shared__ uint32_t next_b;
+
+    for (;;)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            next_b = atomicAdd(counter, 1u);
+        __syncthreads();
+        const uint32_t b = next_b;
+
+        if (b >= n)
+            return;
+        if (methods[b] != CRYOGPU_LZ4 || (route && route[b] != 1u))
+            continue;
+        lz4c_decode_block(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b, status + b,
+                          CRYO_SMEM_BASE(), gseq + (size_t) blockIdx.x * LZ4C_SEQCAP, threadIdx.x);
+    }
 }
 
 /* throughput path: one warp per block, LZ4W_WARPS blocks per CTA */
 __global__ void __launch_bounds__(LZ4W_THREADS)
 k_lz4_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
                const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
-               uint32_t *out_size, int32_t *status, uint32_t n)
+               uint32_t *out_size, int32_t *status, uint32_t n, const uint32_t *route)
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b = blockIdx.x * LZ4W_WARPS + warp;
 
-    if (b >= n || methods[b] != CRYOGPU_LZ4)
+    if (b >= n || methods[b] != CRYOGPU_LZ4 || (route && route[b] != 0u))
         return;
     lz4w_decode_block(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
                       status + b, CRYO_SMEM_BASE() + warp * LZ4W_PER_WARP, lane);
@@ -486,9 +553,9 @@ k_page_compact(const uint8_t *out, uint64_t stride, uint32_t block_size, uint32_
     }
 }
 
-/* which LZ4 decode kernel: CRYOGPU_LZ4_KERNEL=cta selects the one-CTA-per-block variant */
-static bool
-lz4_use_cta_kernel()
+/* CRYOGPU_LZ4_KERNEL = warp | cx forces one LZ4 decoder for every block; default: routed per block */
+static int
+lz4_kernel_choice()
 {
     static int v = -1;
 
@@ -496,23 +563,59 @@ lz4_use_cta_kernel()
     {
         const char *e = getenv("CRYOGPU_LZ4_KERNEL");
 
-        v = (e && strcmp(e, "cta") == 0) ? 1 : 0;
+        v = (e && strcmp(e, "warp") == 0) ? 1 : (e && strcmp(e, "cx") == 0) ? 2 : 0;
     }
-    return v == 1;
+    return v;
 }
 
+/* device memory behind the CTA-per-block LZ4 decoder for a batch of n blocks: the work counter, the
+ * route of every block, and the sequence records of one parse round per CTA */
+static size_t
+lz4c_grid(size_t n, int sm_count)
+{
+    return std::min<size_t>(n, (size_t) sm_count);
+}
+
+static size_t
+lz4c_bytes(size_t n, int sm_count)
+{
+    return 256 + ((n * 4 + 255) & ~(size_t) 255) + lz4c_grid(n, sm_count) * LZ4C_SCRATCH_BYTES;
+}
+
+/*
+ * LZ4 blocks of a batch.  Small batches (every block can have an SM of its own) go to the CTA-per-block
+ * kernel whole; larger ones are routed per block (k_lz4_route).  work: lz4c_bytes(n) bytes, or nullptr
+ * (allocation failed, block size beyond the record format): one warp per block.
+ */
 static void
 launch_lz4_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint8_t *src,
                   const uint64_t *src_off, const uint32_t *src_size, uint8_t *dst,
-                  uint64_t dst_stride, uint32_t cap, uint32_t *out_size, int32_t *status)
+                  uint64_t dst_stride, uint32_t cap, uint32_t *out_size, int32_t *status, void *work,
+                  int sm_count)
 {
-    if (lz4_use_cta_kernel())
-        k_lz4_decode<<<(unsigned) n, LZ4D_THREADS, LZ4D_SMEM, st>>>(methods, src, src_off, src_size,
-                                                                   dst, dst_stride, cap, out_size,
-                                                                   status);
-    else
+    const int choice = lz4_kernel_choice();
+
+    if (!work || cap > LZ4C_MAXCAP || choice == 1)
+    {
         k_lz4_decode_w<<<(unsigned) ((n + LZ4W_WARPS - 1) / LZ4W_WARPS), LZ4W_THREADS, LZ4W_SMEM, st>>>(
-            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n);
+            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n, nullptr);
+        return;
+    }
+    uint32_t *counter = (uint32_t *) work;
+    uint32_t *route = (uint32_t *) ((uint8_t *) work + 256);
+    unsigned long long *gseq = (unsigned long long *) ((uint8_t *) work + 256 + ((n * 4 + 255) & ~(size_t) 255));
+    const bool all_cx = choice == 2 || n <= (size_t) 2 * sm_count;
+
+    cudaMemsetAsync(counter, 0, 4, st);
+    if (!all_cx)
+    {
+        k_lz4_route<<<(unsigned) ((n + 3) / 4), 128, 0, st>>>(methods, src, src_off, src_size, route, (uint32_t) n, cap);
+        k_lz4_decode_w<<<(unsigned) ((n + LZ4W_WARPS - 1) / LZ4W_WARPS), LZ4W_THREADS, LZ4W_SMEM, st>>>(
+            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n, route);
+    }
+    k_lz4_decode_c<<<(unsigned) lz4c_grid(n, sm_count), CX_THREADS, LZ4C_SMEM, st>>>(
+        methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n,
+        all_cx ? nullptr : route, counter, gseq);
 }
 
 /* CRYOGPU_ZSTD_KERNEL = cta | group | warp selects another variant; default: the phase-split
@@ -769,6 +872,8 @@ struct cryogpu_ctx
     cudaEvent_t  ev[2] = {nullptr, nullptr};
     DevBuf       scratch;               /* per-block kernel scratch */
     DevBuf       zp[2];                 /* zstd pipeline work areas (zstd_decode_p.cuh), per lane */
+    DevBuf       lzw[2];                /* CTA-per-block LZ4 decoder work areas (lz4c_bytes), per lane */
+    cudaEvent_t  busy = nullptr;        /* end of the last device-resident call: the work areas are shared */
     cudaStream_t zaux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   /* side streams of the pipeline's concurrent stages */
     cudaEvent_t  zev[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     uint32_t    *predef = nullptr;      /* predefined zstd FSE tables (device) */
@@ -785,6 +890,7 @@ struct cryogpu_ctx
     int          sparse = -1;           /* -1 unset, 0 off, 1 on (CRYOGPU_SPARSE_D2H) */
     uint64_t     last_h2d = 0, last_d2h = 0;
     size_t       last_zp_n = 0;         /* frames of the last decompress_device call that took the pipeline */
+    size_t       last_lz_n = 0;         /* blocks of the last decompress_device call that were routed per block (0: not routed) */
     uint32_t     last_zp_cap = 0;
 };
 
@@ -823,7 +929,7 @@ set_kernel_attrs(cryogpu_ctx *ctx)
 {
     if (ctx->attrs_set)
         return CRYOGPU_OK;
-    CU(cudaFuncSetAttribute(k_lz4_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ4D_SMEM));
+    CU(cudaFuncSetAttribute(k_lz4_decode_c, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ4C_SMEM));
     CU(cudaFuncSetAttribute(k_lz4_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ4W_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSTDD_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSW_SMEM));
@@ -920,7 +1026,8 @@ cryogpu_init(int device, cryogpu_ctx **out)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->busy, cudaEventDisableTiming) != cudaSuccess)
     {
         delete ctx;
         return fail(CRYOGPU_E_CUDA, "stream/event creation failed: %s",
@@ -963,6 +1070,10 @@ cryogpu_shutdown(cryogpu_ctx *ctx)
     cudaFree(ctx->scratch.p);
     cudaFree(ctx->zp[0].p);
     cudaFree(ctx->zp[1].p);
+    cudaFree(ctx->lzw[0].p);
+    cudaFree(ctx->lzw[1].p);
+    if (ctx->busy)
+        cudaEventDestroy(ctx->busy);
     cudaFree(ctx->predef);
     for (int i = 0; i < 2; i++)
     {
@@ -1028,6 +1139,31 @@ cryogpu_zstd_pipeline_stats(cryogpu_ctx *ctx, uint64_t *frames, uint64_t *fallba
     return CRYOGPU_OK;
 }
 
+extern "C" int
+cryogpu_lz4_route_stats(cryogpu_ctx *ctx, uint64_t *blocks, uint64_t *cta_blocks)
+{
+    if (!ctx)
+        return fail(CRYOGPU_E_ARG, "ctx is NULL");
+    uint64_t total = 0, cx = 0;
+
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    if (ctx->last_lz_n)
+    {
+        std::vector<uint32_t> route(ctx->last_lz_n);
+
+        CU(cudaMemcpy(route.data(), (uint8_t *) ctx->lzw[0].p + 256, route.size() * 4, cudaMemcpyDeviceToHost));
+        total = ctx->last_lz_n;
+        for (uint32_t r : route)
+            cx += r == 1u;
+    }
+    if (blocks)
+        *blocks = total;
+    if (cta_blocks)
+        *cta_blocks = cx;
+    return CRYOGPU_OK;
+}
+
 extern "C" void
 cryogpu_last_transfer_bytes(const cryogpu_ctx *ctx, uint64_t *h2d, uint64_t *d2h)
 {
@@ -1089,18 +1225,35 @@ cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
         return fail(CRYOGPU_E_ARG, "block_size or n out of range");
     cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
     bool         use_zp = false;
+    void        *lzw = nullptr;
 
     CU(cudaSetDevice(ctx->device));
+    /*
+     * The work areas belong to the context, so calls on one context run one after the other on the
+     * device whatever streams they were given: this call's stream first waits for the end of the
+     * previous device-resident call (cryogpu.h).  Work areas only grow; growing one frees and
+     * allocates, which waits for the device: a steady-state call only enqueues.
+     */
+    std::lock_guard<std::mutex> g(ctx->mu);
+
+    CU(cudaStreamWaitEvent(st, ctx->busy, 0));
     {
-        std::lock_guard<std::mutex> g(ctx->mu);
         int rc = dev_reserve(ctx->scratch, n * (size_t) ZSTDD_SCRATCH_BYTES);
 
         if (rc != CRYOGPU_OK)
             return rc;
+        /* the CTA-per-block LZ4 decoder's area; without it every LZ4 block takes the warp kernel */
+        if (block_size <= LZ4C_MAXCAP)
+        {
+            if (dev_reserve(ctx->lzw[0], lz4c_bytes(n, ctx->sm_count)) == CRYOGPU_OK)
+                lzw = ctx->lzw[0].p;
+            else
+                cudaGetLastError();
+        }
         /* the pipeline's work area (about 2.3 x the batch's output); without it the batch still
          * decodes, one warp per frame */
         use_zp = zstd_kernel_variant() == 3 && n <= 0xFFFFFFu;
-        if (use_zp && cudaSetDevice(ctx->device) == cudaSuccess)
+        if (use_zp)
         {
             DevBuf &zb = ctx->zp[0];
             const size_t need = zp_bytes(n, block_size);
@@ -1125,13 +1278,15 @@ cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
     k_flag_unknown_methods<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(d_methods, n, d_out_size,
                                                                          d_status);
     launch_lz4_decode(st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
-                      d_out_size, d_status);
+                      d_out_size, d_status, lzw, ctx->sm_count);
     ctx->last_zp_n = use_zp ? n : 0;
     ctx->last_zp_cap = block_size;
+    ctx->last_lz_n = lzw && lz4_kernel_choice() == 0 && n > (size_t) 2 * ctx->sm_count ? n : 0;
     launch_zstd_decode(st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
                        d_out_size, d_status, (uint8_t *) ctx->scratch.p, ctx->predef, use_zp ? ctx->zp[0].p : nullptr, ctx->zaux[0],
                        ctx->zev[0], ctx->sm_count);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->busy, st));
     return CRYOGPU_OK;
 }
 
@@ -1161,8 +1316,10 @@ cryogpu_compress_device(cryogpu_ctx *ctx, size_t n, int method, int level_or_acc
     CU(cudaSetDevice(ctx->device));
     size_t per = method == CRYOGPU_LZ4 ? lz4e_scratch_bytes(block_size) : zstde_scratch_bytes(block_size);
     const size_t zgrid = std::min<size_t>(n, (size_t) ctx->sm_count);
+    std::lock_guard<std::mutex> g(ctx->mu);
+
+    CU(cudaStreamWaitEvent(st, ctx->busy, 0));      /* the scratch area is the context's: see cryogpu_decompress_device */
     {
-        std::lock_guard<std::mutex> g(ctx->mu);
         int rc = dev_reserve(ctx->scratch, (method == CRYOGPU_LZ4 ? n : zgrid) * per);
 
         if (rc != CRYOGPU_OK)
@@ -1177,6 +1334,7 @@ cryogpu_compress_device(cryogpu_ctx *ctx, size_t n, int method, int level_or_acc
             d_src, src_stride, block_size, d_dst, dst_stride, dst_cap, level_or_accel, d_dst_size,
             d_status, (uint8_t *) ctx->scratch.p, per, (uint32_t) n);
     CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->busy, st));
     return CRYOGPU_OK;
 }
 
@@ -1301,6 +1459,7 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
     std::lock_guard<std::mutex> g(ctx->mu);
 
     CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->busy));        /* a device-resident call may still be using the work areas */
     const size_t   chunk = chunk_blocks(block_size);
     const uint64_t stride = ((uint64_t) block_size + 15) & ~(uint64_t) 15;
     const bool     dst_pinned = is_pinned(dst[0]);
@@ -1415,10 +1574,17 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
             (rc = dev_reserve(ctx->d_in[lane], in_bytes + 16)) != CRYOGPU_OK ||
             (rc = dev_reserve(ctx->d_meta[lane], cnt * 24)) != CRYOGPU_OK ||
             (rc = dev_reserve(ctx->d_out[lane], cnt * stride)) != CRYOGPU_OK ||
-            (rc = dev_reserve(ctx->scratch, chunk * (size_t) ZSTDD_SCRATCH_BYTES * 2)) != CRYOGPU_OK ||
-            (zstd_kernel_variant() == 3 &&
-             (rc = dev_reserve(ctx->zp[lane], zp_bytes(chunk, block_size))) != CRYOGPU_OK))
+            (rc = dev_reserve(ctx->scratch, std::min(chunk, n) * (size_t) ZSTDD_SCRATCH_BYTES * 2)) != CRYOGPU_OK)
             return rc;
+        /* work areas by the size of this call (the drop-in's calls are one block each, from every backend);
+         * a missing one only selects the kernels that do without it */
+        void *zpbuf = nullptr, *lzw = nullptr;
+
+        if (zstd_kernel_variant() == 3 && dev_reserve(ctx->zp[lane], zp_bytes(std::min(chunk, n), block_size)) == CRYOGPU_OK)
+            zpbuf = ctx->zp[lane].p;
+        if (block_size <= LZ4C_MAXCAP && dev_reserve(ctx->lzw[lane], lz4c_bytes(std::min(chunk, n), ctx->sm_count)) == CRYOGPU_OK)
+            lzw = ctx->lzw[lane].p;
+        cudaGetLastError();
         const size_t sp_bytes = (cnt * (SP_WORDS + 1) + 1) * 4;
 
         if (sparse &&
@@ -1447,19 +1613,19 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
         CU(cudaMemcpyAsync(ctx->d_in[lane].p, ctx->h_in[lane].p, in_bytes + 16, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(dm, hm, cnt * 16, cudaMemcpyHostToDevice, st));
         h2d += in_bytes + 16 + cnt * 16;
-        uint8_t *scr = (uint8_t *) ctx->scratch.p + (size_t) lane * chunk * ZSTDD_SCRATCH_BYTES;
+        uint8_t *scr = (uint8_t *) ctx->scratch.p + (size_t) lane * std::min(chunk, n) * ZSTDD_SCRATCH_BYTES;
 
         k_flag_unknown_methods<<<(unsigned) ((cnt + 255) / 256), 256, 0, st>>>(
             (int32_t *) (dm + cnt * 12), cnt, (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20));
         launch_lz4_decode(st, cnt, (int32_t *) (dm + cnt * 12), (uint8_t *) ctx->d_in[lane].p,
                           (uint64_t *) dm, (uint32_t *) (dm + cnt * 8),
                           (uint8_t *) ctx->d_out[lane].p, stride, block_size,
-                          (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20));
+                          (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20), lzw, ctx->sm_count);
         launch_zstd_decode(st, cnt, (int32_t *) (dm + cnt * 12), (uint8_t *) ctx->d_in[lane].p,
                            (uint64_t *) dm, (uint32_t *) (dm + cnt * 8),
                            (uint8_t *) ctx->d_out[lane].p, stride, block_size,
                            (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20), scr,
-                           ctx->predef, ctx->zp[lane].p, ctx->zaux[lane], ctx->zev[lane], ctx->sm_count);
+                           ctx->predef, zpbuf, ctx->zaux[lane], ctx->zev[lane], ctx->sm_count);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(hm + cnt * 16, dm + cnt * 16, cnt * 8, cudaMemcpyDeviceToHost, st));
         d2h += cnt * 8;
@@ -1513,6 +1679,7 @@ cryogpu_compress_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel
     std::lock_guard<std::mutex> g(ctx->mu);
 
     CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->busy));
     const size_t   chunk = chunk_blocks(block_size);
     const uint64_t sstride = ((uint64_t) block_size + 15) & ~(uint64_t) 15;
     const uint64_t dstride = (bound + 15) & ~(uint64_t) 15;

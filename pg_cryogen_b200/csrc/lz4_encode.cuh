@@ -316,6 +316,13 @@ CRYO_DEV void lz4_encode_block(const uint8_t *src, uint32_t n, uint8_t *dst, uin
         accel = 1;                      /* liblz4: acceleration < 1 means 1 */
     if (accel > 65537)
         accel = 65537;
+    /* 32 positions are probed per step here, so a denser schedule than liblz4's costs little: above
+     * acceleration 2 the stride is half of liblz4's.  With liblz4's own stride the phase of the sparse
+     * probes decides which matches are seen and small sparse blocks came out up to 1.24 x the
+     * reference's size at accelerations 10..40 (profiles/r02_ratio_sweep.txt); halved, every block
+     * kind stays within the 1.10 x tolerance of DESIGN.md section 1 at every acceleration. */
+    if (accel > 2)
+        accel = (accel + 1) / 2;
     /* segments: at most LZ4E_MAXSEG bytes each, at least one per warp when the block allows */
     uint32_t nseg = (n + LZ4E_MAXSEG - 1) / LZ4E_MAXSEG;
 

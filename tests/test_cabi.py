@@ -22,7 +22,7 @@ def built():
 
 def test_library_exports_every_declared_symbol(built):
     hdr = open(os.path.join(ROOT, "include", "cryogpu.h")).read()
-    declared = set(re.findall(r"\b(cryogpu_[a-z_]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(cryogpu_[a-z0-9_]+)\s*\(", hdr))
     assert declared, "no declarations found"
     assert declared == set(codec.exported_symbols())
     for sym in declared:

@@ -137,3 +137,23 @@ def test_unknown_method_is_reported_per_block(gpu, oracle_ref):
     comp = oracle_ref.compress(COMP_LZ4, 1, blk)[0][0]
     out, osz, st = decode_device(gpu, [COMP_LZ4, 7], [comp, comp])
     assert st[0] == 0 and st[1] == 6
+
+
+def test_lz4_decode_routed_batch_uses_both_decoders(gpu, oracle_ref):
+    """More than two blocks per SM: every block is routed by its estimated sequence count.  Sparse and
+    literal-heavy blocks stay with the warp-per-block kernel, dense low-cardinality blocks (120 K
+    sequences each) go to the CTA-per-block kernel; both must be bit-exact."""
+    kinds = [("S", "hex"), ("D", "lowcard"), ("M", "hex"), ("D", "hex"), ("S", "lowcard"), ("M", "lowcard")]
+    uniq = np.stack([bg.make_block(k, p, 50 + i) for i, (k, p) in enumerate(kinds)])
+    comp = oracle_ref.compress(COMP_LZ4, 1, uniq, nthreads=6)[0]
+    n = 2 * 148 + 37
+    chunks = [comp[i % len(comp)] for i in range(n)]
+    out, osz, st = decode_device(gpu, COMP_LZ4, chunks)
+    assert (st == 0).all() and (osz == CRYO_BLCKSZ).all()
+    for i in range(n):
+        assert np.array_equal(out[i], uniq[i % len(comp)]), i
+    total, cta = gpu.lz4_route_stats()
+    assert total == n
+    per = {kinds[j]: sum(1 for i in range(n) if i % len(comp) == j) for j in range(len(kinds))}
+    assert cta >= per[("D", "lowcard")], (total, cta)          # the match-rich kind is on the CTA kernel
+    assert cta <= n - per[("S", "hex")] - per[("D", "hex")], (total, cta)   # sparse and literal-heavy ones are not

@@ -16,8 +16,8 @@ from gpu_util import decode_device, encode_device
 
 pytestmark = pytest.mark.gpu
 
-TOL_ACCEL_1 = 1.10          # gpu_csize <= 1.10 x reference at the default acceleration
-TOL_ACCEL_N = 1.20          # sparse probing (acceleration > 1) is phase-sensitive
+TOL = 1.10                  # gpu_csize <= 1.10 x reference + SLACK at EVERY acceleration (DESIGN.md section 1;
+SLACK = 64                  # measured worst case per acceleration: profiles/r02_ratio_sweep.txt)
 
 
 def _blocks():
@@ -45,10 +45,9 @@ def test_lz4_encode_roundtrip_and_ratio(gpu, oracle_ref, accel):
     back, ok, _ = oracle_ref.decompress([COMP_LZ4] * len(comp), *oracle_ref.pack(comp))
     assert ok.all(), "the reference's LZ4_decompress_safe rejected a GPU-written block"
     assert np.array_equal(back, blocks)
-    tol = TOL_ACCEL_1 if accel <= 1 else TOL_ACCEL_N
     for i, c in enumerate(comp):
         assert len(c) <= compress_bound(COMP_LZ4), tags[i]
-        assert len(c) <= tol * ref_sizes[i] + 64, (tags[i], accel, len(c), int(ref_sizes[i]))
+        assert len(c) <= TOL * ref_sizes[i] + SLACK, (tags[i], accel, len(c), int(ref_sizes[i]))
     out, osz, dst = decode_device(gpu, COMP_LZ4, comp)
     assert (dst == 0).all() and np.array_equal(out, blocks)
 

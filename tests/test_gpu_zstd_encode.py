@@ -16,7 +16,8 @@ from gpu_util import decode_device, encode_device
 
 pytestmark = pytest.mark.gpu
 
-TOL = 1.15                  # gpu_csize <= 1.15 x reference at the same level
+TOL = 1.15                  # gpu_csize <= 1.15 x reference + SLACK at the same level (DESIGN.md section 1:
+SLACK = 64                  # the 64 bytes cover frame / block headers of near-empty blocks, e.g. all zeros: 73 vs 45 B)
 
 
 def _blocks():
@@ -48,7 +49,7 @@ def test_zstd_encode_roundtrip_and_ratio(gpu, oracle_ref, level):
     assert np.array_equal(back, blocks)
     for i, c in enumerate(comp):
         assert len(c) <= compress_bound(COMP_ZSTD), tags[i]
-        assert len(c) <= TOL * ref_sizes[i] + 64, (tags[i], level, len(c), int(ref_sizes[i]))
+        assert len(c) <= TOL * ref_sizes[i] + SLACK, (tags[i], level, len(c), int(ref_sizes[i]))
     out, osz, dst = decode_device(gpu, COMP_ZSTD, comp)
     assert (dst == 0).all() and (osz == CRYO_BLCKSZ).all() and np.array_equal(out, blocks)
 

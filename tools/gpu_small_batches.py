@@ -35,9 +35,14 @@ def main():
             torch.cuda.synchronize()
             ts.append(time.perf_counter() - t0)
         ts = np.sort(np.array(ts[20:])) * 1e6
+        # the reference's compression.c on ONE host thread (what one PostgreSQL backend gets) on the same blocks
+        rb, ro, rs = ref.pack(chunks)
+        ref.decompress(methods, rb, ro, rs, nthreads=1)
+        cpu1 = ref.decompress(methods, rb, ro, rs, nthreads=1, reps=3)[2] / 3 * 1e6
+        cpuN = ref.decompress(methods, rb, ro, rs, nthreads=os.cpu_count(), reps=3)[2] / 3 * 1e6
         ok = bool((d_st == 0).all().item()) and all(np.array_equal(d_dst[i].cpu().numpy(), blocks[i % len(z)]) for i in range(min(n, 8)))
         print(f"{tag:9s} batch {n:4d} (lz4/zstd alternating, S/M/D kinds): p50 {ts[len(ts)//2]:8.1f} us  p99 {ts[int(len(ts)*0.99)]:8.1f} us  "
-              f"{n*(1<<20)/ts[len(ts)//2]/1e3:8.1f} GB/s at p50  exact={ok}", flush=True)
+              f"{n*(1<<20)/ts[len(ts)//2]/1e3:8.1f} GB/s at p50  exact={ok}  | reference CPU 1 thread {cpu1:9.1f} us, {os.cpu_count()} threads {cpuN:9.1f} us", flush=True)
 
 if __name__ == "__main__":
     main()
