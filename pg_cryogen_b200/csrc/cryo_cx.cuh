@@ -13,11 +13,14 @@
  *     before any byte moves;
  *   - literals depend on nothing: all threads place theirs at once (a lane for a short run,
  *     the warp for a medium one);
- *   - a match depends only on the matches that wrote its source bytes.  Which sequences those
- *     are follows from the positions (a search in the prefix sums); every warp publishes a bit
- *     mask of its finished sequences in shared memory, and a match is copied as soon as the bits
- *     it needs are set.  Independent matches -- most of them -- move in the same round; chains of
- *     dependent ones cost one round per link, not one per sequence;
+ *   - a match byte is a copy of an earlier byte.  If that byte was produced before the chunk it is
+ *     final and is copied at once.  If it lies inside the chunk, the byte only records how far
+ *     back its source is (a 16-bit distance per byte of the chunk, dl[]), and the chunk is then
+ *     resolved by pointer jumping: in a round every unresolved byte looks at its source -- final:
+ *     take the value; unresolved: add the source's distance to its own -- so a chain of n copies
+ *     resolves in log2(n) rounds of perfectly regular work, whatever the structure of the block
+ *     (a dense low-cardinality cryo block has chains hundreds of matches long: executing them
+ *     match by match, in dependency order, was 8 x slower, profiles/r02_cx_phases.txt);
  *   - the most recent output lives in a CX_RING-byte ring in shared memory, so a match source
  *     is a shared-memory read (LZ4's whole 64 KiB window fits); the ring drains to HBM as
  *     aligned 16-byte vectors by all threads;
@@ -36,7 +39,7 @@
 #define CX_WARPS   (CX_THREADS / 32u)
 #define CX_RING    131072u              /* power of two; >= CX_HIST + CX_SPAN + slack */
 #define CX_RMASK   (CX_RING - 1u)
-#define CX_SPAN    32768u               /* output bytes one chunk of sequences may cover */
+#define CX_SPAN    16384u               /* output bytes one chunk of sequences may cover (dl[]: 2 bytes each) */
 #define CX_BIG     8192u                /* runs at least this long are CTA-wide bulk operations (2 * CX_BIG <= CX_SPAN) */
 #define CX_LANE    32u                  /* runs up to this long are moved by the sequence's own lane */
 #define CX_HIST    65536u               /* history reloaded into the ring after a bulk operation (LZ4: offsets <= 65535) */
@@ -46,10 +49,31 @@
 #define CX_LDCG(p) (*(p))
 #define CX_VLD(p) (*reinterpret_cast<const volatile uint32_t *>(p))
 #define CX_VST(p, v) (*reinterpret_cast<volatile uint32_t *>(p) = (v))
+#define CX_SYNC_OR(p) emu_syncthreads_or(p)
 #else
 #define CX_LDCG(p) __ldcg(p)
 #define CX_VLD(p) (*reinterpret_cast<const volatile uint32_t *>(p))
 #define CX_VST(p, v) (*reinterpret_cast<volatile uint32_t *>(p) = (v))
+#define CX_SYNC_OR(p) __syncthreads_or(p)
+#endif
+
+/* development aid (-DCX_PROF): thread 0 of CTA 0 charges the cycles since the previous mark to a phase counter */
+#if defined(CX_PROF) && !defined(CRYO_EMU)
+__device__ unsigned long long cx_prof[32];
+__device__ long long cx_prof_last;
+#define CXP(i)                                                     \
+    if (threadIdx.x == 0 && blockIdx.x == 0)                       \
+    {                                                              \
+        const long long t_ = clock64();                            \
+        cx_prof[i] += (unsigned long long) (t_ - cx_prof_last);    \
+        cx_prof_last = t_;                                         \
+    }
+#define CXP_COUNT(i, v)                                            \
+    if (threadIdx.x == 0 && blockIdx.x == 0)                       \
+        cx_prof[i] += (v);
+#else
+#define CXP(i)
+#define CXP_COUNT(i, v)
 #endif
 
 /* shared-memory control block of one CTA */
@@ -59,8 +83,6 @@ struct CxSh
     uint32_t cut;                       /* first sequence of the chunk that is not executed in it */
     uint32_t err;                       /* (sequence index << 8 | status) of the first failing sequence, ~0u: none */
     uint32_t bcast[4];
-    uint32_t done[CX_WARPS];            /* per warp: bit l set = the match of the warp's sequence l is in the ring */
-    uint32_t pend[CX_THREADS];          /* end position of every sequence of the chunk (dependency search) */
 };
 
 /* per-thread view; every field is uniform over the CTA */
@@ -69,6 +91,8 @@ struct Cx
     uint8_t    *out;                    /* global output block, 16-byte aligned */
     uint8_t    *ring;                   /* shared, CX_RING bytes, 16-byte aligned */
     uint8_t    *pat;                    /* shared, CX_PAT + 32 bytes, 16-byte aligned */
+    uint16_t   *dl;                     /* shared, CX_SPAN entries, 16-byte aligned: distance to the source of every
+                                         * unresolved byte of the chunk, 0: the byte is final */
     CxSh       *sh;
     uint32_t    cap;
     uint32_t    pos;                    /* next output byte */
@@ -77,12 +101,13 @@ struct Cx
     int         err;
 };
 
-CRYO_DEV void cx_init(Cx &cx, uint8_t *out, uint32_t cap, uint8_t *ring, uint8_t *pat, CxSh *sh)
+CRYO_DEV void cx_init(Cx &cx, uint8_t *out, uint32_t cap, uint8_t *ring, uint8_t *pat, uint16_t *dl, CxSh *sh)
 {
     cx.out = out;
     cx.cap = cap;
     cx.ring = ring;
     cx.pat = pat;
+    cx.dl = dl;
     cx.sh = sh;
     cx.pos = 0;
     cx.flushed = 0;
@@ -274,23 +299,6 @@ CRYO_DEV void cx_bulk(Cx &cx, uint32_t ll, const uint8_t *lit, int rle_byte, uin
     cx_reload(cx, tid);
 }
 
-/* lower bound in sh->pend[0, n): first index whose end position is > x */
-CRYO_DEV uint32_t cx_first_end_above(const CxSh *sh, uint32_t n, uint32_t x)
-{
-    uint32_t lo = 0, hi = n;
-
-    while (lo < hi)
-    {
-        const uint32_t mid = (lo + hi) >> 1;
-
-        if (sh->pend[mid] > x)
-            hi = mid;
-        else
-            lo = mid + 1;
-    }
-    return lo;
-}
-
 /*
  * Execute a chunk.  Thread t offers sequence t (valid: t < n, n <= CX_THREADS uniform):
  *   ll, ml, off   literal length, match length (0: none -- the last sequence of an LZ4 block, or
@@ -374,17 +382,23 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
         const int      rb0 = (int) sh->bcast[3];
         const uint8_t *lit0 = reinterpret_cast<const uint8_t *>((uintptr_t) slot[0]);
 
+        CXP(8)
         cx_bulk(cx, ll0, lit0, rb0, ml0, off0, tid);
+        CXP(13)
+        CXP_COUNT(18, 1)
         return 1;
     }
+    CXP(8)
     const bool mine = tid < k;
     /* positions below lo are not in the ring any more (or never were, after a bulk operation) */
     const uint32_t kend = pos0 + CX_SPAN;
     const uint32_t lo = kend > CX_RING && kend - CX_RING > cx.ring_lo ? kend - CX_RING : cx.ring_lo;
 
-    /* ---- literals: no dependencies ---- */
-    if (mine)
-        sh->pend[tid] = end;
+    /* ---- literals: no dependencies; every byte of the chunk starts out final ---- */
+    if (tid == k - 1u)
+        sh->bcast[0] = end;
+    for (uint32_t a = 8u * tid; a < CX_SPAN; a += 8u * CX_THREADS)
+        st16(reinterpret_cast<uint8_t *>(cx.dl + a), make_uint4(0u, 0u, 0u, 0u));
     if (mine && ll && ll <= CX_LANE)
     {
         if (rle_byte >= 0)
@@ -407,139 +421,113 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
         else
             cx_ring_put(cx, js, jp, jl, lane, 32);
     }
-    /* ---- matches: every warp publishes the sequences it has finished ---- */
-    bool     pending = mine && ml != 0;
-    uint32_t mydone = __ballot_sync(CRYO_FULL, !pending);
-
-    if (lane == 0)
-        sh->done[warp] = mydone;
-    __syncthreads();                    /* literals, pend[], done[] */
-    /* which sequences wrote this match's source: [q_lo, q_hi], none when the source is older than the chunk
-     * or lies in the sequence's own literals */
-    uint32_t q_lo = 1, q_hi = 0;
-
-    if (pending)
+    __syncthreads();                    /* dl[] cleared, bcast */
+    CXP(9)
+    const uint32_t kpos = sh->bcast[0];         /* end of the chunk's last sequence */
+    /*
+     * ---- matches, step 1: every match byte either becomes final (its source was produced before the
+     * chunk) or records the distance to its source.  A match that overlaps itself (offset < length)
+     * repeats the offset bytes before it: byte i is sourced from byte i mod offset of that period, so
+     * the chain inside the match is cut here, not by the rounds below. ----
+     */
+    if (mine && ml && ml <= CX_LANE)
     {
-        const uint32_t s = mpos - off;
-        uint32_t       e = s + ml < mpos ? s + ml : mpos;   /* the part of the source that exists before the copy */
+        const uint32_t s0 = mpos - off;
+        uint32_t       r = 0;
 
-        if (e > start)
-            e = start;                  /* own literals are in place */
-        if (e > pos0 && s < e)
+        for (uint32_t i = 0; i < ml; i++)
         {
-            q_lo = s > pos0 ? cx_first_end_above(sh, tid, s) : 0u;
-            q_hi = cx_first_end_above(sh, tid, e - 1u);
-            if (q_hi >= tid)
-                q_hi = tid - 1u;        /* (e <= start = pend[tid - 1]: cannot happen; keeps the masks sane) */
+            const uint32_t sp = s0 + r, d = mpos + i;
+
+            if (sp < pos0)
+                cx.ring[d & CX_RMASK] = cx_src(cx, sp, lo);
+            else
+                cx.dl[d - pos0] = (uint16_t) (d - sp);
+            r++;
+            r = r == off ? 0u : r;
         }
     }
-    for (;;)
+    for (uint32_t m = __ballot_sync(CRYO_FULL, mine && ml > CX_LANE); m; m &= m - 1)
     {
-        bool ready = false;
+        const int      j = __ffs((int) m) - 1;
+        const uint32_t jm = __shfl_sync(CRYO_FULL, ml, j), jo = __shfl_sync(CRYO_FULL, off, j);
+        const uint32_t jp = __shfl_sync(CRYO_FULL, mpos, j), s0 = jp - jo;
+        const uint32_t step = jo >= 32u ? 32u : 32u % jo;
+        uint32_t       r = lane < jo ? lane : lane % jo;
 
-        if (pending)
+        for (uint32_t i = lane; i < jm; i += 32)
         {
-            ready = true;
-            if (q_lo <= q_hi)
-                for (uint32_t w = q_lo >> 5; w <= (q_hi >> 5); w++)
-                {
-                    const uint32_t b0 = w == (q_lo >> 5) ? q_lo & 31u : 0u;
-                    const uint32_t b1 = w == (q_hi >> 5) ? q_hi & 31u : 31u;
-                    const uint32_t need = (b1 == 31u ? ~0u : (2u << b1) - 1u) & (~0u << b0);
-                    const uint32_t have = w == warp ? mydone : CX_VLD(&sh->done[w]);
+            const uint32_t sp = s0 + r, d = jp + i;
 
-                    if ((have & need) != need)
-                    {
-                        ready = false;
-                        break;
-                    }
-                }
-        }
-        if (__any_sync(CRYO_FULL, ready))
-            __threadfence_block();      /* the flags were read before the bytes they stand for */
-        /* short matches: the sequence's own lane.  An overlapping match reads what it has just written. */
-        if (ready && ml <= CX_LANE)
-        {
-            const uint32_t s = mpos - off;
-
-            if (off >= ml)
-            {
-                for (uint32_t i0 = 0; i0 < ml; i0 += 8)
-                {
-                    uint8_t v[8];
-
-#pragma unroll
-                    for (uint32_t q = 0; q < 8; q++)
-                        v[q] = i0 + q < ml ? cx_src(cx, s + i0 + q, lo) : (uint8_t) 0;
-#pragma unroll
-                    for (uint32_t q = 0; q < 8; q++)
-                        if (i0 + q < ml)
-                            cx.ring[(mpos + i0 + q) & CX_RMASK] = v[q];
-                }
-            }
+            if (sp < pos0)
+                cx.ring[d & CX_RMASK] = cx_src(cx, sp, lo);
             else
-                for (uint32_t i = 0; i < ml; i++)
-                {
-                    const uint32_t x = s + i;
-                    const uint8_t  b = x >= lo ? *reinterpret_cast<volatile uint8_t *>(cx.ring + (x & CX_RMASK))
-                                               : CX_LDCG(cx.out + x);
-
-                    *reinterpret_cast<volatile uint8_t *>(cx.ring + ((mpos + i) & CX_RMASK)) = b;
-                }
+                cx.dl[d - pos0] = (uint16_t) (d - sp);
+            r += step;
+            r = r >= jo ? r - jo : r;
         }
-        /* medium matches: the warp, one after the other */
-        for (uint32_t m = __ballot_sync(CRYO_FULL, ready && ml > CX_LANE); m; m &= m - 1)
-        {
-            const int      j = __ffs((int) m) - 1;
-            const uint32_t jm = __shfl_sync(CRYO_FULL, ml, j), jo = __shfl_sync(CRYO_FULL, off, j);
-            const uint32_t jp = __shfl_sync(CRYO_FULL, mpos, j), s = jp - jo;
-
-            if (jo >= jm || jo >= 32u)
-            {
-                for (uint32_t i0 = 0; i0 < jm; i0 += 32)
-                {
-                    const uint32_t i = i0 + lane;
-
-                    if (i < jm)
-                        cx.ring[(jp + i) & CX_RMASK] = cx_src(cx, s + i, lo);
-                    if (jo < jm)
-                        __syncwarp();   /* the next 32 bytes may read these */
-                }
-            }
-            else
-            {
-                /* period below 32: every byte is one of the jo bytes before the match */
-                uint32_t r = lane % jo;
-                const uint32_t step = 32u % jo;
-
-                for (uint32_t i = lane; i < jm; i += 32)
-                {
-                    cx.ring[(jp + i) & CX_RMASK] = cx_src(cx, s + r, lo);
-                    r += step;
-                    r = r >= jo ? r - jo : r;
-                }
-            }
-            __syncwarp();
-        }
-        __syncwarp();
-        const uint32_t newly = __ballot_sync(CRYO_FULL, ready);
-
-        if (newly)
-        {
-            mydone |= newly;
-            __threadfence_block();      /* the bytes before the flag */
-            if (lane == 0)
-                CX_VST(&sh->done[warp], mydone);
-        }
-        pending = pending && !ready;
-        if (__ballot_sync(CRYO_FULL, pending) == 0)
-            break;
-        if (!newly)
-            __nanosleep(32);            /* every pending match of this warp waits for another warp */
     }
     __syncthreads();
-    cx.pos = sh->pend[k - 1];
+    CXP(10)
+    /*
+     * ---- matches, step 2: pointer jumping.  Thread t owns the bytes [16 g, 16 g + 16) of the chunk,
+     * g = t, t + CX_THREADS, ...  A round needs no barrier between its reads and its writes: a byte
+     * that reads a distance another thread is replacing sees either the old or the new one, and both
+     * name a byte with the value it is after; a value is written (and fenced) before its distance is
+     * cleared, and read after the distance was seen cleared.  The barrier at the end of a round only
+     * tells whether any byte is left (bar.red.or).
+     */
+    {
+        const uint32_t ngroups = (kpos - pos0 + 15u) >> 4;
+        volatile const uint16_t *vdl = cx.dl;
+        volatile uint8_t *vring = cx.ring;
+
+        for (;;)
+        {
+            bool left = false;
+
+            CXP_COUNT(16, 1)
+            for (uint32_t g = tid; g < ngroups; g += CX_THREADS)
+            {
+                uint8_t    *gp = reinterpret_cast<uint8_t *>(cx.dl + 16u * g);
+                const uint4 a = ld16(gp), b = ld16(gp + 16);
+                uint32_t    w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+
+                if ((a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) == 0u)
+                    continue;
+#pragma unroll
+                for (uint32_t q = 0; q < 16; q++)
+                {
+                    const uint32_t d = (w[q >> 1] >> (16u * (q & 1u))) & 0xFFFFu;
+
+                    if (d)
+                    {
+                        const uint32_t idx = 16u * g + q, sidx = idx - d;
+                        const uint32_t ds = vdl[sidx];
+
+                        if (ds == 0)
+                        {
+                            vring[(pos0 + idx) & CX_RMASK] = vring[(pos0 + sidx) & CX_RMASK];
+                            w[q >> 1] &= ~(0xFFFFu << (16u * (q & 1u)));
+                        }
+                        else
+                            w[q >> 1] += ds << (16u * (q & 1u));
+                    }
+                }
+                __threadfence_block();  /* the values before the cleared distances */
+                st16(gp, make_uint4(w[0], w[1], w[2], w[3]));
+                st16(gp + 16, make_uint4(w[4], w[5], w[6], w[7]));
+                left = left || (w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) != 0u;
+            }
+            if (!CX_SYNC_OR(left))
+                break;
+        }
+    }
+    CXP(11)
+    cx.pos = kpos;
     cx_drain(cx, tid);
+    CXP(12)
+    CXP_COUNT(17, 1)
     return k;
 }
 

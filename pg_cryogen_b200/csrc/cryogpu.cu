@@ -3,17 +3,16 @@
  * entry points.  Host side: lazy per-device context, pinned staging, chunked
  * H2D / kernel / D2H pipelines for the *_host calls, block-range sharding over
  * several GPUs.  No CPU codec lives here: every byte of LZ4 / zstd work is done
- * by the kernels in lz4_decode.cuh, zstd_decode.cuh, lz4_encode.cuh and
+ * by the kernels in lz4_decode_w/c.cuh, zstd_decode_w/p/c.cuh, lz4_encode.cuh and
  * zstd_encode.cuh.
  */
 #include "../../include/cryogpu.h"
 
 #include "lz4_decode_w.cuh"
 #include "lz4_decode_c.cuh"
-#include "zstd_decode.cuh"
 #include "zstd_decode_w.cuh"
-#include "zstd_decode_g.cuh"
 #include "zstd_decode_p.cuh"
+#include "zstd_decode_c.cuh"
 #include "lz4_encode.cuh"
 #include "zstd_encode.cuh"
 
@@ -65,55 +64,51 @@ fail(int code, const char *fmt, ...)
 /*
  * Which decoder takes an LZ4 block: the one-warp-per-block kernel (thousands of blocks in flight hide its
  * serial chain) or the CTA-per-block kernel (lz4_decode_c.cuh), which a block with many sequences needs
- * whatever the batch size.  The number of sequences is not in the format; it is estimated: eight lanes
- * walk 64 tokens each from eight evenly spaced bytes of the stream (a walk that starts at a wrong byte
- * falls in with the true chain after a few tokens), and the bytes per token of the later half of each
- * walk scale to the stream.  route[b]: 0 = warp, 1 = CTA.
+ * whatever the batch size.  The number of sequences is not in the format; it is estimated by one lane
+ * per block that walks the first LZ4R_PROBE tokens of the stream (the only place where the token chain is
+ * known to start) and scales their density to the stream.  A walk from the middle of the stream is no
+ * use: in a literal-heavy block it hops through hex digits and sees a token every few bytes.
+ * route[b]: 0 = warp, 1 = CTA.
  */
 #define LZ4R_CX_SEQS 4096u             /* estimated sequences from which the CTA kernel is the faster one */
+#define LZ4R_PROBE   96u
 
 __global__ void __launch_bounds__(128)
 k_lz4_route(const int32_t *methods, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_size,
             uint32_t *route, uint32_t n, uint32_t cap)
 {
-    const uint32_t b = blockIdx.x * 4u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+    const uint32_t b = blockIdx.x * 128u + threadIdx.x;
 
     if (b >= n)
         return;
     uint32_t est = 0;
     const uint32_t csize = src_size[b];
 
-    if (methods[b] == CRYOGPU_LZ4 && csize >= 1024u && cap <= LZ4C_MAXCAP && lane < 8u)
+    if (methods[b] == CRYOGPU_LZ4 && csize >= 1024u && cap <= LZ4C_MAXCAP)
     {
         const uint8_t *in = src + src_off[b];
-        const uint32_t part = csize / 8u, lim = lane == 7u ? csize : (lane + 1u) * part;
-        uint32_t p = lane * part, hops = 0, p16 = p;
+        uint32_t p = 0, hops = 0;
 
-        while (hops < 64u && p + 3u <= lim)
+        while (hops < LZ4R_PROBE && p + 3u <= csize)
         {
             const uint32_t tk = in[p];
             uint32_t q = p + 1u, ll = tk >> 4, ml = tk & 15u;
 
             if (ll == 15u)
-                for (uint32_t x = 255u; x == 255u && q < lim; ll += x)
+                for (uint32_t x = 255u; x == 255u && q < csize; ll += x)
                     x = in[q++];
             q += ll + 2u;
             if (ml == 15u)
-                for (uint32_t x = 255u; x == 255u && q < lim; )
+                for (uint32_t x = 255u; x == 255u && q < csize; )
                     x = in[q++];
+            if (q <= p)
+                break;                  /* a literal length that wraps: the decoder will reject the block */
             p = q;
-            if (++hops == 16u)
-                p16 = p;
+            hops++;
         }
-        /* tokens of this eighth of the stream at the density of the walk's later part */
-        if (hops > 16u && p > p16)
-            est = (uint32_t) (((uint64_t) part * (hops - 16u)) / (p - p16));
-        else
-            est = hops;
+        est = p >= csize || p == 0 ? hops : (uint32_t) (((uint64_t) csize * hops) / p);
     }
-    est = __reduce_add_sync(0xffffffffu, est);
-    if (lane == 0)
-        route[b] = est >= LZ4R_CX_SEQS ? 1u : 0u;
+    route[b] = est >= LZ4R_CX_SEQS ? 1u : 0u;
 }
 
 /* latency path and match-rich blocks: one CTA per block, persistent CTAs take the routed blocks in order */
@@ -157,19 +152,6 @@ k_lz4_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_o
                       status + b, CRYO_SMEM_BASE() + warp * LZ4W_PER_WARP, lane);
 }
 
-__global__ void __launch_bounds__(ZSTDD_THREADS)
-k_zstd_decode(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
-              const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
-              uint32_t *out_size, int32_t *status, uint8_t *scratch, uint64_t scratch_stride)
-{
-    const uint32_t b = blockIdx.x;
-
-    if (methods[b] != CRYOGPU_ZSTD)
-        return;
-    zstd_decode_frame(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
-                      status + b, scratch + b * scratch_stride);
-}
-
 /* throughput path (default): one warp per frame, ZSW_WARPS frames per CTA */
 __global__ void __launch_bounds__(ZSW_THREADS, ZSW_CTAS_PER_SM)
 k_zstd_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
@@ -185,24 +167,6 @@ k_zstd_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_
     zstdw_decode_frame(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
                        status + b, scratch + b * scratch_stride, predef,
                        CRYO_SMEM_BASE() + warp * ZSW_PER_WARP, lane);
-}
-
-/* sub-warp variant: ZSG_W lanes per frame, ZSG_GROUPS frames per CTA (CRYOGPU_ZSTD_KERNEL=group) */
-__global__ void __launch_bounds__(ZSG_THREADS, ZSG_CTAS_PER_SM)
-k_zstd_decode_g(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
-                const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
-                uint32_t *out_size, int32_t *status, uint8_t *scratch, uint64_t scratch_stride,
-                const uint32_t *predef, uint32_t n)
-{
-    const uint32_t grp = threadIdx.x / ZSG_W;
-    const uint32_t b = blockIdx.x * ZSG_GROUPS + grp;
-    const Grp<ZSG_W> g = grp_make<ZSG_W>(threadIdx.x & 31u);
-
-    if (b >= n || methods[b] != CRYOGPU_ZSTD)
-        return;
-    zstdg_decode_frame<ZSG_W>(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
-                              status + b, scratch + b * scratch_stride, predef,
-                              CRYO_SMEM_BASE() + grp * ZSW_PER_WARP, g);
 }
 
 /* development aid (-DZP_TIMELINE): every pipeline kernel records the first CTA start and the last CTA
@@ -428,6 +392,29 @@ k_zp_execute(const ZpArgs a)
     ZP_TL_END(7)
 }
 
+/* stage 4 with one CTA per frame (zstd_decode_c.cuh): persistent CTAs take the frames stage 1 routed to them */
+__global__ void __launch_bounds__(CX_THREADS, 1)
+k_zp_execute_c(const ZpArgs a, uint32_t *counter)
+{
+    __shared__ uint32_t next_f;
+
+    for (;;)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            next_f = atomicAdd(counter, 1u);
+        __syncthreads();
+        const uint32_t f = next_f;
+
+        if (f >= a.n)
+            return;
+        if (a.methods[f] != ZP_METHOD_ZSTD || a.flag[f] != 0 || a.fr[(size_t) f * ZP_FF] == 0 ||
+            a.fr[(size_t) f * ZP_FF + 3] != 1u)
+            continue;
+        zp_stage4_cx(a, f, CRYO_SMEM_BASE(), threadIdx.x);
+    }
+}
+
 /* the three predefined FSE tables of RFC 8878 3.1.1.3.2.2, built once per context */
 __global__ void
 k_zstd_build_predef(uint32_t *predef)
@@ -609,7 +596,7 @@ launch_lz4_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint8
     cudaMemsetAsync(counter, 0, 4, st);
     if (!all_cx)
     {
-        k_lz4_route<<<(unsigned) ((n + 3) / 4), 128, 0, st>>>(methods, src, src_off, src_size, route, (uint32_t) n, cap);
+        k_lz4_route<<<(unsigned) ((n + 127) / 128), 128, 0, st>>>(methods, src, src_off, src_size, route, (uint32_t) n, cap);
         k_lz4_decode_w<<<(unsigned) ((n + LZ4W_WARPS - 1) / LZ4W_WARPS), LZ4W_THREADS, LZ4W_SMEM, st>>>(
             methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n, route);
     }
@@ -618,8 +605,8 @@ launch_lz4_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint8
         all_cx ? nullptr : route, counter, gseq);
 }
 
-/* CRYOGPU_ZSTD_KERNEL = cta | group | warp selects another variant; default: the phase-split
- * pipeline (zstd_decode_p.cuh) */
+/* CRYOGPU_ZSTD_KERNEL = warp selects the one-warp-per-frame decoder for every frame (2); default: the
+ * phase-split pipeline (3, zstd_decode_p.cuh), which hands the frames it declines to that decoder */
 static int
 zstd_kernel_variant()
 {
@@ -629,8 +616,7 @@ zstd_kernel_variant()
     {
         const char *e = getenv("CRYOGPU_ZSTD_KERNEL");
 
-        v = (e && strcmp(e, "cta") == 0) ? 1 : (e && strcmp(e, "group") == 0) ? 0
-            : (e && strcmp(e, "warp") == 0) ? 2 : 3;
+        v = (e && strcmp(e, "warp") == 0) ? 2 : 3;
     }
     return v;
 }
@@ -688,15 +674,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
     /* no work area (allocation failed, or more frames than the pipeline indexes): one warp per frame */
     const int variant = zstd_kernel_variant() == 3 && !zpbuf ? 2 : zstd_kernel_variant();
 
-    if (variant == 1)
-        k_zstd_decode<<<(unsigned) n, ZSTDD_THREADS, ZSTDD_SMEM, st>>>(
-            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
-            ZSTDD_SCRATCH_BYTES);
-    else if (variant == 0)
-        k_zstd_decode_g<<<(unsigned) ((n + ZSG_GROUPS - 1) / ZSG_GROUPS), ZSG_THREADS, ZSG_SMEM, st>>>(
-            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
-            ZSTDD_SCRATCH_BYTES, predef, (uint32_t) n);
-    else if (variant == 2)
+    if (variant == 2)
         k_zstd_decode_w<<<(unsigned) ((n + ZSW_WARPS - 1) / ZSW_WARPS), ZSW_THREADS, ZSW_SMEM, st>>>(
             methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
             ZSTDD_SCRATCH_BYTES, predef, (uint32_t) n, nullptr);
@@ -728,7 +706,28 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             }
             a.pf_hint = (uint32_t) hint;
         }
-        cudaMemsetAsync(a.seq_alloc, 0, 8, st);
+        /*
+         * Who runs stage 4.  A batch small enough that every frame can have an SM of its own goes to the
+         * CTA-per-frame executor whole (bit 2): the warp executor and the raw / RLE stage are not launched.
+         * In a larger batch stage 1 routes every frame by its number of sequences.  CRYOGPU_ZSTD_EXEC =
+         * warp | cx forces one of them.
+         */
+        static int exec_choice = -1;
+
+        if (exec_choice < 0)
+        {
+            const char *e = getenv("CRYOGPU_ZSTD_EXEC");
+
+            exec_choice = (e && strcmp(e, "warp") == 0) ? 1 : (e && strcmp(e, "cx") == 0) ? 2 : 0;
+        }
+        const bool all_cx = exec_choice == 2 || (exec_choice == 0 && n <= (size_t) 2 * sm_count);
+        uint32_t  *cx_counter = (uint32_t *) (a.seq_alloc + 1);
+
+        if (all_cx)
+            a.pf_hint |= 4u;
+        else if (exec_choice == 1)
+            a.pf_hint |= 8u;
+        cudaMemsetAsync(a.seq_alloc, 0, 16, st);
         k_zp_parse<<<(unsigned) ((n + 31) / 32), 32, 0, st>>>(a);
         /*
          * literals (st) and sequences (aux 0) are independent of each other and bound by latency.
@@ -759,12 +758,26 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         k_zp_huftab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
         k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
         cudaStreamWaitEvent(st, ev[1], 0);
-        cudaEventRecord(ev[0], st);
-        cudaStreamWaitEvent(aux[1], ev[0], 0);
-        k_zp_prefill<<<pf_grid, ZP0_THREADS, 0, aux[1]>>>(a);
-        cudaEventRecord(ev[2], aux[1]);
-        k_zp_execute<<<(unsigned) ((n + ZP4_WARPS - 1) / ZP4_WARPS), ZP4_THREADS, ZP4_SMEM, st>>>(a);
-        cudaStreamWaitEvent(st, ev[2], 0);
+        if (all_cx)
+            k_zp_execute_c<<<(unsigned) std::min<size_t>(n, (size_t) sm_count), CX_THREADS, ZC_SMEM, st>>>(a, cx_counter);
+        else
+        {
+            cudaEventRecord(ev[0], st);
+            cudaStreamWaitEvent(aux[1], ev[0], 0);
+            k_zp_prefill<<<pf_grid, ZP0_THREADS, 0, aux[1]>>>(a);
+            cudaEventRecord(ev[2], aux[1]);
+            if (exec_choice != 1)
+            {
+                /* the frames with many sequences, beside the warp executor */
+                cudaStreamWaitEvent(aux[0], ev[0], 0);
+                k_zp_execute_c<<<(unsigned) std::min<size_t>(n, (size_t) sm_count), CX_THREADS, ZC_SMEM, aux[0]>>>(a, cx_counter);
+                cudaEventRecord(ev[3], aux[0]);
+            }
+            k_zp_execute<<<(unsigned) ((n + ZP4_WARPS - 1) / ZP4_WARPS), ZP4_THREADS, ZP4_SMEM, st>>>(a);
+            cudaStreamWaitEvent(st, ev[2], 0);
+            if (exec_choice != 1)
+                cudaStreamWaitEvent(st, ev[3], 0);
+        }
         /* frames the pipeline declined (flag set): decoded from scratch, one warp per frame */
         k_zstd_decode_w<<<(unsigned) ((n + ZSW_WARPS - 1) / ZSW_WARPS), ZSW_THREADS, ZSW_SMEM, st>>>(
             methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, scratch,
@@ -875,7 +888,7 @@ struct cryogpu_ctx
     DevBuf       lzw[2];                /* CTA-per-block LZ4 decoder work areas (lz4c_bytes), per lane */
     cudaEvent_t  busy = nullptr;        /* end of the last device-resident call: the work areas are shared */
     cudaStream_t zaux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   /* side streams of the pipeline's concurrent stages */
-    cudaEvent_t  zev[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    cudaEvent_t  zev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
     uint32_t    *predef = nullptr;      /* predefined zstd FSE tables (device) */
     /* *_host staging (device + pinned host), two lanes */
     DevBuf       d_in[2], d_out[2], d_meta[2];
@@ -930,10 +943,9 @@ set_kernel_attrs(cryogpu_ctx *ctx)
     if (ctx->attrs_set)
         return CRYOGPU_OK;
     CU(cudaFuncSetAttribute(k_lz4_decode_c, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ4C_SMEM));
+    CU(cudaFuncSetAttribute(k_zp_execute_c, cudaFuncAttributeMaxDynamicSharedMemorySize, ZC_SMEM));
     CU(cudaFuncSetAttribute(k_lz4_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, LZ4W_SMEM));
-    CU(cudaFuncSetAttribute(k_zstd_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSTDD_SMEM));
     CU(cudaFuncSetAttribute(k_zstd_decode_w, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSW_SMEM));
-    CU(cudaFuncSetAttribute(k_zstd_decode_g, cudaFuncAttributeMaxDynamicSharedMemorySize, ZSG_SMEM));
     CU(cudaFuncSetAttribute(k_zp_sequences_large, cudaFuncAttributeMaxDynamicSharedMemorySize, ZP3B_SMEM(ZP3B_LARGE, ZP_G)));
     CU(cudaFuncSetAttribute(k_zp_sequences_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES)));
@@ -943,7 +955,10 @@ set_kernel_attrs(cryogpu_ctx *ctx)
         const void *zp_kernels[] = {(const void *) k_zp_parse, (const void *) k_zp_prefill, (const void *) k_zp_huftab,
                                     (const void *) k_zp_literals, (const void *) k_zp_fsetab,
                                     (const void *) k_zp_sequences_small, (const void *) k_zp_sequences_large,
-                                    (const void *) k_zp_execute, (const void *) k_zstd_decode_w};
+                                    (const void *) k_zp_execute, (const void *) k_zstd_decode_w,
+                                    (const void *) k_zp_execute_c, (const void *) k_lz4_decode_c,
+                                    (const void *) k_lz4_decode_w, (const void *) k_lz4_route,
+                                    (const void *) k_flag_unknown_methods};
 
         for (const void *k : zp_kernels)
             CU(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1041,7 +1056,7 @@ cryogpu_init(int device, cryogpu_ctx **out)
                 delete ctx;
                 return fail(CRYOGPU_E_CUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
-        for (int k = 0; k < 3; k++)
+        for (int k = 0; k < 4; k++)
             if (cudaEventCreateWithFlags(&ctx->zev[l][k], cudaEventDisableTiming) != cudaSuccess)
             {
                 delete ctx;
@@ -1095,7 +1110,7 @@ cryogpu_shutdown(cryogpu_ctx *ctx)
     {
         for (int k = 0; k < 2; k++)
             cudaStreamDestroy(ctx->zaux[l][k]);
-        for (int k = 0; k < 3; k++)
+        for (int k = 0; k < 4; k++)
             cudaEventDestroy(ctx->zev[l][k]);
     }
     delete ctx->pool;
@@ -1835,6 +1850,22 @@ cryogpu_compress_host_multi(cryogpu_ctx *const *ctxs, int nctx, size_t n, int me
                                      dst + lo, dst_cap, dst_size + lo, status + lo);
     });
 }
+
+#ifdef CX_PROF
+/* development aid: phase cycle counters of CTA 0 of the CTA-per-block decoders; not part of include/cryogpu.h */
+extern "C" int
+cryogpu_debug_cxprof(unsigned long long *out32, int reset)
+{
+    unsigned long long zero[32] = {0};
+
+    cudaDeviceSynchronize();
+    if (out32)
+        cudaMemcpyFromSymbol(out32, cx_prof, sizeof(zero));
+    if (reset)
+        cudaMemcpyToSymbol(cx_prof, zero, sizeof(zero));
+    return 0;
+}
+#endif
 
 #ifdef ZP_TIMELINE
 /* development aid: read (and optionally reset) the pipeline timeline; not part of include/cryogpu.h */

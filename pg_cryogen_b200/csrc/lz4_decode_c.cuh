@@ -10,8 +10,8 @@
  *
  *   stage   the next LZ4C_REGION bytes of the stream -> shared memory, one bulk copy by the
  *           copy engine (cp.async.bulk global -> shared, completion on an mbarrier)
- *   walk    lane l starts at byte 64 * l of the region AS IF a token started there and walks to
- *           the end of its 64-byte segment, recording the token starts it visits (a bitmap).
+ *   walk    lane l starts at byte 64 * (l - 1) of the region AS IF a token started there and walks to
+ *           the end of its own 64-byte segment, recording the token starts it visits there (a bitmap).
  *           A chain that starts at a wrong byte meets the true chain after a few tokens and
  *           then follows it (the token stream self-synchronises), so most of every lane's walk
  *           is the true chain;
@@ -34,7 +34,7 @@
 #define LZ4C_LANES      (CX_THREADS < 512u ? CX_THREADS : 512u)
 #define LZ4C_REGION     (LZ4C_SEG * LZ4C_LANES)         /* stream bytes whose tokens one round parses */
 #define LZ4C_STAGE      (LZ4C_REGION + 1024u)           /* staged bytes: the region, its 16-byte alignment, look-ahead */
-#define LZ4C_MAXHOPS    32u
+#define LZ4C_MAXHOPS    24u
 #define LZ4C_SEQCAP     (LZ4C_REGION / 3u + 64u)        /* a sequence that is not the last takes >= 3 bytes */
 #define LZ4C_MAXCAP     ((1u << 22) - 1u)               /* record fields are 22 bits */
 #define LZ4C_BAD        0xFFFFFFFFu
@@ -50,7 +50,8 @@
 #define LZ4C_OFF_RING   0u
 #define LZ4C_OFF_STAGE  (LZ4C_OFF_RING + CX_RING)
 #define LZ4C_OFF_PAT    (LZ4C_OFF_STAGE + LZ4C_STAGE)
-#define LZ4C_OFF_CXSH   (LZ4C_OFF_PAT + CX_PAT + 32u)
+#define LZ4C_OFF_DL     (LZ4C_OFF_PAT + CX_PAT + 32u)
+#define LZ4C_OFF_CXSH   (LZ4C_OFF_DL + 2u * CX_SPAN)
 #define LZ4C_OFF_PARSE  ((LZ4C_OFF_CXSH + (uint32_t) sizeof(CxSh) + 15u) & ~15u)
 struct Lz4cParse
 {
@@ -69,6 +70,7 @@ struct Lz4cParse
     uint32_t    saw_last;
 };
 #define LZ4C_SMEM       (LZ4C_OFF_PARSE + (uint32_t) sizeof(Lz4cParse))
+static_assert(LZ4C_SMEM <= 232448u, "one CTA's shared memory on sm_100");
 
 struct Lz4cIn
 {
@@ -91,29 +93,78 @@ struct Lz4cTok
     uint32_t st;                /* 0: sequence with a match, 1: the last sequence (literals only), 2: malformed */
 };
 
+/* the 8 stream bytes at p, little-endian; bytes at or past in.end read as zero */
+CRYO_DEV unsigned long long lz4c_ld8(const Lz4cIn &in, uint32_t p)
+{
+    const uint32_t r = p - in.sbase;
+
+    if (r + 12u <= in.slen && p + 8u <= in.end)
+    {
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(in.stage) + (r >> 2);
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], sh = (r & 3u) * 8u;
+
+        return (unsigned long long) __funnelshift_r(w0, w1, sh) | ((unsigned long long) __funnelshift_r(w1, w2, sh) << 32);
+    }
+    unsigned long long v = 0;
+
+    for (uint32_t i = 0; i < 8u && p + i < in.end; i++)
+        v |= (unsigned long long) lz4c_byte(in, p + i) << (8u * i);
+    return v;
+}
+
+/*
+ * Length extension at q: bytes are added until one is below 255.  Sixteen bytes per step (the
+ * zero run of a sparse cryo block is a match of ~1 MB: 4 030 extension bytes).  False: the
+ * stream ends inside the run.
+ */
+CRYO_DEV bool lz4c_extension(const Lz4cIn &in, uint32_t &q, uint32_t &len)
+{
+    for (;;)
+    {
+        if (q >= in.end)
+            return false;
+        const unsigned long long a = lz4c_ld8(in, q), b = lz4c_ld8(in, q + 8u);
+
+        if (a == ~0ull && b == ~0ull && q + 16u <= in.end)
+        {
+            len += 16u * 255u;
+            q += 16u;
+            if (len > (1u << 24))
+                return false;
+            continue;
+        }
+        const unsigned long long x = a == ~0ull ? b : a;
+        const uint32_t base = a == ~0ull ? 8u : 0u;
+        const uint32_t k = x == ~0ull ? 8u : (uint32_t) (__ffsll((long long) ~x) - 1) >> 3;     /* first byte below 255 */
+
+        if (k == 8u)
+        {
+            /* (only when the stream ends within these 16 bytes) */
+            len += (base + 8u) * 255u;
+            q += base + 8u;
+            continue;
+        }
+        if (q + base + k >= in.end)
+            return false;
+        len += (base + k) * 255u + (uint32_t) ((x >> (8u * k)) & 0xFFu);
+        q += base + k + 1u;
+        return true;
+    }
+}
+
 /* decode the token at p (p < in.end) */
 CRYO_DEV void lz4c_tok(const Lz4cIn &in, uint32_t p, Lz4cTok &t)
 {
-    const uint32_t tk = lz4c_byte(in, p);
+    const unsigned long long W = lz4c_ld8(in, p);
+    const uint32_t tk = (uint32_t) W & 0xFFu;
     uint32_t q = p + 1, ll = tk >> 4, ml = tk & 15u;
 
     t.st = 2;
     t.ml = 0;
     t.off = 0;
     t.next = LZ4C_BAD;
-    if (ll == 15u)
-        for (;;)
-        {
-            if (q >= in.end)
-                return;
-            const uint32_t b = lz4c_byte(in, q++);
-
-            ll += b;
-            if (b != 255u)
-                break;
-            if (ll > (1u << 24))
-                return;
-        }
+    if (ll == 15u && !lz4c_extension(in, q, ll))
+        return;
     t.ll = ll;
     t.lit = q;
     if (ll > in.end - q)
@@ -127,21 +178,14 @@ CRYO_DEV void lz4c_tok(const Lz4cIn &in, uint32_t p, Lz4cTok &t)
     }
     if (q + 2u > in.end)
         return;
-    t.off = lz4c_byte(in, q) | (lz4c_byte(in, q + 1u) << 8);
+    /* the offset: still inside the 8 bytes read for the token when the literal run is short */
+    if (q - p <= 6u)
+        t.off = (uint32_t) (W >> (8u * (q - p))) & 0xFFFFu;
+    else
+        t.off = (uint32_t) lz4c_ld8(in, q) & 0xFFFFu;
     q += 2;
-    if (ml == 15u)
-        for (;;)
-        {
-            if (q >= in.end)
-                return;
-            const uint32_t b = lz4c_byte(in, q++);
-
-            ml += b;
-            if (b != 255u)
-                break;
-            if (ml > (1u << 24))
-                return;
-        }
+    if (ml == 15u && !lz4c_extension(in, q, ml))
+        return;
     t.ml = ml + 4u;
     t.next = q;
     t.st = 0;
@@ -153,7 +197,8 @@ CRYO_DEV uint32_t lz4c_ext(uint32_t v)
     return v < 15u ? 0u : (v - 15u) / 255u + 1u;
 }
 
-/* lane l walks its segment from position p0 (inside it): visited bitmap and exit position */
+/* lane l walks to the end of its segment from position p0 (inside it, or before it: the run-up):
+ * token starts visited inside the segment, and the exit position */
 CRYO_DEV void lz4c_walk(const Lz4cIn &in, uint32_t segstart, uint32_t segend, uint32_t p0,
                         unsigned long long &vis, uint32_t &exitp)
 {
@@ -164,7 +209,8 @@ CRYO_DEV void lz4c_walk(const Lz4cIn &in, uint32_t segstart, uint32_t segend, ui
     {
         Lz4cTok t;
 
-        v |= 1ull << (p - segstart);
+        if (p >= segstart)
+            v |= 1ull << (p - segstart);
         lz4c_tok(in, p, t);
         p = t.next;             /* LZ4C_BAD ends the loop */
     }
@@ -232,8 +278,12 @@ CRYO_DEV uint32_t lz4c_parse_round(const Lz4cIn &in, Lz4cParse *ps, CxSh *sh, ui
         unsigned long long v = 0;
         uint32_t x = LZ4C_BAD;
 
+        /* the walk starts one segment early (not before rp, which is a true token start): by the time
+         * the chain enters its own segment it has almost always fallen in with the true chain, so the
+         * true chain of the lane before finds it at once (without the run-up one lane in forty of a dense
+         * block missed it within LZ4C_MAXHOPS tokens and had to be repaired, one serial walk each) */
         if (lane_on)
-            lz4c_walk(in, segstart, segend, segstart, v, x);
+            lz4c_walk(in, segstart, segend, l == 0 ? segstart : segstart - LZ4C_SEG, v, x);
         ps->vis[l] = v;
         ps->exitp[l] = x;
     }
@@ -243,13 +293,16 @@ CRYO_DEV uint32_t lz4c_parse_round(const Lz4cIn &in, Lz4cParse *ps, CxSh *sh, ui
         ps->saw_last = 0;
     }
     __syncthreads();
+    CXP(1)
     /* link */
     if (lane_on)
         lz4c_extend(in, ps, rp, re, ps->exitp[l], ps->link[l], ps->extc[l]);
     __syncthreads();
+    CXP(2)
     /* mark (and repair an irregular link of a marked lane, then mark again) */
     for (;;)
     {
+        CXP_COUNT(19, 1)
         if (l < LZ4C_LANES)
         {
             uint32_t nx = LZ4C_END;
@@ -326,6 +379,7 @@ CRYO_DEV uint32_t lz4c_parse_round(const Lz4cIn &in, Lz4cParse *ps, CxSh *sh, ui
             __syncthreads();
         }
     }
+    CXP(3)
     /* emit: count, prefix sum, write */
     const bool     marked = lane_on && ps->mark[l];
     const uint32_t ent = marked ? ps->entry[l] : 0u;
@@ -364,6 +418,7 @@ CRYO_DEV uint32_t lz4c_parse_round(const Lz4cIn &in, Lz4cParse *ps, CxSh *sh, ui
             ps->bad = 1;                /* the chain died before the link (malformed token) */
     }
     __syncthreads();
+    CXP(4)
     st = ST_OK;
     if (ps->bad || ps->stop == LZ4C_DEAD || total > LZ4C_SEQCAP)
         st = ST_INPUT;
@@ -389,7 +444,7 @@ CRYO_DEV void lz4c_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
     bool       got_last = false;
     uint32_t   phase = 0;
 
-    cx_init(cx, out, cap, smem + LZ4C_OFF_RING, smem + LZ4C_OFF_PAT, sh);
+    cx_init(cx, out, cap, smem + LZ4C_OFF_RING, smem + LZ4C_OFF_PAT, reinterpret_cast<uint16_t *>(smem + LZ4C_OFF_DL), sh);
     in.base = src - delta;
     in.end = csize + delta;
     in.stage = stage;
@@ -405,6 +460,10 @@ CRYO_DEV void lz4c_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
     }
 #endif
     __syncthreads();
+#if defined(CX_PROF) && !defined(CRYO_EMU)
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        cx_prof_last = clock64();
+#endif
     uint32_t rp = delta;
 
     while (err == ST_OK && rp < in.end)
@@ -440,6 +499,7 @@ CRYO_DEV void lz4c_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
         }
         phase ^= 1u;
 #endif
+        CXP(0)
         const uint32_t re = in.end - rp < LZ4C_REGION ? in.end : rp + LZ4C_REGION;
         uint32_t next_rp = in.end;
         bool     saw_last = false;
@@ -463,7 +523,9 @@ CRYO_DEV void lz4c_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
             uint32_t cum = valid ? ll + ml : 0u, icum = inlen;
 
             __syncthreads();            /* scan scratch of the previous chunk / of the parse */
+            CXP(5)
             cx_scan2(sh, cum, icum, tid);
+            CXP(6)
             const uint32_t lit = tokpos + icum - inlen + hdr;       /* first literal byte, `base` coordinates */
             const uint32_t start = cx.pos + cum - ll - ml;
             int            pre = ST_OK;
@@ -479,6 +541,7 @@ CRYO_DEV void lz4c_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
             }
             const uint32_t rl = lit - in.sbase;
             const uint8_t *lp = rl < in.slen && rl + ll <= in.slen ? stage + rl : in.base + lit;
+            CXP(7)
             const uint32_t k = cx_chunk(cx, n, ll, ml, off, lp, -1, cum, pre, tid);
 
             if (k == 0)
@@ -500,6 +563,7 @@ CRYO_DEV void lz4c_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
     if (err == ST_OK && !got_last)
         err = ST_INPUT;                 /* the stream ends with a match, or without its last literals */
     cx_finish(cx, tid);
+    CXP(14)
     if (tid == 0)
     {
         *out_size = err == ST_OK ? cx.pos : 0u;

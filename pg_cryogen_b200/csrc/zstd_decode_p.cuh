@@ -36,7 +36,8 @@
 #define ZP_G      8u            /* frames per entropy warp */
 #define ZP_BF     19u           /* u32 fields per block descriptor */
 #define ZP_PREFILL_MIN 2048u     /* raw / RLE blocks at least this long are written ahead by stage 0 */
-#define ZP_FF     4u            /* u32 fields per frame descriptor: nblk, fcs, has_fcs, - */
+#define ZP_FF     4u            /* u32 fields per frame descriptor: nblk, fcs, has_fcs, route (1: stage 4 by a CTA, zstd_decode_c.cuh) */
+#define ZP_CX_SEQS 8192u        /* frames with at least this many sequences take the CTA-per-frame stage 4 */
 
 enum
 {
@@ -79,7 +80,8 @@ struct ZpArgs
     unsigned long long *seq_alloc;
     uint32_t       *pf_done;    /* n; blocks of the frame stage 0 has finished (release / acquire with stage 4) */
     uint32_t        pf_hint;    /* bit 0: stage 0 bulk stores with the L2 evict_first policy; bit 1: stage 4 asks L2 for
-                                 * sequences and literals a few loads ahead */
+                                 * sequences and literals a few loads ahead; bit 2: every frame takes the CTA-per-frame
+                                 * stage 4 (small batches); bit 3: none does */
     uint8_t        *lit;        /* n x lit_stride: Huffman-decoded literals */
     uint64_t        lit_stride; /* multiple of 16, >= cap + 16 * ZP_MAXB */
     uint64_t       *seq;        /* ll | ml << 17 | offset_value << 35 */
@@ -337,6 +339,14 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
         if (base + seq_total > a.seq_cap)
             ok = false;
         a.seqbase[f] = base;
+        /* who executes the frame: a warp (k_zp_execute, with stage 0 writing its Raw / RLE blocks), or a
+         * whole CTA (k_zp_execute_c), which writes every block itself */
+        const bool cx = !(a.pf_hint & 8u) && ((a.pf_hint & 4u) || seq_total >= ZP_CX_SEQS);
+
+        fr[3] = cx ? 1u : 0u;
+        if (cx)
+            for (uint32_t j = 0; j < fr[0]; j++)
+                a.blk[((size_t) f * ZP_MAXB + j) * ZP_BF + ZPB_SPECPOS] = ~0u;
     }
     if (!ok)
     {
@@ -1357,7 +1367,7 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 /* stage 4 body: one warp, frame f */
 CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lane)
 {
-    if (f >= a.n || a.methods[f] != ZP_METHOD_ZSTD || a.flag[f] != 0)
+    if (f >= a.n || a.methods[f] != ZP_METHOD_ZSTD || a.flag[f] != 0 || a.fr[(size_t) f * ZP_FF + 3] != 0)
         return;
     const uint32_t nb = a.fr[(size_t) f * ZP_FF], cap = a.cap;
     const uint8_t *in = a.src + a.src_off[f], *fin = in;    /* fin: for ZP4_CONFIRM, where `in` is shadowed */

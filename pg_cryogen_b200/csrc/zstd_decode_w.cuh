@@ -21,7 +21,7 @@
  */
 #pragma once
 #include "cryo_wexec.cuh"
-#include "zstd_decode.cuh"
+#include "zstd_format.cuh"
 
 #define ZSW_WARPS     8
 #define ZSW_THREADS   (32 * ZSW_WARPS)

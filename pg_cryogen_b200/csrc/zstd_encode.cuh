@@ -35,7 +35,7 @@
  */
 #pragma once
 #include "cryo_common.cuh"
-#include "zstd_decode.cuh"
+#include "zstd_format.cuh"
 #include "zstd_decode_w.cuh"
 
 #define ZSE_WARPS       16

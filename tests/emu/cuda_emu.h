@@ -245,6 +245,22 @@ static inline Tidx tidx() { return Tidx{g_cta->cur, 0, 0}; }
 
 static inline void __syncthreads() { emu::cta_barrier(emu::g_cta->bar_gen, emu::g_cta->bar_arrived, emu::g_cta->nthreads); }
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::warp_barrier(mask); }
+/* __syncthreads_or: barrier + OR of the predicate over the CTA (two barriers: collect, then read and reset) */
+static inline int emu_syncthreads_or(int pred)
+{
+    static int acc = 0, result = 0;
+
+    if (pred)
+        acc = 1;
+    emu::cta_barrier(emu::g_cta->bar_gen, emu::g_cta->bar_arrived, emu::g_cta->nthreads);
+    if (emu::g_cta->cur == 0)
+    {
+        result = acc;
+        acc = 0;
+    }
+    emu::cta_barrier(emu::g_cta->bar_gen, emu::g_cta->bar_arrived, emu::g_cta->nthreads);
+    return result;
+}
 static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 static inline void __nanosleep(unsigned) { emu::yield(); }

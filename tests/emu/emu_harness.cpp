@@ -6,11 +6,8 @@
  */
 #define CRYO_EMU 1
 #include "cuda_emu.h"
-#include "../../pg_cryogen_b200/csrc/lz4_decode.cuh"
-#include "../../pg_cryogen_b200/csrc/zstd_decode.cuh"
 #include "../../pg_cryogen_b200/csrc/lz4_decode_w.cuh"
 #include "../../pg_cryogen_b200/csrc/zstd_decode_w.cuh"
-#include "../../pg_cryogen_b200/csrc/zstd_decode_g.cuh"
 #include "../../pg_cryogen_b200/csrc/zstd_decode_p.cuh"
 #include "../../pg_cryogen_b200/csrc/lz4_encode.cuh"
 #include "../../pg_cryogen_b200/csrc/zstd_encode.cuh"
@@ -36,48 +33,6 @@ struct Padded
 };
 }
 
-extern "C" int
-emu_lz4_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap, unsigned shift,
-               uint32_t *out_size)
-{
-    Padded  in(src, csize, shift);
-    Padded  out(nullptr, 0, 0);
-    int32_t status = -1;
-
-    out.buf.assign(cap + 256, 0xAA);
-    uint8_t *o = (uint8_t *) ((((uintptr_t) out.buf.data() + 63) & ~(uintptr_t) 63) + 64);
-    emu::launch(dim3(1), dim3(LZ4D_THREADS), LZ4D_SMEM, [&]() {
-        lz4_decode_block(in.p, csize, o, cap, out_size, &status);
-    });
-    memcpy(dst, o, cap);
-    /* the kernel must not write outside [o, o + cap) */
-    for (int i = 1; i <= 64; i++)
-        if (o[-i] != 0xAA || o[cap + i - 1] != 0xAA)
-            return -100;
-    return status;
-}
-
-extern "C" int
-emu_zstd_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap, unsigned shift,
-                uint32_t *out_size)
-{
-    Padded  in(src, csize, shift);
-    std::vector<uint8_t> obuf(cap + 256, 0xAA), scr(ZSTDD_SCRATCH_BYTES + 128, 0x77);
-    int32_t status = -1;
-    uint8_t *o = (uint8_t *) ((((uintptr_t) obuf.data() + 63) & ~(uintptr_t) 63) + 64);
-    uint8_t *sc = (uint8_t *) ((((uintptr_t) scr.data() + 63) & ~(uintptr_t) 63));
-
-    emu::launch(dim3(1), dim3(ZSTDD_THREADS), ZSTDD_SMEM, [&]() {
-        zstd_decode_frame(in.p, csize, o, cap, out_size, &status, sc);
-    });
-    memcpy(dst, o, cap);
-    for (int i = 1; i <= 64; i++)
-        if (o[-i] != 0xAA || o[cap + i - 1] != 0xAA)
-            return -100;
-    return status;
-}
-
-/* warp-per-block LZ4 decoder: two copies of the block so both warps of the CTA run */
 extern "C" int
 emu_lz4w_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap, unsigned shift,
                 uint32_t *out_size)
@@ -219,81 +174,6 @@ emu_zstd_encode(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t dst_cap, 
  * group decoder (8 lanes per frame): up to ZSG_GROUPS different streams decoded side by side
  * in one CTA, so the groups of a warp diverge as they do on mixed batches.
  * srcs/csizes/dsts/out_sizes/statuses are arrays of n entries (n <= ZSG_GROUPS).
- */
-extern "C" int
-emu_zstdg_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes, uint8_t *const *dsts,
-                       uint32_t cap, unsigned shift, uint32_t *out_sizes, int32_t *statuses)
-{
-    static uint32_t predef[ZSW_PREDEF_CELLS];
-    static bool have_predef = false;
-    std::vector<Padded> ins;
-    uint32_t stride = (cap + 15u) & ~15u;
-    std::vector<uint8_t> obuf((size_t) n * stride + 512, 0xAA), scr((size_t) n * ZSTDD_SCRATCH_BYTES + 128, 0x77);
-    uint8_t *o = (uint8_t *) ((((uintptr_t) obuf.data() + 63) & ~(uintptr_t) 63) + 64);
-    uint8_t *sc = (uint8_t *) ((((uintptr_t) scr.data() + 63) & ~(uintptr_t) 63));
-
-    if (n < 1 || n > ZSG_GROUPS)
-        return -102;
-    for (int i = 0; i < n; i++)
-        ins.emplace_back(srcs[i], csizes[i], shift + 3 * i);
-    if (!have_predef)
-    {
-        emu::launch(dim3(1), dim3(32), 2048, [&]() { zsw_build_predef(predef, CRYO_SMEM_BASE(), threadIdx.x); });
-        have_predef = true;
-    }
-    emu::launch(dim3(1), dim3(ZSG_THREADS), ZSG_SMEM, [&]() {
-        const uint32_t grp = threadIdx.x / ZSG_W;
-        const Grp<ZSG_W> g = grp_make<ZSG_W>(threadIdx.x & 31);
-
-        if ((int) grp < n)
-            zstdg_decode_frame<ZSG_W>(ins[grp].p, csizes[grp], o + grp * (size_t) stride, cap, out_sizes + grp,
-                                      statuses + grp, sc + grp * (size_t) ZSTDD_SCRATCH_BYTES, predef,
-                                      CRYO_SMEM_BASE() + grp * ZSW_PER_WARP, g);
-    });
-    for (int i = 0; i < n; i++)
-        memcpy(dsts[i], o + i * (size_t) stride, cap);
-    for (int i = 1; i <= 64; i++)
-        if (o[-i] != 0xAA)
-            return -100;
-    return 0;
-}
-
-extern "C" int
-emu_zstdg_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap, unsigned shift,
-                 uint32_t *out_size)
-{
-    /* the same stream in five groups (a full warp of four plus one in the second warp) */
-    const int n = 5;
-    const uint8_t *srcs[n];
-    uint32_t csz[n], osz[n];
-    int32_t st[n];
-    std::vector<std::vector<uint8_t>> outs(n, std::vector<uint8_t>(cap));
-    uint8_t *dsts[n];
-
-    for (int i = 0; i < n; i++)
-    {
-        srcs[i] = src;
-        csz[i] = csize;
-        dsts[i] = outs[i].data();
-        osz[i] = 0;
-        st[i] = -1;
-    }
-    int rc = emu_zstdg_decode_multi(n, srcs, csz, dsts, cap, shift, osz, st);
-
-    if (rc)
-        return rc;
-    for (int i = 1; i < n; i++)
-        if (st[i] != st[0] || osz[i] != osz[0] || (st[0] == 0 && memcmp(dsts[i], dsts[0], cap) != 0))
-            return -101;
-    memcpy(dst, dsts[0], cap);
-    *out_size = osz[0];
-    return st[0];
-}
-
-/*
- * phase-split pipeline (zstd_decode_p.cuh): n frames through stages 1-4, then the
- * warp-per-frame decoder for every frame whose flag was raised.  flags[i] reports which frames
- * took the fallback, so tests can assert that the pipeline itself decoded what it should.
  */
 extern "C" int
 emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes, uint8_t *const *dsts,

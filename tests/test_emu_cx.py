@@ -119,3 +119,76 @@ def test_cx_lz4_mutated_streams(cx):
         assert (st == 0) == (want >= 0), (k, pos, st, want)
         if want >= 0:
             assert sz == want and np.array_equal(out[:want], ref_out[:want]), (k, pos)
+
+
+# ---------------------------------------------------------------- zstd: CTA-per-frame stage 4 (zstd_decode_c.cuh)
+
+def zstd_compress(b, level=1):
+    z = C.CDLL("libzstd.so.1")
+    z.ZSTD_compress.restype = C.c_size_t
+    z.ZSTD_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
+    b = np.ascontiguousarray(b, dtype=np.uint8)
+    out = np.zeros(b.size + b.size // 128 + 512, dtype=np.uint8)
+    n = z.ZSTD_compress(out.ctypes.data, out.size, b.ctypes.data, b.size, level)
+    assert n < out.size
+    return out[:n].copy()
+
+
+@pytest.fixture(scope="module", params=["64", "1024"])
+def zcx(request):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
+    L = C.CDLL(os.path.join(HERE, "emu", f"libcryoemu_cx{request.param}.so"))
+    L.emu_zstdc_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint, C.POINTER(C.c_uint32),
+                                   C.POINTER(C.c_uint32)]
+
+    def run(stream, cap, shift=0):
+        s = np.ascontiguousarray(stream, dtype=np.uint8)
+        out = np.zeros(max(cap, 16), dtype=np.uint8)
+        sz, flag = C.c_uint32(0), C.c_uint32(0)
+        st = L.emu_zstdc_decode(s.ctypes.data if s.size else None, s.size, out.ctypes.data, cap, shift, C.byref(sz), C.byref(flag))
+        return st, sz.value, out[:cap], flag.value
+    run.threads = int(request.param)
+    return run
+
+
+def test_cx_zstd_matches_libzstd(zcx, oracle_port):
+    """Frames written by the reference's libzstd (compression.c:93-109), decoded by stages 1-3 + the CTA stage 4."""
+    sizes = (100, 4097, 70000, 300000) if zcx.threads == 64 else (4097, 140000)
+    for n in sizes:
+        for tag, blk in _slices(n):
+            blk = np.ascontiguousarray(blk)
+            for level in (1, 3, -5):
+                c = zstd_compress(blk, level)
+                st, sz, out, flag = zcx(c, n, shift=(n + level) % 16)
+                assert st == 0 and sz == n and np.array_equal(out, blk), (tag, n, level, st, sz, flag)
+                # the pipeline's work area holds cap / 8 + 64 sequence records per frame (zp_seq_cap); a frame with
+                # more is decoded by the warp-per-frame decoder (flag), any other must take the CTA stage
+                nseq = oracle_port.zstd_decode(c, n, stats=True)[2]["sequences"]
+                assert flag == (1 if nseq > n // 8 + 64 else 0), (tag, n, level, nseq, "routing")
+
+
+def test_cx_zstd_full_blocks(zcx, oracle_ref):
+    kinds = [("S", "hex")] if zcx.threads == 1024 else [("S", "hex"), ("M", "lowcard"), ("D", "lowcard")]
+    for kind, pl in kinds:
+        blk = bg.make_block(kind, pl, 31)
+        c = oracle_ref.compress(1, 1, blk)[0][0]
+        st, sz, out, flag = zcx(c, MiB, shift=3)
+        assert st == 0 and sz == MiB and np.array_equal(out, blk) and flag == 0, (kind, pl, st, sz, flag)
+
+
+def test_cx_zstd_mutated_frames(zcx, oracle_ref, oracle_port):
+    """Corrupted frames: never a crash or a write outside the block; the verdict is the port's
+    (DESIGN.md section 1 lists where the port is stricter than libzstd), accepted frames give its bytes."""
+    rng = np.random.default_rng(11)
+    blk = np.ascontiguousarray(bg.make_block("D", "lowcard", 3)[-9000:])
+    c = zstd_compress(blk, 1)
+    for k in range(20 if zcx.threads == 1024 else 80):
+        m = c.copy()
+        pos = int(rng.integers(0, m.size))
+        m[pos] = int(rng.integers(0, 256))
+        want_n, want = oracle_port.zstd_decode(m, 9000)
+        st, sz, out, flag = zcx(m, 9000, shift=k % 16)
+        assert st != -100
+        assert (st == 0) == (want_n >= 0), (k, pos, st, want_n)
+        if want_n >= 0:
+            assert sz == want_n and np.array_equal(out[:sz], want[:sz]), (k, pos)

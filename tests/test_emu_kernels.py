@@ -18,15 +18,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 MiB = 1 << 20
 
 
-@pytest.fixture(scope="module", params=["group", "warp", "cta"])
-def emu(request):
-    """group = the throughput kernels (8 lanes per zstd frame; LZ4 one warp per block), warp = one
-    warp per block, cta = the one-CTA-per-block variants."""
+@pytest.fixture(scope="module")
+def emu():
+    """The one-warp-per-block decoders (lz4_decode_w.cuh, zstd_decode_w.cuh); the CTA-per-block ones
+    are in test_emu_cx.py, the phase-split pipeline further down."""
     subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
     L = C.CDLL(os.path.join(HERE, "emu", "libcryoemu.so"))
-    warp = request.param in ("warp", "group")
-    group = request.param == "group"
-    for f in (L.emu_lz4_decode, L.emu_zstd_decode, L.emu_lz4w_decode, L.emu_zstdw_decode, L.emu_zstdg_decode):
+    for f in (L.emu_lz4w_decode, L.emu_zstdw_decode):
         f.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint, C.POINTER(C.c_uint32)]
         f.restype = C.c_int
 
@@ -34,10 +32,7 @@ def emu(request):
         s = np.ascontiguousarray(stream, dtype=np.uint8)
         out = np.zeros(cap, dtype=np.uint8)
         sz = C.c_uint32(0)
-        if warp:
-            fn = L.emu_lz4w_decode if method == 0 else (L.emu_zstdg_decode if group else L.emu_zstdw_decode)
-        else:
-            fn = L.emu_lz4_decode if method == 0 else L.emu_zstd_decode
+        fn = L.emu_lz4w_decode if method == 0 else L.emu_zstdw_decode
         st = fn(s.ctypes.data if s.size else None, s.size, out.ctypes.data, cap, shift, C.byref(sz))
         return st, sz.value, out
     return run
@@ -113,35 +108,6 @@ def test_emulated_zstd_encoder_roundtrips_through_libzstd(oracle_ref, oracle_por
         c = enc(src[:n], 1)
         got, out = oracle_port.zstd_decode(c, cap=max(n, 1))[:2]
         assert got == n and np.array_equal(out[:n], src[:n]), n
-
-
-def test_emulated_group_decoder_diverging_frames(oracle_ref):
-    """Eight different frames side by side in one CTA of the group decoder (8 lanes per frame):
-    the four groups of a warp take different paths (Raw / RLE / Compressed blocks, different
-    sequence counts, a malformed frame) and must not disturb each other."""
-    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
-    L = C.CDLL(os.path.join(HERE, "emu", "libcryoemu.so"))
-    L.emu_zstdg_decode_multi.restype = C.c_int
-    blocks = [bg.make_block("S", "hex", 31), np.zeros(MiB, dtype=np.uint8), bg.make_block("S", "lowcard", 32),
-              bg.make_block("D", "random", 33), bg.regression_block(291, 500), bg.make_block("S", "hex", 34),
-              bg.make_block("M", "hex", 35), bg.make_block("S", "random", 36)]
-    levels = [1, 1, 3, 1, -5, 19, 1, 2]
-    comp = [oracle_ref.compress(1, lv, b)[0][0] for lv, b in zip(levels, blocks)]
-    comp[5] = comp[5][:-37].copy()                      # truncated: must fail alone
-    n = len(comp)
-    outs = [np.zeros(MiB, dtype=np.uint8) for _ in range(n)]
-    srcs = (C.c_void_p * n)(*[c.ctypes.data for c in comp])
-    dsts = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
-    csz = (C.c_uint32 * n)(*[c.size for c in comp])
-    osz = (C.c_uint32 * n)()
-    st = (C.c_int32 * n)()
-    rc = L.emu_zstdg_decode_multi(n, srcs, csz, dsts, MiB, 5, osz, st)
-    assert rc == 0
-    for i in range(n):
-        if i == 5:
-            assert st[i] != 0
-        else:
-            assert st[i] == 0 and osz[i] == MiB and np.array_equal(outs[i], blocks[i]), i
 
 
 # ---- phase-split pipeline (zstd_decode_p.cuh): stages 1-4 + fallback -------------------------
