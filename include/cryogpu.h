@@ -161,10 +161,11 @@ void cryogpu_last_transfer_bytes(const cryogpu_ctx *ctx, uint64_t *h2d, uint64_t
 int cryogpu_zstd_pipeline_stats(cryogpu_ctx *ctx, uint64_t *frames, uint64_t *fallback_frames);
 
 /*
- * LZ4 blocks of the last cryogpu_decompress_device call on this context when it was routed per block
- * (batches of more than two blocks per SM): how many blocks the call had, and how many of them the
- * router sent to the CTA-per-block decoder (lz4_decode_c.cuh: blocks with many sequences); smaller
- * batches go to that decoder whole and report 0 / 0.  Waits for the device.  Diagnostics.
+ * LZ4 blocks of the last cryogpu_decompress_device call on this context when the batch had more than
+ * two blocks per SM: how many blocks the call had, and how many of them the one-warp-per-block decoder
+ * handed to the CTA-per-block decoder (lz4_decode_c.cuh) because they had more sequences than a warp
+ * should walk (lz4_decode_w.cuh); smaller batches go to that decoder whole and report 0 / 0.  Waits
+ * for the device.  Diagnostics.
  */
 int cryogpu_lz4_route_stats(cryogpu_ctx *ctx, uint64_t *blocks, uint64_t *cta_blocks);
 

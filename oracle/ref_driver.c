@@ -45,6 +45,24 @@ oref_block_size(void)
     return CRYO_BLCKSZ;
 }
 
+/* sizes and field offsets of the page headers, from the reference's own storage.h (pins oracle/cryo_pages.c) */
+void
+oref_page_layout(uint32_t out[12])
+{
+    out[0] = sizeof(CryoPageHeader);
+    out[1] = sizeof(CryoFirstPageHeader);
+    out[2] = offsetof(CryoPageHeader, first);
+    out[3] = offsetof(CryoPageHeader, next);
+    out[4] = offsetof(CryoFirstPageHeader, created_xid);
+    out[5] = offsetof(CryoFirstPageHeader, compression_method);
+    out[6] = offsetof(CryoFirstPageHeader, compressed_size);
+    out[7] = offsetof(CryoFirstPageHeader, npages);
+    out[8] = offsetof(PageHeaderClone, pd_lower);
+    out[9] = offsetof(PageHeaderClone, pd_upper);
+    out[10] = offsetof(PageHeaderClone, pd_special);
+    out[11] = BLCKSZ;
+}
+
 /* bound the reference allocates: compression.c:67 / compression.c:99 */
 uint64_t
 oref_compress_bound(int method)

@@ -43,18 +43,22 @@
 #define CX_BIG     8192u                /* runs at least this long are CTA-wide bulk operations (2 * CX_BIG <= CX_SPAN) */
 #define CX_LANE    32u                  /* runs up to this long are moved by the sequence's own lane */
 #define CX_HIST    65536u               /* history reloaded into the ring after a bulk operation (LZ4: offsets <= 65535) */
+#define CX_FAR     49152u               /* a match from further back is copied when it is met (CX_FAR + CX_BIG < 65536, CX_FAR >= CX_SPAN) */
 #define CX_PAT     1024u                /* pattern staging for periodic fills (k * off >= 512, + 32) */
+#define CX_TPW     ((CX_SPAN / 512u + CX_WARPS - 1u) / CX_WARPS)    /* 512-byte tiles of a chunk per warp (1 with 1 024 threads) */
 
 #ifdef CRYO_EMU
 #define CX_LDCG(p) (*(p))
 #define CX_VLD(p) (*reinterpret_cast<const volatile uint32_t *>(p))
 #define CX_VST(p, v) (*reinterpret_cast<volatile uint32_t *>(p) = (v))
 #define CX_SYNC_OR(p) emu_syncthreads_or(p)
+#define CX_COMPILER_FENCE() __asm__ __volatile__("" ::: "memory")
 #else
 #define CX_LDCG(p) __ldcg(p)
 #define CX_VLD(p) (*reinterpret_cast<const volatile uint32_t *>(p))
 #define CX_VST(p, v) (*reinterpret_cast<volatile uint32_t *>(p) = (v))
 #define CX_SYNC_OR(p) __syncthreads_or(p)
+#define CX_COMPILER_FENCE() asm volatile("" ::: "memory")
 #endif
 
 /* development aid (-DCX_PROF): thread 0 of CTA 0 charges the cycles since the previous mark to a phase counter */
@@ -425,44 +429,54 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
     CXP(9)
     const uint32_t kpos = sh->bcast[0];         /* end of the chunk's last sequence */
     /*
-     * ---- matches, step 1: every match byte either becomes final (its source was produced before the
-     * chunk) or records the distance to its source.  A match that overlaps itself (offset < length)
-     * repeats the offset bytes before it: byte i is sourced from byte i mod offset of that period, so
-     * the chain inside the match is cut here, not by the rounds below. ----
+     * ---- matches, step 1: every match byte records the distance to its source (16 bits: a chunk covers
+     * CX_SPAN bytes and the window of an LZ4 block is 64 KiB; a zstd match from further back than CX_FAR
+     * is copied here instead -- its source is older than the chunk, so it is final).  Stores only, no
+     * loads.  A match that overlaps itself (offset < length) repeats the offset bytes before it: byte i
+     * is sourced from byte i mod offset of that period, so the chain inside the match is cut here, not
+     * by the rounds below. ----
      */
     if (mine && ml && ml <= CX_LANE)
     {
-        const uint32_t s0 = mpos - off;
-        uint32_t       r = 0;
-
-        for (uint32_t i = 0; i < ml; i++)
+        if (off > CX_FAR)
         {
-            const uint32_t sp = s0 + r, d = mpos + i;
+            const uint32_t s0 = mpos - off;
 
-            if (sp < pos0)
-                cx.ring[d & CX_RMASK] = cx_src(cx, sp, lo);
-            else
-                cx.dl[d - pos0] = (uint16_t) (d - sp);
-            r++;
-            r = r == off ? 0u : r;
+            for (uint32_t i = 0; i < ml; i++)
+                cx.ring[(mpos + i) & CX_RMASK] = cx_src(cx, s0 + i, lo);
+        }
+        else
+        {
+            uint16_t *dp = cx.dl + (mpos - pos0);
+            uint32_t  r = 0;
+
+            for (uint32_t i = 0; i < ml; i++)
+            {
+                dp[i] = (uint16_t) (off + i - r);
+                r++;
+                r = r == off ? 0u : r;
+            }
         }
     }
     for (uint32_t m = __ballot_sync(CRYO_FULL, mine && ml > CX_LANE); m; m &= m - 1)
     {
         const int      j = __ffs((int) m) - 1;
         const uint32_t jm = __shfl_sync(CRYO_FULL, ml, j), jo = __shfl_sync(CRYO_FULL, off, j);
-        const uint32_t jp = __shfl_sync(CRYO_FULL, mpos, j), s0 = jp - jo;
+        const uint32_t jp = __shfl_sync(CRYO_FULL, mpos, j);
+
+        if (jo > CX_FAR)
+        {
+            for (uint32_t i = lane; i < jm; i += 32)
+                cx.ring[(jp + i) & CX_RMASK] = cx_src(cx, jp - jo + i, lo);
+            continue;
+        }
         const uint32_t step = jo >= 32u ? 32u : 32u % jo;
         uint32_t       r = lane < jo ? lane : lane % jo;
+        uint16_t      *dp = cx.dl + (jp - pos0);
 
         for (uint32_t i = lane; i < jm; i += 32)
         {
-            const uint32_t sp = s0 + r, d = jp + i;
-
-            if (sp < pos0)
-                cx.ring[d & CX_RMASK] = cx_src(cx, sp, lo);
-            else
-                cx.dl[d - pos0] = (uint16_t) (d - sp);
+            dp[i] = (uint16_t) (jo + i - r);
             r += step;
             r = r >= jo ? r - jo : r;
         }
@@ -470,56 +484,78 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
     __syncthreads();
     CXP(10)
     /*
-     * ---- matches, step 2: pointer jumping.  Thread t owns the bytes [16 g, 16 g + 16) of the chunk,
-     * g = t, t + CX_THREADS, ...  A round needs no barrier between its reads and its writes: a byte
-     * that reads a distance another thread is replacing sees either the old or the new one, and both
-     * name a byte with the value it is after; a value is written (and fenced) before its distance is
-     * cleared, and read after the distance was seen cleared.  The barrier at the end of a round only
-     * tells whether any byte is left (bar.red.or).
+     * ---- matches, step 2: pointer jumping.  A warp owns tiles of 512 bytes of the chunk and takes them
+     * 32 consecutive bytes at a time, one per lane: the bytes of one match then read consecutive
+     * sources, so the scattered 1- and 2-byte accesses of a row fall into few shared-memory wavefronts
+     * (with 16 consecutive bytes per thread every access of a warp went to 8 banks).  An unresolved
+     * byte whose source lies before the chunk, or is final, takes its value; one whose source is
+     * unresolved adds that byte's distance to its own.  A round needs no barrier between its reads
+     * and its writes: a byte that reads a distance another thread is replacing sees the old or the
+     * new one, and both name a byte with the value it is after; a value is written (and fenced)
+     * before its distance is cleared, and read after the distance was seen cleared.  The barrier at
+     * the end of a round only tells whether any byte is left (bar.red.or).
      */
     {
-        const uint32_t ngroups = (kpos - pos0 + 15u) >> 4;
-        volatile const uint16_t *vdl = cx.dl;
-        volatile uint8_t *vring = cx.ring;
+        const uint32_t ntiles = (kpos - pos0 + 511u) >> 9;
+        uint32_t       rows[CX_TPW];    /* per tile of this warp (warp, warp + CX_WARPS, ...): rows with unresolved bytes */
+
+#pragma unroll
+        for (uint32_t which = 0; which < CX_TPW; which++)
+            rows[which] = warp + which * CX_WARPS < ntiles ? 0xFFFFu : 0u;
 
         for (;;)
         {
-            bool left = false;
-
             CXP_COUNT(16, 1)
-            for (uint32_t g = tid; g < ngroups; g += CX_THREADS)
-            {
-                uint8_t    *gp = reinterpret_cast<uint8_t *>(cx.dl + 16u * g);
-                const uint4 a = ld16(gp), b = ld16(gp + 16);
-                uint32_t    w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            uint32_t any = 0;
 
-                if ((a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) == 0u)
+#pragma unroll
+            for (uint32_t which = 0; which < CX_TPW; which++)
+            {
+                uint32_t       r = rows[which];
+                const uint32_t base = ((warp + which * CX_WARPS) << 9) + lane;
+
+                if (r == 0)
                     continue;
 #pragma unroll
-                for (uint32_t q = 0; q < 16; q++)
+                for (uint32_t h = 0; h < 16; h += 4)
                 {
-                    const uint32_t d = (w[q >> 1] >> (16u * (q & 1u))) & 0xFFFFu;
+                    if (((r >> h) & 15u) == 0u)
+                        continue;
+                    uint32_t d[4], ds[4];
+                    uint8_t  v[4];
 
-                    if (d)
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; q++)
+                        d[q] = cx.dl[base + 32u * (h + q)];
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; q++)
                     {
-                        const uint32_t idx = 16u * g + q, sidx = idx - d;
-                        const uint32_t ds = vdl[sidx];
+                        const uint32_t idx = base + 32u * (h + q);
 
-                        if (ds == 0)
-                        {
-                            vring[(pos0 + idx) & CX_RMASK] = vring[(pos0 + sidx) & CX_RMASK];
-                            w[q >> 1] &= ~(0xFFFFu << (16u * (q & 1u)));
-                        }
-                        else
-                            w[q >> 1] += ds << (16u * (q & 1u));
+                        ds[q] = (d[q] != 0u && d[q] <= idx) ? (uint32_t) cx.dl[idx - d[q]] : 0u;
+                    }
+                    CX_COMPILER_FENCE();        /* the values are read after the distances */
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; q++)
+                        v[q] = (d[q] != 0u && ds[q] == 0u) ? cx_src(cx, pos0 + base + 32u * (h + q) - d[q], lo) : (uint8_t) 0;
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; q++)
+                        if (d[q] != 0u && ds[q] == 0u)
+                            cx.ring[(pos0 + base + 32u * (h + q)) & CX_RMASK] = v[q];
+                    __threadfence_block();      /* the values before the cleared distances */
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; q++)
+                    {
+                        if (d[q] != 0u)
+                            cx.dl[base + 32u * (h + q)] = (uint16_t) (ds[q] == 0u ? 0u : d[q] + ds[q]);
+                        if (__ballot_sync(CRYO_FULL, d[q] != 0u && ds[q] != 0u) == 0u)
+                            r &= ~(1u << (h + q));
                     }
                 }
-                __threadfence_block();  /* the values before the cleared distances */
-                st16(gp, make_uint4(w[0], w[1], w[2], w[3]));
-                st16(gp + 16, make_uint4(w[4], w[5], w[6], w[7]));
-                left = left || (w[0] | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) != 0u;
+                rows[which] = r;
+                any |= r;
             }
-            if (!CX_SYNC_OR(left))
+            if (!CX_SYNC_OR(any != 0u))
                 break;
         }
     }

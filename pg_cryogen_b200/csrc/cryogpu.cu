@@ -61,114 +61,6 @@ fail(int code, const char *fmt, ...)
 
 /* ----------------------------------------------------------------- kernels */
 
-/*
- * Which decoder takes an LZ4 block: the one-warp-per-block kernel (thousands of blocks in flight hide its
- * serial chain) or the CTA-per-block kernel (lz4_decode_c.cuh), which a block with many sequences needs
- * whatever the batch size.  The number of sequences is not in the format; it is estimated by one lane
- * per block that walks the first LZ4R_PROBE tokens of the stream (the only place where the token chain is
- * known to start) and scales their density to the stream.  A walk from the middle of the stream is no
- * use: in a literal-heavy block it hops through hex digits and sees a token every few bytes.
- * route[b]: 0 = warp, 1 = CTA.
- */
-#define LZ4R_CX_SEQS 4096u             /* estimated sequences from which the CTA kernel is the faster one */
-#define LZ4R_PROBE   96u
-
-__global__ void __launch_bounds__(128)
-k_lz4_route(const int32_t *methods, const uint8_t *src, const uint64_t *src_off, const uint32_t *src_size,
-            uint32_t *route, uint32_t n, uint32_t cap)
-{
-    const uint32_t b = blockIdx.x * 128u + threadIdx.x;
-
-    if (b >= n)
-        return;
-    uint32_t est = 0;
-    const uint32_t csize = src_size[b];
-
-    if (methods[b] == CRYOGPU_LZ4 && csize >= 1024u && cap <= LZ4C_MAXCAP)
-    {
-        const uint8_t *in = src + src_off[b];
-        uint32_t p = 0, hops = 0;
-
-        while (hops < LZ4R_PROBE && p + 3u <= csize)
-        {
-            const uint32_t tk = in[p];
-            uint32_t q = p + 1u, ll = tk >> 4, ml = tk & 15u;
-
-            if (ll == 15u)
-                for (uint32_t x = 255u; x == 255u && q < csize; ll += x)
-                    x = in[q++];
-            q += ll + 2u;
-            if (ml == 15u)
-                for (uint32_t x = 255u; x == 255u && q < csize; )
-                    x = in[q++];
-            if (q <= p)
-                break;                  /* a literal length that wraps: the decoder will reject the block */
-            p = q;
-            hops++;
-        }
-        est = p >= csize || p == 0 ? hops : (uint32_t) (((uint64_t) csize * hops) / p);
-    }
-    route[b] = est >= LZ4R_CX_SEQS ? 1u : 0u;
-}
-
-/* latency path and match-rich blocks: one CTA per block, persistent CTAs take the routed blocks in order */
-__global__ void __launch_bounds__(CX_THREADS, 1)
-k_lz4_decode_c(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
-               const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
-               uint32_t *out_size, int32_t *status, uint32_t n, const uint32_t *route,
-               uint32_t *counter, unsigned long long *gseq)
-{
-    __shared__ uint32_t next_b;
-
-    for (;;)
-    {
-        __syncthreads();
-        if (threadIdx.x == 0)
-            next_b = atomicAdd(counter, 1u);
-        __syncthreads();
-        const uint32_t b = next_b;
-
-        if (b >= n)
-            return;
-        if (methods[b] != CRYOGPU_LZ4 || (route && route[b] != 1u))
-            continue;
-        lz4c_decode_block(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b, status + b,
-                          CRYO_SMEM_BASE(), gseq + (size_t) blockIdx.x * LZ4C_SEQCAP, threadIdx.x);
-    }
-}
-
-/* throughput path: one warp per block, LZ4W_WARPS blocks per CTA */
-__global__ void __launch_bounds__(LZ4W_THREADS)
-k_lz4_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
-               const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
-               uint32_t *out_size, int32_t *status, uint32_t n, const uint32_t *route)
-{
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t b = blockIdx.x * LZ4W_WARPS + warp;
-
-    if (b >= n || methods[b] != CRYOGPU_LZ4 || (route && route[b] != 0u))
-        return;
-    lz4w_decode_block(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
-                      status + b, CRYO_SMEM_BASE() + warp * LZ4W_PER_WARP, lane);
-}
-
-/* throughput path (default): one warp per frame, ZSW_WARPS frames per CTA */
-__global__ void __launch_bounds__(ZSW_THREADS, ZSW_CTAS_PER_SM)
-k_zstd_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
-                const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
-                uint32_t *out_size, int32_t *status, uint8_t *scratch, uint64_t scratch_stride,
-                const uint32_t *predef, uint32_t n, const uint32_t *only)
-{
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t b = blockIdx.x * ZSW_WARPS + warp;
-
-    if (b >= n || methods[b] != CRYOGPU_ZSTD || (only && only[b] == 0))
-        return;
-    zstdw_decode_frame(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
-                       status + b, scratch + b * scratch_stride, predef,
-                       CRYO_SMEM_BASE() + warp * ZSW_PER_WARP, lane);
-}
-
 /* development aid (-DZP_TIMELINE): every pipeline kernel records the first CTA start and the last CTA
  * end on the GPU's global timer, printed by cryogpu_decompress_device when CRYOGPU_ZP_TIMELINE is set */
 #ifdef ZP_TIMELINE
@@ -192,6 +84,77 @@ __device__ unsigned long long zp_tl[32];
 #define ZP_TL_BEGIN(k)
 #define ZP_TL_END(k)
 #endif
+
+/* sequences after which the one-warp-per-block LZ4 decoder hands a block to the CTA decoder (lz4_decode_w.cuh) */
+#define LZ4W_BUDGET 3072u
+
+/* latency path and match-rich blocks: one CTA per block, persistent CTAs take the routed blocks in order */
+__global__ void __launch_bounds__(CX_THREADS, 1)
+k_lz4_decode_c(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
+               const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
+               uint32_t *out_size, int32_t *status, uint32_t n, const uint32_t *list,
+               uint32_t *counter, unsigned long long *gseq)
+{
+    __shared__ uint32_t next_b;
+
+    ZP_TL_BEGIN(10)
+    for (;;)
+    {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            next_b = atomicAdd(counter, 1u);
+        __syncthreads();
+        /* list: the blocks the warp decoder gave up (counter[1] of them); without it every LZ4 block of the batch */
+        if (next_b >= (list ? counter[1] : n))
+        {
+            ZP_TL_END(10)
+            return;
+        }
+        const uint32_t b = list ? list[next_b] : next_b;
+
+        if (methods[b] != CRYOGPU_LZ4)
+            continue;
+        lz4c_decode_block(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b, status + b,
+                          CRYO_SMEM_BASE(), gseq + (size_t) blockIdx.x * LZ4C_SEQCAP, threadIdx.x);
+    }
+}
+
+/* throughput path: one warp per block, LZ4W_WARPS blocks per CTA */
+__global__ void __launch_bounds__(LZ4W_THREADS)
+k_lz4_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
+               const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
+               uint32_t *out_size, int32_t *status, uint32_t n, uint32_t *list, uint32_t *count)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * LZ4W_WARPS + warp;
+
+    ZP_TL_BEGIN(9)
+    if (b >= n || methods[b] != CRYOGPU_LZ4)
+        return;
+    /* list: where the blocks with too many sequences for one warp are queued for k_lz4_decode_c */
+    if (lz4w_decode_block(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
+                          status + b, CRYO_SMEM_BASE() + warp * LZ4W_PER_WARP, lane,
+                          list && cap <= LZ4C_MAXCAP ? LZ4W_BUDGET : 0u) && lane == 0)
+        list[atomicAdd(count, 1u)] = b;
+}
+
+/* throughput path (default): one warp per frame, ZSW_WARPS frames per CTA */
+__global__ void __launch_bounds__(ZSW_THREADS, ZSW_CTAS_PER_SM)
+k_zstd_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_off,
+                const uint32_t *src_size, uint8_t *dst, uint64_t dst_stride, uint32_t cap,
+                uint32_t *out_size, int32_t *status, uint8_t *scratch, uint64_t scratch_stride,
+                const uint32_t *predef, uint32_t n, const uint32_t *only)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * ZSW_WARPS + warp;
+
+    ZP_TL_BEGIN(12)
+    if (b >= n || methods[b] != CRYOGPU_ZSTD || (only && only[b] == 0))
+        return;
+    zstdw_decode_frame(src + src_off[b], src_size[b], dst + b * dst_stride, cap, out_size + b,
+                       status + b, scratch + b * scratch_stride, predef,
+                       CRYO_SMEM_BASE() + warp * ZSW_PER_WARP, lane);
+}
 
 /* defaults of the pipeline's knobs (each has an environment override, see launch_zstd_decode) */
 #ifndef ZP_L2HINT_DEFAULT
@@ -398,19 +361,22 @@ k_zp_execute_c(const ZpArgs a, uint32_t *counter)
 {
     __shared__ uint32_t next_f;
 
+    ZP_TL_BEGIN(11)
     for (;;)
     {
         __syncthreads();
         if (threadIdx.x == 0)
             next_f = atomicAdd(counter, 1u);
         __syncthreads();
-        const uint32_t f = next_f;
-
-        if (f >= a.n)
+        if (next_f >= *a.cxcount)
+        {
+            ZP_TL_END(11)
             return;
-        if (a.methods[f] != ZP_METHOD_ZSTD || a.flag[f] != 0 || a.fr[(size_t) f * ZP_FF] == 0 ||
-            a.fr[(size_t) f * ZP_FF + 3] != 1u)
-            continue;
+        }
+        const uint32_t f = a.cxlist[next_f];
+
+        if (a.flag[f] != 0 || a.fr[(size_t) f * ZP_FF] == 0)
+            continue;                   /* a later stage declined the frame */
         zp_stage4_cx(a, f, CRYO_SMEM_BASE(), threadIdx.x);
     }
 }
@@ -555,8 +521,8 @@ lz4_kernel_choice()
     return v;
 }
 
-/* device memory behind the CTA-per-block LZ4 decoder for a batch of n blocks: the work counter, the
- * route of every block, and the sequence records of one parse round per CTA */
+/* device memory behind the CTA-per-block LZ4 decoder for a batch of n blocks: the work counter and the
+ * length of the list, the list of blocks the warp decoder gave up, the sequence records of one parse round per CTA */
 static size_t
 lz4c_grid(size_t n, int sm_count)
 {
@@ -571,7 +537,7 @@ lz4c_bytes(size_t n, int sm_count)
 
 /*
  * LZ4 blocks of a batch.  Small batches (every block can have an SM of its own) go to the CTA-per-block
- * kernel whole; larger ones are routed per block (k_lz4_route).  work: lz4c_bytes(n) bytes, or nullptr
+ * kernel whole; in larger ones the warp decoder hands over the blocks with too many sequences.  work: lz4c_bytes(n) bytes, or nullptr
  * (allocation failed, block size beyond the record format): one warp per block.
  */
 static void
@@ -585,24 +551,22 @@ launch_lz4_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint8
     if (!work || cap > LZ4C_MAXCAP || choice == 1)
     {
         k_lz4_decode_w<<<(unsigned) ((n + LZ4W_WARPS - 1) / LZ4W_WARPS), LZ4W_THREADS, LZ4W_SMEM, st>>>(
-            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n, nullptr);
+            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n, nullptr, nullptr);
         return;
     }
     uint32_t *counter = (uint32_t *) work;
-    uint32_t *route = (uint32_t *) ((uint8_t *) work + 256);
-    unsigned long long *gseq = (unsigned long long *) ((uint8_t *) work + 256 + ((n * 4 + 255) & ~(size_t) 255));
+    const size_t na = (n * 4 + 255) & ~(size_t) 255;
+    uint32_t *list = (uint32_t *) ((uint8_t *) work + 256);
+    unsigned long long *gseq = (unsigned long long *) ((uint8_t *) work + 256 + na);
     const bool all_cx = choice == 2 || n <= (size_t) 2 * sm_count;
 
-    cudaMemsetAsync(counter, 0, 4, st);
+    cudaMemsetAsync(counter, 0, 8, st);         /* work counter, length of the list */
     if (!all_cx)
-    {
-        k_lz4_route<<<(unsigned) ((n + 127) / 128), 128, 0, st>>>(methods, src, src_off, src_size, route, (uint32_t) n, cap);
         k_lz4_decode_w<<<(unsigned) ((n + LZ4W_WARPS - 1) / LZ4W_WARPS), LZ4W_THREADS, LZ4W_SMEM, st>>>(
-            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n, route);
-    }
+            methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n, list, counter + 1);
     k_lz4_decode_c<<<(unsigned) lz4c_grid(n, sm_count), CX_THREADS, LZ4C_SMEM, st>>>(
         methods, src, src_off, src_size, dst, dst_stride, cap, out_size, status, (uint32_t) n,
-        all_cx ? nullptr : route, counter, gseq);
+        all_cx ? nullptr : list, counter, gseq);
 }
 
 /* CRYOGPU_ZSTD_KERNEL = warp selects the one-warp-per-frame decoder for every frame (2); default: the
@@ -631,7 +595,7 @@ zp_al(size_t v)
 static size_t
 zp_bytes(size_t n, uint32_t cap)
 {
-    return zp_al(n * ZP_FF * 4) + 2 * zp_al(n * 4) + zp_al(n * 8) + 256 + zp_al(n * ZP_MAXB * ZP_BF * 4) +
+    return zp_al(n * ZP_FF * 4) + 3 * zp_al(n * 4) + zp_al(n * 8) + 256 + zp_al(n * ZP_MAXB * ZP_BF * 4) +
            zp_al(n * zp_lit_stride(cap)) + zp_al(zp_seq_cap(n, cap) * 8) + zp_al(n * ZP_MAXB * 4096) +
            zp_al(n * ZP_MAXB * ZP3_CELLS * 4);
 }
@@ -647,9 +611,12 @@ zp_carve(ZpArgs &a, void *base, size_t n, uint32_t cap)
     p += zp_al(n * 4);
     a.pf_done = (uint32_t *) p;
     p += zp_al(n * 4);
+    a.cxlist = (uint32_t *) p;
+    p += zp_al(n * 4);
     a.seqbase = (uint64_t *) p;
     p += zp_al(n * 8);
-    a.seq_alloc = (unsigned long long *) p;
+    a.seq_alloc = (unsigned long long *) p;         /* + 8: work counter of k_zp_execute_c, + 12: cxcount */
+    a.cxcount = (uint32_t *) p + 3;
     p += 256;
     a.blk = (uint32_t *) p;
     p += zp_al(n * ZP_MAXB * ZP_BF * 4);
@@ -766,17 +733,18 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             cudaStreamWaitEvent(aux[1], ev[0], 0);
             k_zp_prefill<<<pf_grid, ZP0_THREADS, 0, aux[1]>>>(a);
             cudaEventRecord(ev[2], aux[1]);
-            if (exec_choice != 1)
-            {
-                /* the frames with many sequences, beside the warp executor */
-                cudaStreamWaitEvent(aux[0], ev[0], 0);
-                k_zp_execute_c<<<(unsigned) std::min<size_t>(n, (size_t) sm_count), CX_THREADS, ZC_SMEM, aux[0]>>>(a, cx_counter);
-                cudaEventRecord(ev[3], aux[0]);
-            }
             k_zp_execute<<<(unsigned) ((n + ZP4_WARPS - 1) / ZP4_WARPS), ZP4_THREADS, ZP4_SMEM, st>>>(a);
-            cudaStreamWaitEvent(st, ev[2], 0);
+            /*
+             * The frames with many sequences, after the warp executor in the same stream.  A CTA of this
+             * kernel takes a whole SM (1 024 threads x 64 registers): launched beside the others it makes
+             * the SMs drain first and then races the raw / RLE stage and the warp executor for them, and
+             * that stage must have its CTAs resident before the executor's (profiles/r01e_arrangements.txt;
+             * measured again in round 2: 4.0 ms per headline step instead of 1.1).  With nothing routed the
+             * CTAs find an empty list and leave.
+             */
             if (exec_choice != 1)
-                cudaStreamWaitEvent(st, ev[3], 0);
+                k_zp_execute_c<<<(unsigned) std::min<size_t>(n, (size_t) sm_count), CX_THREADS, ZC_SMEM, st>>>(a, cx_counter);
+            cudaStreamWaitEvent(st, ev[2], 0);
         }
         /* frames the pipeline declined (flag set): decoded from scratch, one warp per frame */
         k_zstd_decode_w<<<(unsigned) ((n + ZSW_WARPS - 1) / ZSW_WARPS), ZSW_THREADS, ZSW_SMEM, st>>>(
@@ -957,7 +925,7 @@ set_kernel_attrs(cryogpu_ctx *ctx)
                                     (const void *) k_zp_sequences_small, (const void *) k_zp_sequences_large,
                                     (const void *) k_zp_execute, (const void *) k_zstd_decode_w,
                                     (const void *) k_zp_execute_c, (const void *) k_lz4_decode_c,
-                                    (const void *) k_lz4_decode_w, (const void *) k_lz4_route,
+                                    (const void *) k_lz4_decode_w,
                                     (const void *) k_flag_unknown_methods};
 
         for (const void *k : zp_kernels)
@@ -1051,11 +1019,18 @@ cryogpu_init(int device, cryogpu_ctx **out)
     for (int l = 0; l < 2; l++)
     {
         for (int k = 0; k < 2; k++)
-            if (cudaStreamCreateWithFlags(&ctx->zaux[l][k], cudaStreamNonBlocking) != cudaSuccess)
+        {
+            /* zaux[l][1] carries the raw / RLE stage, whose CTAs must become resident before the executor's
+             * (profiles/r01e_arrangements.txt): highest priority, so they win whenever an SM has room */
+            int lo_pri = 0, hi_pri = 0;
+
+            cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+            if (cudaStreamCreateWithPriority(&ctx->zaux[l][k], cudaStreamNonBlocking, k == 1 ? hi_pri : lo_pri) != cudaSuccess)
             {
                 delete ctx;
                 return fail(CRYOGPU_E_CUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
+        }
         for (int k = 0; k < 4; k++)
             if (cudaEventCreateWithFlags(&ctx->zev[l][k], cudaEventDisableTiming) != cudaSuccess)
             {
@@ -1165,12 +1140,11 @@ cryogpu_lz4_route_stats(cryogpu_ctx *ctx, uint64_t *blocks, uint64_t *cta_blocks
     CU(cudaDeviceSynchronize());
     if (ctx->last_lz_n)
     {
-        std::vector<uint32_t> route(ctx->last_lz_n);
+        uint32_t cnt[2] = {0, 0};       /* work counter, length of the list of blocks handed to the CTA decoder */
 
-        CU(cudaMemcpy(route.data(), (uint8_t *) ctx->lzw[0].p + 256, route.size() * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(cnt, ctx->lzw[0].p, sizeof(cnt), cudaMemcpyDeviceToHost));
         total = ctx->last_lz_n;
-        for (uint32_t r : route)
-            cx += r == 1u;
+        cx = cnt[1];
     }
     if (blocks)
         *blocks = total;

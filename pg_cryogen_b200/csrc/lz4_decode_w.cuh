@@ -1,6 +1,6 @@
 /*
  * lz4_decode_w.cuh -- batched LZ4 block decompression, ONE WARP per cryo block
- * (the throughput path; lz4_decode.cuh is the one-CTA-per-block variant).
+ * (the throughput path; lz4_decode_c.cuh is the one-CTA-per-block decoder).
  *
  * Replaces LZ4_decompress_safe as called at reference compression.c:84, with
  * the same acceptance rules.  The token stream is parsed out of
@@ -10,6 +10,13 @@
  * them in heap-tuple data -- takes a straight-line fast path: two dependent
  * shared-memory reads (token, offset), one predicated literal move, one
  * predicated match move.
+ *
+ * A warp takes about half a microsecond per sequence, so a block with a hundred thousand of
+ * them is not for this decoder.  How many sequences a block has is not in the format, and
+ * sampling the stream does not tell (a literal-heavy block looks dense wherever a sample starts
+ * but at a true token; the item-id array at the head of a cryo block is dense whatever follows):
+ * the warp simply counts, and past `budget` sequences it gives the block up -- writes nothing
+ * to status -- and the caller queues it for the CTA decoder, which starts it from scratch.
  */
 #pragma once
 #include "cryo_wexec.cuh"
@@ -84,10 +91,13 @@ CRYO_DEV uint32_t lz4w_read_ext(Lz4Win &in, uint32_t &ip, uint32_t lane, int &er
     }
 }
 
-/* one warp decodes one block; `smem` is this warp's LZ4W_PER_WARP bytes */
-CRYO_DEV void lz4w_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out, uint32_t cap,
-                                uint32_t *out_size, int32_t *status, uint8_t *smem, uint32_t lane)
+/* one warp decodes one block; `smem` is this warp's LZ4W_PER_WARP bytes.  budget: sequences after which the
+ * block is given up (0: never).  Returns true when it was. */
+CRYO_DEV bool lz4w_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out, uint32_t cap,
+                                uint32_t *out_size, int32_t *status, uint8_t *smem, uint32_t lane, uint32_t budget = 0)
 {
+    uint32_t nseq = 0;
+
     WOut   o;
     Lz4Win in;
     int    err = ST_OK;
@@ -118,6 +128,8 @@ CRYO_DEV void lz4w_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
             err = ST_INPUT;
             break;
         }
+        if (budget && ++nseq > budget)
+            return true;
         uint32_t rel = ip - in.wbase;
         uint32_t token = in.win[rel];
         uint32_t ll = token >> 4, ml = token & 15u;
@@ -277,4 +289,5 @@ CRYO_DEV void lz4w_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
         *out_size = err == ST_OK ? o.pos : 0u;
         *status = err;
     }
+    return false;
 }

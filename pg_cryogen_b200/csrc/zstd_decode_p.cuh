@@ -78,6 +78,8 @@ struct ZpArgs
     uint32_t       *flag;       /* n; non-zero: frame goes to the warp-per-frame decoder */
     uint64_t       *seqbase;    /* n; first entry of the frame in seq[] */
     unsigned long long *seq_alloc;
+    uint32_t       *cxlist;     /* frames routed to the CTA-per-frame stage 4, in no particular order */
+    uint32_t       *cxcount;    /* how many */
     uint32_t       *pf_done;    /* n; blocks of the frame stage 0 has finished (release / acquire with stage 4) */
     uint32_t        pf_hint;    /* bit 0: stage 0 bulk stores with the L2 evict_first policy; bit 1: stage 4 asks L2 for
                                  * sequences and literals a few loads ahead; bit 2: every frame takes the CTA-per-frame
@@ -345,8 +347,11 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
 
         fr[3] = cx ? 1u : 0u;
         if (cx)
+        {
             for (uint32_t j = 0; j < fr[0]; j++)
                 a.blk[((size_t) f * ZP_MAXB + j) * ZP_BF + ZPB_SPECPOS] = ~0u;
+            a.cxlist[atomicAdd(a.cxcount, 1u)] = f;
+        }
     }
     if (!ok)
     {

@@ -62,12 +62,13 @@ emu_zstdc_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap,
     if (csize)
         memcpy(ib + off, src, csize);
     const uint64_t lit_stride = zp_lit_stride(cap), seq_cap = zp_seq_cap(1, cap);
-    std::vector<uint32_t> fr(ZP_FF, 0xCDCDCDCD), blk((size_t) ZP_MAXB * ZP_BF, 0xCDCDCDCD), flag(1, 0xCDCDCDCD), pf_done(1, 0);
+    std::vector<uint32_t> fr(ZP_FF, 0xCDCDCDCD), blk((size_t) ZP_MAXB * ZP_BF, 0xCDCDCDCD), flag(1, 0xCDCDCDCD), pf_done(1, 0), cxlist(1, 0);
     std::vector<uint64_t> seqbase(1, 0), seq(seq_cap + 8, 0x7777777777777777ull);
     std::vector<uint8_t>  lit(lit_stride + 64, 0x99);
     std::vector<uint16_t> huftab((size_t) ZP_MAXB * 2048, 0x3333);
     std::vector<uint32_t> fsetab((size_t) ZP_MAXB * ZP3_CELLS, 0x44444444);
     unsigned long long    seq_alloc = 0;
+    uint32_t              cxcount = 0;
     ZpArgs a;
 
     a.methods = &method;
@@ -85,6 +86,8 @@ emu_zstdc_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap,
     a.flag = flag.data();
     a.seqbase = seqbase.data();
     a.seq_alloc = &seq_alloc;
+    a.cxcount = &cxcount;
+    a.cxlist = cxlist.data();
     a.pf_done = pf_done.data();
     a.pf_hint = 4u;                     /* every frame to the CTA-per-frame stage 4 */
     a.lit = (uint8_t *) ((((uintptr_t) lit.data() + 15) & ~(uintptr_t) 15));

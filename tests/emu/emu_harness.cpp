@@ -211,6 +211,7 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
         if (csizes[i])
             memcpy(ib + off[i], srcs[i], csizes[i]);
     const uint64_t lit_stride = zp_lit_stride(cap), seq_cap = zp_seq_cap((uint64_t) n, cap);
+    std::vector<uint32_t> cxlist((size_t) n, 0);
     std::vector<uint32_t> fr((size_t) n * ZP_FF, 0xCDCDCDCD), blk((size_t) n * ZP_MAXB * ZP_BF, 0xCDCDCDCD),
                           flag(n, 0xCDCDCDCD);
     std::vector<uint64_t> seqbase(n, 0), seq(seq_cap + 8, 0x7777777777777777ull);
@@ -218,6 +219,7 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     std::vector<uint16_t> huftab((size_t) n * ZP_MAXB * 2048, 0x3333);
     std::vector<uint32_t> fsetab((size_t) n * ZP_MAXB * ZP3_CELLS, 0x44444444);
     unsigned long long    seq_alloc = 0;
+    uint32_t              cxcount = 0;
     std::vector<uint32_t> pf_done(n, 0xCDCDCDCD);
     ZpArgs a;
 
@@ -236,8 +238,10 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     a.flag = flag.data();
     a.seqbase = seqbase.data();
     a.seq_alloc = &seq_alloc;
+    a.cxcount = &cxcount;
+    a.cxlist = cxlist.data();
     a.pf_done = pf_done.data();
-    a.pf_hint = 0;
+    a.pf_hint = 8u;                     /* every frame to the warp stage 4 (the CTA stage: emu_cx.cpp) */
     a.lit = (uint8_t *) ((((uintptr_t) lit.data() + 15) & ~(uintptr_t) 15));
     a.lit_stride = lit_stride;
     a.seq = seq.data();

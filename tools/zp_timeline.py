@@ -4,11 +4,12 @@ import ctypes as C, os, subprocess, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-so = os.path.join(ROOT, "gpurun_out", "libcryogpu_tl.so")
+so = os.path.join(ROOT, "tools", "_prof", "libcryogpu_tl.so")      # prebuilt in the build container, or built here
 os.makedirs(os.path.dirname(so), exist_ok=True)
-subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DZP_TIMELINE",
-                       "-Xcompiler", "-fPIC", "-diag-suppress", "550", "-shared", "-o", so,
-                       os.path.join(ROOT, "pg_cryogen_b200", "csrc", "cryogpu.cu")])
+if not os.path.exists(so):
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DZP_TIMELINE",
+                           "-Xcompiler", "-fPIC", "-diag-suppress", "550", "-shared", "-o", so,
+                           os.path.join(ROOT, "pg_cryogen_b200", "csrc", "cryogpu.cu")])
 import benchdata
 from pg_cryogen_b200 import CryoGPU, blockgen as bg, codec
 from pg_cryogen_b200.codec import pack_chunks
@@ -27,7 +28,8 @@ d_sz = torch.from_numpy(sizes.view(np.int32)).to(dev); d_me = torch.full((nblk,)
 d_dst = torch.empty((nblk, 1 << 20), dtype=torch.uint8, device=dev)
 d_osz = torch.zeros((nblk,), dtype=torch.int32, device=dev); d_st = torch.full((nblk,), -1, dtype=torch.int32, device=dev)
 s = torch.cuda.current_stream().cuda_stream
-names = ["parse", "prefill", "huftab", "literals", "fsetab", "seq_small", "seq_large", "execute"]
+names = ["parse", "prefill", "huftab", "literals", "fsetab", "seq_small", "seq_large", "execute",
+         "lz4_route", "lz4_warp", "lz4_cta", "execute_cta", "zstd_warp"]
 for it in range(4):
     L.cryogpu_debug_timeline(None, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -36,7 +38,7 @@ for it in range(4):
     e1.record(); torch.cuda.synchronize()
     out = (C.c_ulonglong * 32)()
     L.cryogpu_debug_timeline(out, 0)
-    t0 = min(out[2 * k] for k in range(8) if out[2 * k + 1])
+    t0 = min(out[2 * k] for k in range(len(names)) if out[2 * k + 1])
     print(f"iteration {it}: {e0.elapsed_time(e1) * 1e3:.0f} us by events")
     for k, nm in enumerate(names):
         if out[2 * k + 1]:
