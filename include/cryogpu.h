@@ -61,6 +61,11 @@ extern "C" {
 #define CRYOGPU_ST_SIZE          5   /* zstd frame content size does not match */
 #define CRYOGPU_ST_METHOD        6   /* unknown per-block method */
 #define CRYOGPU_ST_UNSUPPORTED   7   /* valid but outside what this build handles */
+/* page-chain calls only (cache.c:112-129 returns CRYO_ERR_EMPTY_BLOCK / CRYO_ERR_WRONG_STARTING_BLOCK there) */
+#define CRYOGPU_ST_EMPTY_BLOCK   8   /* the first page is new (pd_upper == 0), or the chain is empty */
+#define CRYOGPU_ST_WRONG_START   9   /* the first page of the chain is not the first page of its cryo block */
+#define CRYOGPU_ST_CHAIN        10   /* the pages do not form the chain of one block, or it is shorter than
+                                      * compressed_size needs (the reference fails in cryo_decompress then) */
 
 typedef struct cryogpu_ctx cryogpu_ctx;
 
@@ -168,6 +173,87 @@ int cryogpu_zstd_pipeline_stats(cryogpu_ctx *ctx, uint64_t *frames, uint64_t *fa
  * for the device.  Diagnostics.
  */
 int cryogpu_lz4_route_stats(cryogpu_ctx *ctx, uint64_t *blocks, uint64_t *cta_blocks);
+
+/*
+ * ------------------------------------------------------------------ page chains
+ *
+ * On disk a compressed cryo block is a chain of 8 KiB PostgreSQL pages (reference storage.h:49-67:
+ * CryoPageHeader 32 bytes with first / next block numbers; the first page's CryoFirstPageHeader, 48 bytes,
+ * adds created_xid, compression_method, compressed_size, npages).  These calls take and give the pages
+ * themselves, so the reference's host-side copies on either side of the codec disappear:
+ *
+ *   cryogpu_decompress_pages_*  replaces the gather loop of cryo_read_decompress (cache.c:151-176) plus the
+ *                               cryo_decompress call after it (cache.c:178): method and compressed size are
+ *                               read from the first page's header on the device;
+ *   cryogpu_compress_pages_*    replaces cryo_compress (pg_cryogen.c:726) plus the split loop of cryo_preserve
+ *                               (pg_cryogen.c:761-805): the output is the page images, headers filled in
+ *                               (first, next, pd_lower / pd_upper / pd_special, and on the first page npages,
+ *                               compression_method, compressed_size, created_xid).  pd_lsn and pd_checksum are
+ *                               the buffer manager's (GenericXLogFinish, PageSetChecksumInplace) and stay zero.
+ *
+ * A chain is described by the host, which has to walk `next` anyway to fetch the pages:
+ *   page_slot[e]   (device call) index of entry e's page in d_pages
+ *   page_blkno[e]  its block number in the relation
+ *   chain_off[i]   block i's chain is the entries [chain_off[i], chain_off[i + 1]), first page first
+ * The device checks every page's first / next against that description (CRYOGPU_ST_CHAIN otherwise).
+ */
+#define CRYOGPU_PAGE_SIZE 8192u
+
+/* cryo_pages_needed, pg_cryogen.c:692-704 */
+uint32_t cryogpu_pages_needed(uint64_t compressed_size);
+
+/* d_methods[i] (out): compression_method as the header has it; d_comp_size[i] (out, may be NULL): compressed_size */
+int cryogpu_decompress_pages_device(cryogpu_ctx *ctx, size_t n, const uint8_t *d_pages,
+                                    const uint32_t *d_page_slot, const uint32_t *d_page_blkno,
+                                    const uint32_t *d_chain_off, size_t total_entries,
+                                    uint8_t *d_dst, uint64_t dst_stride, uint32_t block_size,
+                                    uint32_t *d_out_size, int32_t *d_status, int32_t *d_methods,
+                                    uint32_t *d_comp_size, void *stream);
+
+/*
+ * d_page_blkno: n x cap_pages block numbers reserved for the blocks' pages (block i uses the first
+ * d_npages[i] of its row); cap_pages >= cryogpu_pages_needed(cryogpu_compress_bound(method, block_size)).
+ * d_pages: n x cap_pages x 8 KiB; block i's page k is written at (i * cap_pages + k) * 8192.
+ */
+int cryogpu_compress_pages_device(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel,
+                                  const uint8_t *d_src, uint64_t src_stride, uint32_t block_size,
+                                  const uint32_t *d_page_blkno, uint32_t cap_pages, uint32_t created_xid,
+                                  uint8_t *d_pages, uint32_t *d_npages, uint32_t *d_comp_size,
+                                  int32_t *d_status, void *stream);
+
+/* host pointers: pages[e] = the 8 KiB page of chain entry e where it lies (buffer pool) */
+int cryogpu_decompress_pages_host(cryogpu_ctx *ctx, size_t n, const void *const *pages,
+                                  const uint32_t *page_blkno, const uint32_t *chain_off,
+                                  void *const *dst, uint32_t block_size, uint32_t *out_size,
+                                  int32_t *status, int32_t *methods, uint32_t *comp_size);
+
+/* pages_out[i * cap_pages + k]: where block i's page k goes (only the first npages[i] are written) */
+int cryogpu_compress_pages_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel,
+                                const void *const *src, uint32_t block_size,
+                                const uint32_t *page_blkno, uint32_t cap_pages, uint32_t created_xid,
+                                void *const *pages_out, uint32_t *npages, uint32_t *comp_size,
+                                int32_t *status);
+
+/*
+ * ------------------------------------------------------------ tuple-level work
+ *
+ * The item walk of a sequential scan (cryo_getnextslot, pg_cryogen.c:293-307, over cryo_storage_fetch,
+ * storage.c:55-68) on decoded blocks that are still in HBM: per block the number of tuples, the sum of
+ * their lengths, and whether every CryoItemId lies inside the block.  d_status (may be NULL): blocks whose
+ * decode status is not CRYOGPU_ST_OK are skipped (0 / 0 / 0).  Enqueues one kernel on `stream`.
+ */
+int cryogpu_tuple_stats_device(cryogpu_ctx *ctx, size_t n, const uint8_t *d_blocks, uint64_t stride,
+                               uint32_t block_size, const int32_t *d_status, uint32_t *d_ntuples,
+                               uint64_t *d_tuple_bytes, int32_t *d_valid, void *stream);
+
+/*
+ * Count pushdown: compressed blocks in host memory in; per block ntuples, tuple_bytes and status out.  The
+ * decoded blocks stay on the device, so the call moves csize + 24 bytes per block over the bus instead of
+ * csize + block_size.  A block that decodes but whose item ids point outside it gets CRYOGPU_ST_FORMAT.
+ */
+int cryogpu_decompress_count_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
+                                  const void *const *src, const uint32_t *src_size, uint32_t block_size,
+                                  uint32_t *ntuples, uint64_t *tuple_bytes, int32_t *status);
 
 /*
  * Multi-GPU host variants: the batch is split into contiguous block ranges, one

@@ -152,3 +152,33 @@ cryo_oracle_pages_gather(const uint8_t *rel, uint32_t nrel, uint32_t block, uint
     *got = (uint32_t) (p - out);
     return CRYO_ERR_SUCCESS;
 }
+
+/*
+ * Tuple-level walk of one decoded cryo block: what a sequential scan visits.
+ * storage.h:69-86: CryoDataHeader {uint32 lower, upper; char data[]}, CryoItemId {uint32 off, len};
+ * item positions are 1-based (storage.c:55-68); cryo_getnextslot returns item cur_item while
+ * cur_item * sizeof(CryoItemId) < hdr->lower (pg_cryogen.c:293).  valid: every item lies inside
+ * [upper, block_size) -- the reference only asserts this.
+ */
+void
+cryo_oracle_block_tuple_stats(const uint8_t *block, uint32_t block_size, uint32_t *ntuples, uint64_t *tuple_bytes,
+                              int32_t *valid)
+{
+    const uint32_t lower = get32(block), upper = get32(block + 4);
+    uint32_t n = 0;
+    uint64_t bytes = 0;
+    int      ok = lower >= 8 && lower <= upper && upper <= block_size;
+
+    for (uint32_t cur = 1; (uint64_t) cur * 8u < lower && (uint64_t) cur * 8u + 8u <= block_size; cur++)
+    {
+        const uint32_t off = get32(block + 8u * cur), len = get32(block + 8u * cur + 4);
+
+        bytes += len;
+        n++;
+        if (off < upper || off > block_size || len > block_size - off)
+            ok = 0;
+    }
+    *ntuples = n;
+    *tuple_bytes = bytes;
+    *valid = ok;
+}

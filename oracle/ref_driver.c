@@ -63,6 +63,31 @@ oref_page_layout(uint32_t out[12])
     out[11] = BLCKSZ;
 }
 
+/*
+ * The item walk of a sequential scan over one decoded block: the loop condition of cryo_getnextslot
+ * (pg_cryogen.c:293) around the reference's own cryo_storage_fetch (storage.c:55-68).  Pins
+ * cryo_oracle_block_tuple_stats and the GPU's k_tuple_stats.
+ */
+void
+oref_block_walk(char *block, uint32_t *ntuples, uint64_t *tuple_bytes)
+{
+    CryoDataHeader *hdr = (CryoDataHeader *) block;
+    uint32_t    cur_item = 1, n = 0;
+    uint64_t    bytes = 0;
+
+    while (cur_item * sizeof(CryoItemId) < hdr->lower)
+    {
+        HeapTupleData t;
+
+        cryo_storage_fetch(hdr, cur_item, &t);
+        bytes += t.t_len;
+        n++;
+        cur_item++;
+    }
+    *ntuples = n;
+    *tuple_bytes = bytes;
+}
+
 /* bound the reference allocates: compression.c:67 / compression.c:99 */
 uint64_t
 oref_compress_bound(int method)

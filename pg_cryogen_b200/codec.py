@@ -56,6 +56,23 @@ _PROTOS = {
     "cryogpu_compress_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
                                         C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                         C.c_void_p]),
+    "cryogpu_pages_needed": (C.c_uint32, [C.c_uint64]),
+    "cryogpu_decompress_pages_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_uint32,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cryogpu_compress_pages_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
+                                                C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p,
+                                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cryogpu_decompress_pages_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p]),
+    "cryogpu_compress_pages_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_uint32,
+                                              C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p]),
+    "cryogpu_tuple_stats_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cryogpu_decompress_count_host": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "cryogpu_decompress_host_multi": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p,
                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                                 C.c_void_p, C.c_void_p]),
@@ -211,6 +228,68 @@ class CryoGPU:
             self.handle, n, method, level_or_accel, srcp, block_size, dstp, bound,
             sz.ctypes.data, st.ctypes.data), "cryogpu_compress_host")
         return [dst[i, : sz[i]].copy() for i in range(n)], st
+
+
+    def decompress_count_host(self, methods, chunks, block_size: int = CRYO_BLCKSZ):
+        """Count pushdown: (ntuples, tuple_bytes, status) per block; the decoded blocks stay in HBM."""
+        n = len(chunks)
+        chunks = [np.ascontiguousarray(c, dtype=np.uint8) for c in chunks]
+        methods = np.ascontiguousarray(np.broadcast_to(np.asarray(methods, dtype=np.int32), (n,)))
+        sizes = np.array([c.size for c in chunks], dtype=np.uint32)
+        srcp = (C.c_void_p * n)(*[c.ctypes.data for c in chunks])
+        nt = np.zeros(n, dtype=np.uint32)
+        by = np.zeros(n, dtype=np.uint64)
+        st = np.full(n, -1, dtype=np.int32)
+        self._check(self.lib.cryogpu_decompress_count_host(
+            self.handle, n, methods.ctypes.data, srcp, sizes.ctypes.data, block_size, nt.ctypes.data,
+            by.ctypes.data, st.ctypes.data), "cryogpu_decompress_count_host")
+        return nt, by, st
+
+    # ---- page chains (storage.h:49-67; cache.c:151-176, pg_cryogen.c:761-805) ----
+
+    def decompress_pages_host(self, relation: np.ndarray, chains, block_size: int = CRYO_BLCKSZ):
+        """relation: [npages, 8192] uint8, indexed by block number; chains: per cryo block the list of
+        block numbers of its pages, first page first (what the reader found following `next`).
+        Returns (out [n, block_size], out_size, status, methods, comp_size)."""
+        n = len(chains)
+        flat = [b for ch in chains for b in ch]
+        coff = np.zeros(n + 1, dtype=np.uint32)
+        coff[1:] = np.cumsum([len(ch) for ch in chains])
+        blk = np.asarray(flat, dtype=np.uint32)
+        pagep = (C.c_void_p * max(len(flat), 1))(*[relation[b].ctypes.data for b in flat])
+        out = np.zeros((n, block_size), dtype=np.uint8)
+        dstp = (C.c_void_p * n)(*[out[i].ctypes.data for i in range(n)])
+        osz = np.zeros(n, dtype=np.uint32)
+        st = np.full(n, -1, dtype=np.int32)
+        me = np.full(n, -1, dtype=np.int32)
+        csz = np.zeros(n, dtype=np.uint32)
+        self._check(self.lib.cryogpu_decompress_pages_host(
+            self.handle, n, pagep, blk.ctypes.data, coff.ctypes.data, dstp, block_size, osz.ctypes.data,
+            st.ctypes.data, me.ctypes.data, csz.ctypes.data), "cryogpu_decompress_pages_host")
+        return out, osz, st, me, csz
+
+    def compress_pages_host(self, method: int, level_or_accel: int, blocks: np.ndarray, relation: np.ndarray,
+                            blknos: np.ndarray, created_xid: int, block_size: int = CRYO_BLCKSZ):
+        """blocks: [n, block_size]; blknos: [n, cap_pages] block numbers reserved per block; the pages
+        are written into relation[blkno].  Returns (npages, comp_size, status)."""
+        blocks = np.ascontiguousarray(blocks, dtype=np.uint8).reshape(-1, block_size)
+        n = blocks.shape[0]
+        blknos = np.ascontiguousarray(blknos, dtype=np.uint32).reshape(n, -1)
+        cap = blknos.shape[1]
+        srcp = (C.c_void_p * n)(*[blocks[i].ctypes.data for i in range(n)])
+        outp = (C.c_void_p * (n * cap))(*[relation[int(b)].ctypes.data for b in blknos.reshape(-1)])
+        npg = np.zeros(n, dtype=np.uint32)
+        csz = np.zeros(n, dtype=np.uint32)
+        st = np.full(n, -1, dtype=np.int32)
+        self._check(self.lib.cryogpu_compress_pages_host(
+            self.handle, n, method, level_or_accel, srcp, block_size, blknos.ctypes.data, cap, created_xid, outp,
+            npg.ctypes.data, csz.ctypes.data, st.ctypes.data), "cryogpu_compress_pages_host")
+        return npg, csz, st
+
+
+def pages_needed(compressed_size: int) -> int:
+    """cryo_pages_needed, pg_cryogen.c:692-704"""
+    return int(load_library().cryogpu_pages_needed(compressed_size))
 
 
 def pack_chunks(chunks, align: int = 16):

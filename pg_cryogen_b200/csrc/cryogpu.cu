@@ -15,6 +15,7 @@
 #include "zstd_decode_c.cuh"
 #include "lz4_encode.cuh"
 #include "zstd_encode.cuh"
+#include "cryo_pages.cuh"
 
 #include <cuda_runtime.h>
 
@@ -506,6 +507,77 @@ k_page_compact(const uint8_t *out, uint64_t stride, uint32_t block_size, uint32_
     }
 }
 
+/* ---- page chains (cryo_pages.cuh): one CTA per cryo block ---- */
+
+__global__ void __launch_bounds__(256)
+k_pages_gather(const uint8_t *pages, const uint32_t *slot, const uint32_t *blkno, const uint32_t *chain_off,
+               uint8_t *comp, uint64_t *src_off, uint32_t *src_size, int32_t *dec_method, int32_t *hdr_method,
+               int32_t *chain_status, uint32_t max_csize)
+{
+    const uint32_t b = blockIdx.x;
+
+    pg_gather_block(pages, slot, blkno, chain_off[b], chain_off[b + 1], comp, src_off + b, src_size + b, dec_method + b,
+                    hdr_method + b, chain_status + b, max_csize, threadIdx.x, 256);
+}
+
+/* after the decoders: a block whose chain failed reports that, not the decoders' "unknown method" */
+__global__ void
+k_pages_status(const int32_t *chain_status, const uint32_t *src_size, int32_t *status, uint32_t *out_size,
+               uint32_t *comp_size, uint32_t n)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+
+    if (b >= n)
+        return;
+    if (chain_status[b] != PG_ST_OK)
+    {
+        status[b] = chain_status[b];
+        out_size[b] = 0;
+    }
+    if (comp_size)
+        comp_size[b] = src_size[b];
+}
+
+__global__ void __launch_bounds__(256)
+k_pages_split(const uint8_t *comp, uint64_t comp_stride, const uint32_t *comp_size, const int32_t *comp_status,
+              uint32_t method, uint32_t xid, const uint32_t *blkno, uint32_t cap_pages, uint8_t *pages,
+              uint64_t pages_stride, uint32_t *npages, int32_t *status)
+{
+    const uint32_t b = blockIdx.x;
+    uint32_t np = 0;
+
+    if (comp_status[b] == ST_OK)
+        np = pg_split_block(comp + b * comp_stride, comp_size[b], method, xid, blkno + (size_t) b * cap_pages, cap_pages,
+                            pages + b * pages_stride, threadIdx.x, 256);
+    if (threadIdx.x == 0)
+    {
+        npages[b] = np;
+        status[b] = comp_status[b] != ST_OK ? comp_status[b] : np ? ST_OK : ST_OUTPUT;
+    }
+}
+
+/* tuple-level walk of decoded blocks (cryo_pages.cuh): one warp per block, 8 blocks per CTA */
+__global__ void __launch_bounds__(256)
+k_tuple_stats(const uint8_t *blocks, uint64_t stride, uint32_t block_size, const int32_t *status, uint32_t *ntuples,
+              unsigned long long *tuple_bytes, int32_t *valid, uint32_t n)
+{
+    const uint32_t b = blockIdx.x * 8u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+
+    if (b >= n)
+        return;
+    if (status && status[b] != ST_OK)
+    {
+        if (lane == 0)
+        {
+            ntuples[b] = 0;
+            tuple_bytes[b] = 0;
+            valid[b] = 0;
+        }
+        return;
+    }
+    pg_tuple_stats(blocks + b * stride, block_size, ntuples + b, tuple_bytes + b, valid + b, lane);
+}
+
 /* CRYOGPU_LZ4_KERNEL = warp | cx forces one LZ4 decoder for every block; default: routed per block */
 static int
 lz4_kernel_choice()
@@ -854,6 +926,7 @@ struct cryogpu_ctx
     DevBuf       scratch;               /* per-block kernel scratch */
     DevBuf       zp[2];                 /* zstd pipeline work areas (zstd_decode_p.cuh), per lane */
     DevBuf       lzw[2];                /* CTA-per-block LZ4 decoder work areas (lz4c_bytes), per lane */
+    DevBuf       pgw;                   /* page-chain calls: gathered streams / compressed blocks before the split */
     cudaEvent_t  busy = nullptr;        /* end of the last device-resident call: the work areas are shared */
     cudaStream_t zaux[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   /* side streams of the pipeline's concurrent stages */
     cudaEvent_t  zev[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
@@ -861,7 +934,7 @@ struct cryogpu_ctx
     /* *_host staging (device + pinned host), two lanes */
     DevBuf       d_in[2], d_out[2], d_meta[2];
     DevBuf       h_in[2], h_meta[2], h_out[2];
-    std::mutex   mu;
+    std::recursive_mutex mu;            /* recursive: the page-chain host calls hold it around the device calls they make */
     bool         attrs_set = false;
     int          sm_count = 148;
     /* sparse return of the host decompress call */
@@ -966,6 +1039,9 @@ cryogpu_status_string(int s)
         case CRYOGPU_ST_SIZE: return "frame content size mismatch";
         case CRYOGPU_ST_METHOD: return "unknown compression method";
         case CRYOGPU_ST_UNSUPPORTED: return "unsupported stream feature";
+        case CRYOGPU_ST_EMPTY_BLOCK: return "first page of the chain is new (empty block)";
+        case CRYOGPU_ST_WRONG_START: return "page is not the first page of its cryo block";
+        case CRYOGPU_ST_CHAIN: return "page chain does not hold the compressed block";
         default: return "unknown status";
     }
 }
@@ -1062,6 +1138,7 @@ cryogpu_shutdown(cryogpu_ctx *ctx)
     cudaFree(ctx->zp[1].p);
     cudaFree(ctx->lzw[0].p);
     cudaFree(ctx->lzw[1].p);
+    cudaFree(ctx->pgw.p);
     if (ctx->busy)
         cudaEventDestroy(ctx->busy);
     cudaFree(ctx->predef);
@@ -1195,37 +1272,29 @@ cryogpu_host_free(void *p)
 
 /* ------------------------------------------------------- device-resident API */
 
-extern "C" int
-cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
-                          const uint8_t *d_src, const uint64_t *d_src_off,
-                          const uint32_t *d_src_size, uint8_t *d_dst, uint64_t dst_stride,
-                          uint32_t block_size, uint32_t *d_out_size, int32_t *d_status,
-                          void *stream)
+/* argument checks of the device-resident decompress calls */
+static int
+check_decompress_args(const cryogpu_ctx *ctx, size_t n, const void *d_dst, uint64_t dst_stride, uint32_t block_size)
 {
     if (!ctx)
         return fail(CRYOGPU_E_ARG, "ctx is NULL");
-    if (n == 0)
-        return CRYOGPU_OK;
-    if (!d_methods || !d_src || !d_src_off || !d_src_size || !d_dst || !d_out_size || !d_status)
-        return fail(CRYOGPU_E_ARG, "NULL device pointer");
     if (((uintptr_t) d_dst & 15) || (dst_stride & 15) || dst_stride < block_size)
         return fail(CRYOGPU_E_ARG, "d_dst and dst_stride must be multiples of 16, stride >= block_size");
     if (block_size == 0 || block_size > (1u << 27) || n > 0x7fffffffu)
         return fail(CRYOGPU_E_ARG, "block_size or n out of range");
-    cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
-    bool         use_zp = false;
-    void        *lzw = nullptr;
+    return CRYOGPU_OK;
+}
 
-    CU(cudaSetDevice(ctx->device));
-    /*
-     * The work areas belong to the context, so calls on one context run one after the other on the
-     * device whatever streams they were given: this call's stream first waits for the end of the
-     * previous device-resident call (cryogpu.h).  Work areas only grow; growing one frees and
-     * allocates, which waits for the device: a steady-state call only enqueues.
-     */
-    std::lock_guard<std::mutex> g(ctx->mu);
+/* the launches of one batched decompression on st; ctx->mu is held and st already waits for ctx->busy */
+static int
+decompress_device_locked(cryogpu_ctx *ctx, cudaStream_t st, size_t n, const int32_t *d_methods,
+                         const uint8_t *d_src, const uint64_t *d_src_off,
+                         const uint32_t *d_src_size, uint8_t *d_dst, uint64_t dst_stride,
+                         uint32_t block_size, uint32_t *d_out_size, int32_t *d_status)
+{
+    bool  use_zp = false;
+    void *lzw = nullptr;
 
-    CU(cudaStreamWaitEvent(st, ctx->busy, 0));
     {
         int rc = dev_reserve(ctx->scratch, n * (size_t) ZSTDD_SCRATCH_BYTES);
 
@@ -1275,7 +1344,66 @@ cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
                        d_out_size, d_status, (uint8_t *) ctx->scratch.p, ctx->predef, use_zp ? ctx->zp[0].p : nullptr, ctx->zaux[0],
                        ctx->zev[0], ctx->sm_count);
     CU(cudaGetLastError());
+    return CRYOGPU_OK;
+}
+
+extern "C" int
+cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
+                          const uint8_t *d_src, const uint64_t *d_src_off,
+                          const uint32_t *d_src_size, uint8_t *d_dst, uint64_t dst_stride,
+                          uint32_t block_size, uint32_t *d_out_size, int32_t *d_status,
+                          void *stream)
+{
+    if (ctx && n == 0)
+        return CRYOGPU_OK;
+    int rc = check_decompress_args(ctx, n, d_dst, dst_stride, block_size);
+
+    if (rc != CRYOGPU_OK)
+        return rc;
+    if (!d_methods || !d_src || !d_src_off || !d_src_size || !d_dst || !d_out_size || !d_status)
+        return fail(CRYOGPU_E_ARG, "NULL device pointer");
+    cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
+
+    CU(cudaSetDevice(ctx->device));
+    /*
+     * The work areas belong to the context, so calls on one context run one after the other on the
+     * device whatever streams they were given: this call's stream first waits for the end of the
+     * previous device-resident call (cryogpu.h).  Work areas only grow; growing one frees and
+     * allocates, which waits for the device: a steady-state call only enqueues.
+     */
+    std::lock_guard<std::recursive_mutex> g(ctx->mu);
+
+    CU(cudaStreamWaitEvent(st, ctx->busy, 0));
+    rc = decompress_device_locked(ctx, st, n, d_methods, d_src, d_src_off, d_src_size, d_dst, dst_stride, block_size,
+                                  d_out_size, d_status);
+    if (rc != CRYOGPU_OK)
+        return rc;
     CU(cudaEventRecord(ctx->busy, st));
+    return CRYOGPU_OK;
+}
+
+/* the launch of one batched compression on st; ctx->mu is held and st already waits for ctx->busy */
+static int
+compress_device_locked(cryogpu_ctx *ctx, cudaStream_t st, size_t n, int method, int level_or_accel,
+                       const uint8_t *d_src, uint64_t src_stride, uint32_t block_size,
+                       uint8_t *d_dst, uint64_t dst_stride, uint32_t dst_cap,
+                       uint32_t *d_dst_size, int32_t *d_status)
+{
+    const size_t per = method == CRYOGPU_LZ4 ? lz4e_scratch_bytes(block_size) : zstde_scratch_bytes(block_size);
+    const size_t zgrid = std::min<size_t>(n, (size_t) ctx->sm_count);
+    int          rc = dev_reserve(ctx->scratch, (method == CRYOGPU_LZ4 ? n : zgrid) * per);
+
+    if (rc != CRYOGPU_OK)
+        return rc;
+    if (method == CRYOGPU_LZ4)
+        k_lz4_encode<<<(unsigned) n, LZ4E_THREADS, LZ4E_SMEM, st>>>(
+            d_src, src_stride, block_size, d_dst, dst_stride, dst_cap, level_or_accel, d_dst_size,
+            d_status, (uint8_t *) ctx->scratch.p, per);
+    else
+        k_zstd_encode<<<(unsigned) zgrid, ZSTDE_THREADS, ZSTDE_SMEM, st>>>(
+            d_src, src_stride, block_size, d_dst, dst_stride, dst_cap, level_or_accel, d_dst_size,
+            d_status, (uint8_t *) ctx->scratch.p, per, (uint32_t) n);
+    CU(cudaGetLastError());
     return CRYOGPU_OK;
 }
 
@@ -1303,27 +1431,405 @@ cryogpu_compress_device(cryogpu_ctx *ctx, size_t n, int method, int level_or_acc
     cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
 
     CU(cudaSetDevice(ctx->device));
-    size_t per = method == CRYOGPU_LZ4 ? lz4e_scratch_bytes(block_size) : zstde_scratch_bytes(block_size);
-    const size_t zgrid = std::min<size_t>(n, (size_t) ctx->sm_count);
-    std::lock_guard<std::mutex> g(ctx->mu);
+    std::lock_guard<std::recursive_mutex> g(ctx->mu);
 
     CU(cudaStreamWaitEvent(st, ctx->busy, 0));      /* the scratch area is the context's: see cryogpu_decompress_device */
-    {
-        int rc = dev_reserve(ctx->scratch, (method == CRYOGPU_LZ4 ? n : zgrid) * per);
+    int rc = compress_device_locked(ctx, st, n, method, level_or_accel, d_src, src_stride, block_size, d_dst, dst_stride,
+                                    dst_cap, d_dst_size, d_status);
 
-        if (rc != CRYOGPU_OK)
-            return rc;
-    }
-    if (method == CRYOGPU_LZ4)
-        k_lz4_encode<<<(unsigned) n, LZ4E_THREADS, LZ4E_SMEM, st>>>(
-            d_src, src_stride, block_size, d_dst, dst_stride, dst_cap, level_or_accel, d_dst_size,
-            d_status, (uint8_t *) ctx->scratch.p, per);
-    else
-        k_zstd_encode<<<(unsigned) zgrid, ZSTDE_THREADS, ZSTDE_SMEM, st>>>(
-            d_src, src_stride, block_size, d_dst, dst_stride, dst_cap, level_or_accel, d_dst_size,
-            d_status, (uint8_t *) ctx->scratch.p, per, (uint32_t) n);
+    if (rc != CRYOGPU_OK)
+        return rc;
+    CU(cudaEventRecord(ctx->busy, st));
+    return CRYOGPU_OK;
+}
+
+/* ------------------------------------------------------------ page chains */
+
+extern "C" uint32_t
+cryogpu_pages_needed(uint64_t compressed_size)
+{
+    return pg_pages_needed(compressed_size);
+}
+
+extern "C" int
+cryogpu_decompress_pages_device(cryogpu_ctx *ctx, size_t n, const uint8_t *d_pages, const uint32_t *d_page_slot,
+                                const uint32_t *d_page_blkno, const uint32_t *d_chain_off, size_t total_entries,
+                                uint8_t *d_dst, uint64_t dst_stride, uint32_t block_size, uint32_t *d_out_size,
+                                int32_t *d_status, int32_t *d_methods, uint32_t *d_comp_size, void *stream)
+{
+    if (ctx && n == 0)
+        return CRYOGPU_OK;
+    int rc = check_decompress_args(ctx, n, d_dst, dst_stride, block_size);
+
+    if (rc != CRYOGPU_OK)
+        return rc;
+    if (!d_pages || !d_page_slot || !d_page_blkno || !d_chain_off || !d_dst || !d_out_size || !d_status || !d_methods)
+        return fail(CRYOGPU_E_ARG, "NULL device pointer");
+    if (((uintptr_t) d_pages & 15) || total_entries == 0 || total_entries > 0x7fffffffu)
+        return fail(CRYOGPU_E_ARG, "d_pages must be 16-byte aligned, total_entries in range");
+    cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
+
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::recursive_mutex> g(ctx->mu);
+
+    CU(cudaStreamWaitEvent(st, ctx->busy, 0));
+    /* work area: the gathered streams (one page of room per chain entry), then per block: offset, size, the
+     * method for the decoders, the outcome of the gather */
+    const size_t comp_bytes = total_entries * (size_t) PG_PAGE, na = (n * 8 + 255) & ~(size_t) 255;
+
+    rc = dev_reserve(ctx->pgw, comp_bytes + 4 * na);
+    if (rc != CRYOGPU_OK)
+        return rc;
+    uint8_t  *comp = (uint8_t *) ctx->pgw.p;
+    uint64_t *src_off = (uint64_t *) (comp + comp_bytes);
+    uint32_t *src_size = (uint32_t *) (comp + comp_bytes + na);
+    int32_t  *dec_method = (int32_t *) (comp + comp_bytes + 2 * na);
+    int32_t  *chain_status = (int32_t *) (comp + comp_bytes + 3 * na);
+    /* the largest stream either library writes for a block of this size */
+    const uint32_t max_csize = (uint32_t) std::max(cryogpu_compress_bound(CRYOGPU_LZ4, block_size),
+                                                   cryogpu_compress_bound(CRYOGPU_ZSTD, block_size));
+
+    k_pages_gather<<<(unsigned) n, 256, 0, st>>>(d_pages, d_page_slot, d_page_blkno, d_chain_off, comp, src_off, src_size,
+                                                 dec_method, d_methods, chain_status, max_csize);
+    rc = decompress_device_locked(ctx, st, n, dec_method, comp, src_off, src_size, d_dst, dst_stride, block_size,
+                                  d_out_size, d_status);
+    if (rc != CRYOGPU_OK)
+        return rc;
+    k_pages_status<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(chain_status, src_size, d_status, d_out_size, d_comp_size,
+                                                                  (uint32_t) n);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ctx->busy, st));
+    return CRYOGPU_OK;
+}
+
+extern "C" int
+cryogpu_compress_pages_device(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel, const uint8_t *d_src,
+                              uint64_t src_stride, uint32_t block_size, const uint32_t *d_page_blkno, uint32_t cap_pages,
+                              uint32_t created_xid, uint8_t *d_pages, uint32_t *d_npages, uint32_t *d_comp_size,
+                              int32_t *d_status, void *stream)
+{
+    if (!ctx)
+        return fail(CRYOGPU_E_ARG, "ctx is NULL");
+    if (method != CRYOGPU_LZ4 && method != CRYOGPU_ZSTD)
+        return fail(CRYOGPU_E_METHOD, "unknown compression method %d", method);
+    if (n == 0)
+        return CRYOGPU_OK;
+    if (!d_src || !d_page_blkno || !d_pages || !d_npages || !d_comp_size || !d_status)
+        return fail(CRYOGPU_E_ARG, "NULL device pointer");
+    if (((uintptr_t) d_src & 15) || (src_stride & 15) || ((uintptr_t) d_pages & 15))
+        return fail(CRYOGPU_E_ARG, "device pointers and strides must be multiples of 16");
+    if (block_size == 0 || block_size > (1u << 27) || src_stride < block_size || n > 0x7fffffffu)
+        return fail(CRYOGPU_E_ARG, "size out of range");
+    const uint64_t bound = cryogpu_compress_bound(method, block_size);
+
+    if (cap_pages < pg_pages_needed(bound) || cap_pages > 0xFFFFu)
+        return fail(CRYOGPU_E_ARG, "cap_pages %u below cryogpu_pages_needed(cryogpu_compress_bound)", cap_pages);
+    cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
+
+    CU(cudaSetDevice(ctx->device));
+    std::lock_guard<std::recursive_mutex> g(ctx->mu);
+
+    CU(cudaStreamWaitEvent(st, ctx->busy, 0));
+    const uint64_t cstride = (bound + 15) & ~(uint64_t) 15;
+    const size_t   na = (n * 4 + 255) & ~(size_t) 255;
+    int            rc = dev_reserve(ctx->pgw, n * cstride + na);
+
+    if (rc != CRYOGPU_OK)
+        return rc;
+    uint8_t *comp = (uint8_t *) ctx->pgw.p;
+    int32_t *cst = (int32_t *) (comp + n * cstride);
+
+    rc = compress_device_locked(ctx, st, n, method, level_or_accel, d_src, src_stride, block_size, comp, cstride,
+                                (uint32_t) cstride, d_comp_size, cst);
+    if (rc != CRYOGPU_OK)
+        return rc;
+    k_pages_split<<<(unsigned) n, 256, 0, st>>>(comp, cstride, d_comp_size, cst, (uint32_t) method, created_xid, d_page_blkno,
+                                                cap_pages, d_pages, (uint64_t) cap_pages * PG_PAGE, d_npages, d_status);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ctx->busy, st));
+    return CRYOGPU_OK;
+}
+
+/*
+ * Host-pointer variants: the pages as they lie in the buffer pool (one pointer per page), staged through
+ * pinned memory in chunks, the device calls above, results back.  Sized for the cache-fill and flush calls
+ * (tens of blocks), not pipelined like cryogpu_decompress_host.
+ */
+#define PG_HOST_CHUNK 32u
+
+extern "C" int
+cryogpu_decompress_pages_host(cryogpu_ctx *ctx, size_t n, const void *const *pages, const uint32_t *page_blkno,
+                              const uint32_t *chain_off, void *const *dst, uint32_t block_size, uint32_t *out_size,
+                              int32_t *status, int32_t *methods, uint32_t *comp_size)
+{
+    if (!ctx)
+        return fail(CRYOGPU_E_ARG, "ctx is NULL");
+    if (n == 0)
+        return CRYOGPU_OK;
+    if (!pages || !page_blkno || !chain_off || !dst || !out_size || !status || !methods)
+        return fail(CRYOGPU_E_ARG, "NULL argument");
+    if (block_size == 0 || block_size > (1u << 27))
+        return fail(CRYOGPU_E_ARG, "block_size out of range");
+    const uint64_t stride = ((uint64_t) block_size + 15) & ~(uint64_t) 15;
+    uint64_t       h2d = 0, d2h = 0;
+    std::lock_guard<std::recursive_mutex> hold(ctx->mu);     /* the staging areas are the context's */
+
+    CU(cudaSetDevice(ctx->device));
+    for (size_t lo = 0; lo < n; lo += PG_HOST_CHUNK)
+    {
+        const size_t   cnt = std::min<size_t>(PG_HOST_CHUNK, n - lo);
+        const uint32_t e0 = chain_off[lo], e1 = chain_off[lo + cnt], ne = e1 - e0;
+
+        if (e1 < e0)
+            return fail(CRYOGPU_E_ARG, "chain_off must not decrease");
+        if (ne == 0)
+        {
+            for (size_t i = 0; i < cnt; i++)
+            {
+                status[lo + i] = CRYOGPU_ST_EMPTY_BLOCK;
+                out_size[lo + i] = 0;
+                methods[lo + i] = 0;
+                if (comp_size)
+                    comp_size[lo + i] = 0;
+            }
+            continue;
+        }
+        /* layout of the staging areas: pages | slot | blkno | chain_off (cnt + 1) ; results: out_size | status | methods | comp_size */
+        const size_t pg_bytes = (size_t) ne * PG_PAGE, meta_in = ((size_t) ne * 8 + (cnt + 1) * 4 + 255) & ~(size_t) 255;
+        const size_t meta_out = (cnt * 16 + 255) & ~(size_t) 255;
+        int          rc;
+
+        if ((rc = host_reserve(ctx->h_in[0], pg_bytes + meta_in)) != CRYOGPU_OK ||
+            (rc = dev_reserve(ctx->d_in[0], pg_bytes + meta_in)) != CRYOGPU_OK ||
+            (rc = host_reserve(ctx->h_out[0], cnt * stride + meta_out)) != CRYOGPU_OK ||
+            (rc = dev_reserve(ctx->d_out[0], cnt * stride + meta_out)) != CRYOGPU_OK)
+            return rc;
+        uint8_t  *hi = (uint8_t *) ctx->h_in[0].p, *di = (uint8_t *) ctx->d_in[0].p;
+        uint8_t  *ho = (uint8_t *) ctx->h_out[0].p, *dout = (uint8_t *) ctx->d_out[0].p;
+        uint32_t *h_slot = (uint32_t *) (hi + pg_bytes), *h_blk = h_slot + ne, *h_coff = h_blk + ne;
+
+        for (uint32_t e = 0; e < ne; e++)
+        {
+            memcpy(hi + (size_t) e * PG_PAGE, pages[e0 + e], PG_PAGE);
+            h_slot[e] = e;
+            h_blk[e] = page_blkno[e0 + e];
+        }
+        for (size_t i = 0; i <= cnt; i++)
+            h_coff[i] = chain_off[lo + i] - e0;
+        CU(cudaMemcpyAsync(di, hi, pg_bytes + meta_in, cudaMemcpyHostToDevice, ctx->stream));
+        h2d += pg_bytes + meta_in;
+        uint8_t *dm = dout + cnt * stride;
+
+        rc = cryogpu_decompress_pages_device(ctx, cnt, di, (uint32_t *) (di + pg_bytes), (uint32_t *) (di + pg_bytes) + ne,
+                                             (uint32_t *) (di + pg_bytes) + 2 * (size_t) ne, ne, dout, stride, block_size,
+                                             (uint32_t *) dm, (int32_t *) (dm + cnt * 4), (int32_t *) (dm + cnt * 8),
+                                             (uint32_t *) (dm + cnt * 12), ctx->stream);
+        if (rc != CRYOGPU_OK)
+            return rc;
+        CU(cudaMemcpyAsync(ho, dout, cnt * stride + meta_out, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        d2h += cnt * stride + meta_out;
+        const uint8_t *hm = ho + cnt * stride;
+
+        memcpy(out_size + lo, hm, cnt * 4);
+        memcpy(status + lo, hm + cnt * 4, cnt * 4);
+        memcpy(methods + lo, hm + cnt * 8, cnt * 4);
+        if (comp_size)
+            memcpy(comp_size + lo, hm + cnt * 12, cnt * 4);
+        for (size_t i = 0; i < cnt; i++)
+            if (status[lo + i] == CRYOGPU_ST_OK)
+                memcpy(dst[lo + i], ho + i * stride, out_size[lo + i]);
+    }
+    ctx->last_h2d = h2d;
+    ctx->last_d2h = d2h;
+    return CRYOGPU_OK;
+}
+
+extern "C" int
+cryogpu_compress_pages_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel, const void *const *src,
+                            uint32_t block_size, const uint32_t *page_blkno, uint32_t cap_pages, uint32_t created_xid,
+                            void *const *pages_out, uint32_t *npages, uint32_t *comp_size, int32_t *status)
+{
+    if (!ctx)
+        return fail(CRYOGPU_E_ARG, "ctx is NULL");
+    if (method != CRYOGPU_LZ4 && method != CRYOGPU_ZSTD)
+        return fail(CRYOGPU_E_METHOD, "unknown compression method %d", method);
+    if (n == 0)
+        return CRYOGPU_OK;
+    if (!src || !page_blkno || !pages_out || !npages || !comp_size || !status)
+        return fail(CRYOGPU_E_ARG, "NULL argument");
+    if (block_size == 0 || block_size > (1u << 27))
+        return fail(CRYOGPU_E_ARG, "block_size out of range");
+    const uint64_t stride = ((uint64_t) block_size + 15) & ~(uint64_t) 15;
+    const size_t   pstride = (size_t) cap_pages * PG_PAGE;
+    uint64_t       h2d = 0, d2h = 0;
+    std::lock_guard<std::recursive_mutex> hold(ctx->mu);     /* the staging areas are the context's */
+
+    CU(cudaSetDevice(ctx->device));
+    for (size_t lo = 0; lo < n; lo += PG_HOST_CHUNK)
+    {
+        const size_t cnt = std::min<size_t>(PG_HOST_CHUNK, n - lo);
+        const size_t meta_in = (cnt * cap_pages * 4 + 255) & ~(size_t) 255, meta_out = (cnt * 12 + 255) & ~(size_t) 255;
+        int          rc;
+
+        if ((rc = host_reserve(ctx->h_in[0], cnt * stride + meta_in)) != CRYOGPU_OK ||
+            (rc = dev_reserve(ctx->d_in[0], cnt * stride + meta_in)) != CRYOGPU_OK ||
+            (rc = host_reserve(ctx->h_out[0], cnt * pstride + meta_out)) != CRYOGPU_OK ||
+            (rc = dev_reserve(ctx->d_out[0], cnt * pstride + meta_out)) != CRYOGPU_OK)
+            return rc;
+        uint8_t *hi = (uint8_t *) ctx->h_in[0].p, *di = (uint8_t *) ctx->d_in[0].p;
+        uint8_t *ho = (uint8_t *) ctx->h_out[0].p, *dout = (uint8_t *) ctx->d_out[0].p;
+
+        for (size_t i = 0; i < cnt; i++)
+            memcpy(hi + i * stride, src[lo + i], block_size);
+        memcpy(hi + cnt * stride, page_blkno + lo * cap_pages, cnt * cap_pages * 4);
+        CU(cudaMemcpyAsync(di, hi, cnt * stride + meta_in, cudaMemcpyHostToDevice, ctx->stream));
+        h2d += cnt * stride + meta_in;
+        uint8_t *dm = dout + cnt * pstride;
+
+        rc = cryogpu_compress_pages_device(ctx, cnt, method, level_or_accel, di, stride, block_size,
+                                           (uint32_t *) (di + cnt * stride), cap_pages, created_xid, dout, (uint32_t *) dm,
+                                           (uint32_t *) (dm + cnt * 4), (int32_t *) (dm + cnt * 8), ctx->stream);
+        if (rc != CRYOGPU_OK)
+            return rc;
+        /* the counts first: only the pages each block needs come back */
+        CU(cudaMemcpyAsync(ho + cnt * pstride, dm, meta_out, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        const uint8_t *hm = ho + cnt * pstride;
+
+        memcpy(npages + lo, hm, cnt * 4);
+        memcpy(comp_size + lo, hm + cnt * 4, cnt * 4);
+        memcpy(status + lo, hm + cnt * 8, cnt * 4);
+        d2h += meta_out;
+        for (size_t i = 0; i < cnt; i++)
+            if (status[lo + i] == CRYOGPU_ST_OK)
+            {
+                CU(cudaMemcpyAsync(ho + i * pstride, dout + i * pstride, (size_t) npages[lo + i] * PG_PAGE,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+                d2h += (size_t) npages[lo + i] * PG_PAGE;
+            }
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (size_t i = 0; i < cnt; i++)
+            if (status[lo + i] == CRYOGPU_ST_OK)
+                for (uint32_t k = 0; k < npages[lo + i]; k++)
+                    memcpy(pages_out[(lo + i) * cap_pages + k], ho + i * pstride + (size_t) k * PG_PAGE, PG_PAGE);
+    }
+    ctx->last_h2d = h2d;
+    ctx->last_d2h = d2h;
+    return CRYOGPU_OK;
+}
+
+/* ----------------------------------------------------- tuple-level work (f-4) */
+
+extern "C" int
+cryogpu_tuple_stats_device(cryogpu_ctx *ctx, size_t n, const uint8_t *d_blocks, uint64_t stride, uint32_t block_size,
+                           const int32_t *d_status, uint32_t *d_ntuples, uint64_t *d_tuple_bytes, int32_t *d_valid,
+                           void *stream)
+{
+    if (!ctx)
+        return fail(CRYOGPU_E_ARG, "ctx is NULL");
+    if (n == 0)
+        return CRYOGPU_OK;
+    if (!d_blocks || !d_ntuples || !d_tuple_bytes || !d_valid)
+        return fail(CRYOGPU_E_ARG, "NULL device pointer");
+    if (((uintptr_t) d_blocks & 7) || (stride & 7) || block_size < 16 || stride < block_size || n > 0x7fffffffu)
+        return fail(CRYOGPU_E_ARG, "blocks must be 8-byte aligned, block_size >= 16, stride >= block_size");
+    cudaStream_t st = stream ? (cudaStream_t) stream : ctx->stream;
+
+    CU(cudaSetDevice(ctx->device));
+    k_tuple_stats<<<(unsigned) ((n + 7) / 8), 256, 0, st>>>(d_blocks, stride, block_size, d_status, d_ntuples,
+                                                            (unsigned long long *) d_tuple_bytes, d_valid, (uint32_t) n);
+    CU(cudaGetLastError());
+    return CRYOGPU_OK;
+}
+
+/*
+ * Count pushdown for the host-pointer caller: compressed blocks in, per block the number of tuples, their
+ * bytes and the decode status out; the decoded blocks never leave HBM.
+ */
+extern "C" int
+cryogpu_decompress_count_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods, const void *const *src,
+                              const uint32_t *src_size, uint32_t block_size, uint32_t *ntuples, uint64_t *tuple_bytes,
+                              int32_t *status)
+{
+    if (!ctx)
+        return fail(CRYOGPU_E_ARG, "ctx is NULL");
+    if (n == 0)
+        return CRYOGPU_OK;
+    if (!methods || !src || !src_size || !ntuples || !tuple_bytes || !status)
+        return fail(CRYOGPU_E_ARG, "NULL argument");
+    if (block_size < 16 || block_size > (1u << 27))
+        return fail(CRYOGPU_E_ARG, "block_size out of range");
+    const uint64_t stride = ((uint64_t) block_size + 15) & ~(uint64_t) 15;
+    const size_t   chunk = 512;
+    uint64_t       h2d = 0, d2h = 0;
+    std::lock_guard<std::recursive_mutex> hold(ctx->mu);
+
+    CU(cudaSetDevice(ctx->device));
+    for (size_t lo = 0; lo < n; lo += chunk)
+    {
+        const size_t cnt = std::min(chunk, n - lo);
+        size_t       in_bytes = 0;
+
+        for (size_t i = 0; i < cnt; i++)
+            in_bytes += ((size_t) src_size[lo + i] + 15) & ~(size_t) 15;
+        /* staging in: streams | offsets u64 | sizes u32 | methods i32 ; out: ntuples u32 | status i32 | valid i32 | bytes u64 */
+        const size_t in_al = (in_bytes + 255) & ~(size_t) 255, meta_in = cnt * 16, meta_out = cnt * 24;
+        int          rc;
+
+        if ((rc = host_reserve(ctx->h_in[0], in_al + meta_in + 16)) != CRYOGPU_OK ||
+            (rc = dev_reserve(ctx->d_in[0], in_al + meta_in + 16)) != CRYOGPU_OK ||
+            (rc = host_reserve(ctx->h_out[0], meta_out)) != CRYOGPU_OK ||
+            (rc = dev_reserve(ctx->d_out[0], cnt * stride + meta_out)) != CRYOGPU_OK)
+            return rc;
+        uint8_t  *hi = (uint8_t *) ctx->h_in[0].p, *di = (uint8_t *) ctx->d_in[0].p, *dout = (uint8_t *) ctx->d_out[0].p;
+        uint64_t *h_off = (uint64_t *) (hi + in_al);
+        uint32_t *h_sz = (uint32_t *) (hi + in_al + cnt * 8);
+        int32_t  *h_me = (int32_t *) (hi + in_al + cnt * 12);
+        size_t    at = 0;
+
+        for (size_t i = 0; i < cnt; i++)
+        {
+            memcpy(hi + at, src[lo + i], src_size[lo + i]);
+            h_off[i] = at;
+            h_sz[i] = src_size[lo + i];
+            h_me[i] = methods[lo + i];
+            at += ((size_t) src_size[lo + i] + 15) & ~(size_t) 15;
+        }
+        CU(cudaMemcpyAsync(di, hi, in_al + meta_in, cudaMemcpyHostToDevice, ctx->stream));
+        h2d += in_al + meta_in;
+        uint8_t  *dm = dout + cnt * stride;
+        uint32_t *d_nt = (uint32_t *) dm;
+        int32_t  *d_st = (int32_t *) (dm + cnt * 4), *d_ok = (int32_t *) (dm + cnt * 8);
+        uint64_t *d_by = (uint64_t *) (dm + cnt * 16);          /* cnt * 12 rounded up to 8-byte alignment: cnt * 16 */
+        uint32_t *d_osz = (uint32_t *) (dm + cnt * 12);
+
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->busy, 0));
+        rc = decompress_device_locked(ctx, ctx->stream, cnt, (int32_t *) (di + in_al + cnt * 12), di, (uint64_t *) (di + in_al),
+                                      (uint32_t *) (di + in_al + cnt * 8), dout, stride, block_size, d_osz, d_st);
+        if (rc != CRYOGPU_OK)
+            return rc;
+        k_tuple_stats<<<(unsigned) ((cnt + 7) / 8), 256, 0, ctx->stream>>>(dout, stride, block_size, d_st, d_nt,
+                                                                          (unsigned long long *) d_by, d_ok, (uint32_t) cnt);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->busy, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_out[0].p, dm, meta_out, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        d2h += meta_out;
+        const uint8_t *hm = (const uint8_t *) ctx->h_out[0].p;
+
+        memcpy(ntuples + lo, hm, cnt * 4);
+        memcpy(status + lo, hm + cnt * 4, cnt * 4);
+        memcpy(tuple_bytes + lo, hm + cnt * 16, cnt * 8);
+        /* a decoded block whose item ids point outside it is reported as malformed */
+        const int32_t *h_ok = (const int32_t *) (hm + cnt * 8);
+
+        for (size_t i = 0; i < cnt; i++)
+            if (status[lo + i] == CRYOGPU_ST_OK && !h_ok[i])
+                status[lo + i] = CRYOGPU_ST_FORMAT;
+    }
+    ctx->last_h2d = h2d;
+    ctx->last_d2h = d2h;
     return CRYOGPU_OK;
 }
 
@@ -1445,7 +1951,7 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
         return fail(CRYOGPU_E_ARG, "NULL argument");
     if (block_size == 0 || block_size > (1u << 27))
         return fail(CRYOGPU_E_ARG, "block_size out of range");
-    std::lock_guard<std::mutex> g(ctx->mu);
+    std::lock_guard<std::recursive_mutex> g(ctx->mu);
 
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventSynchronize(ctx->busy));        /* a device-resident call may still be using the work areas */
@@ -1665,7 +2171,7 @@ cryogpu_compress_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel
     if (dst_cap < bound)
         return fail(CRYOGPU_E_ARG, "dst_cap %u below cryogpu_compress_bound %llu", dst_cap,
                     (unsigned long long) bound);
-    std::lock_guard<std::mutex> g(ctx->mu);
+    std::lock_guard<std::recursive_mutex> g(ctx->mu);
 
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventSynchronize(ctx->busy));
