@@ -235,6 +235,21 @@ int cryogpu_compress_pages_host(cryogpu_ctx *ctx, size_t n, int method, int leve
                                 int32_t *status);
 
 /*
+ * The flush of a batch of blocks as cryo_preserve does it (pg_cryogen.c:726-805), for blocks whose first
+ * page number was reserved when the block was started (cryo_reserve_blockno, pg_cryogen.c:588-601):
+ * compress all blocks, then call alloc(arg) once for every further page a block needs -- block by block,
+ * page by page, the order of the reference's ReadBuffer(P_NEW) calls -- then cut the page images on the
+ * device and copy each to page_ptr(arg, blkno) (BufferGetPage of that block).
+ */
+typedef uint32_t (*cryogpu_alloc_page_fn)(void *arg);
+typedef void *(*cryogpu_page_ptr_fn)(void *arg, uint32_t blkno);
+int cryogpu_compress_pages_alloc_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel,
+                                      const void *const *src, uint32_t block_size,
+                                      const uint32_t *first_blkno, cryogpu_alloc_page_fn alloc,
+                                      cryogpu_page_ptr_fn page_ptr, void *arg, uint32_t created_xid,
+                                      uint32_t *npages, uint32_t *comp_size, int32_t *status);
+
+/*
  * ------------------------------------------------------------ tuple-level work
  *
  * The item walk of a sequential scan (cryo_getnextslot, pg_cryogen.c:293-307, over cryo_storage_fetch,

@@ -36,7 +36,7 @@
 
 /* cache.c error codes (cache.h) */
 #define CRYO_ERR_SUCCESS                0
-#define CRYO_ERR_WRONG_STARTING_BLOCK   1
+#define CRYO_ERR_WRONG_STARTING_BLOCK   2
 #define CRYO_ERR_EMPTY_BLOCK            3
 
 static void put16(uint8_t *p, uint32_t v) { p[0] = (uint8_t) v; p[1] = (uint8_t) (v >> 8); }

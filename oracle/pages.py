@@ -9,7 +9,7 @@ import numpy as np
 from . import port
 
 PAGE = 8192
-ERR_SUCCESS, ERR_WRONG_STARTING_BLOCK, ERR_EMPTY_BLOCK = 0, 1, 3
+ERR_SUCCESS, ERR_WRONG_STARTING_BLOCK, ERR_EMPTY_BLOCK = 0, 2, 3
 
 
 def _lib():

@@ -1719,6 +1719,116 @@ cryogpu_compress_pages_host(cryogpu_ctx *ctx, size_t n, int method, int level_or
     return CRYOGPU_OK;
 }
 
+/*
+ * Flush path of a batch of blocks (f-3): compress, THEN ask the caller for the block numbers -- how many
+ * pages a block needs is only known after compression, and cryo_preserve (pg_cryogen.c:737-759) allocates
+ * them then too: the first page was reserved when the block was started (cryo_reserve_blockno,
+ * pg_cryogen.c:588-601), the others come from ReadBuffer(P_NEW) -- then cut the page images on the device
+ * and place them where the caller says each page lives.
+ */
+extern "C" int
+cryogpu_compress_pages_alloc_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel, const void *const *src,
+                                  uint32_t block_size, const uint32_t *first_blkno, cryogpu_alloc_page_fn alloc,
+                                  cryogpu_page_ptr_fn page_ptr, void *arg, uint32_t created_xid, uint32_t *npages,
+                                  uint32_t *comp_size, int32_t *status)
+{
+    if (!ctx)
+        return fail(CRYOGPU_E_ARG, "ctx is NULL");
+    if (method != CRYOGPU_LZ4 && method != CRYOGPU_ZSTD)
+        return fail(CRYOGPU_E_METHOD, "unknown compression method %d", method);
+    if (n == 0)
+        return CRYOGPU_OK;
+    if (!src || !first_blkno || !alloc || !page_ptr || !npages || !comp_size || !status)
+        return fail(CRYOGPU_E_ARG, "NULL argument");
+    if (block_size == 0 || block_size > (1u << 27))
+        return fail(CRYOGPU_E_ARG, "block_size out of range");
+    const uint64_t stride = ((uint64_t) block_size + 15) & ~(uint64_t) 15;
+    const uint64_t bound = cryogpu_compress_bound(method, block_size), cstride = (bound + 15) & ~(uint64_t) 15;
+    const uint32_t cap_pages = pg_pages_needed(bound);
+    const size_t   pstride = (size_t) cap_pages * PG_PAGE;
+    uint64_t       h2d = 0, d2h = 0;
+    std::lock_guard<std::recursive_mutex> hold(ctx->mu);
+
+    CU(cudaSetDevice(ctx->device));
+    for (size_t lo = 0; lo < n; lo += PG_HOST_CHUNK)
+    {
+        const size_t cnt = std::min<size_t>(PG_HOST_CHUNK, n - lo);
+        const size_t blk_bytes = (cnt * cap_pages * 4 + 255) & ~(size_t) 255, meta = (cnt * 12 + 255) & ~(size_t) 255;
+        int          rc;
+
+        if ((rc = host_reserve(ctx->h_in[0], cnt * stride + blk_bytes)) != CRYOGPU_OK ||
+            (rc = dev_reserve(ctx->d_in[0], cnt * stride + blk_bytes)) != CRYOGPU_OK ||
+            (rc = host_reserve(ctx->h_out[0], cnt * pstride + meta)) != CRYOGPU_OK ||
+            (rc = dev_reserve(ctx->d_out[0], cnt * pstride + meta)) != CRYOGPU_OK ||
+            (rc = dev_reserve(ctx->pgw, cnt * cstride + meta)) != CRYOGPU_OK)
+            return rc;
+        uint8_t  *hi = (uint8_t *) ctx->h_in[0].p, *di = (uint8_t *) ctx->d_in[0].p;
+        uint8_t  *ho = (uint8_t *) ctx->h_out[0].p, *dout = (uint8_t *) ctx->d_out[0].p;
+        uint8_t  *comp = (uint8_t *) ctx->pgw.p, *dm = dout + cnt * pstride;
+        uint32_t *d_np = (uint32_t *) dm, *d_cs = (uint32_t *) (dm + cnt * 4);
+        int32_t  *d_st = (int32_t *) (dm + cnt * 8), *d_cst = (int32_t *) (comp + cnt * cstride);
+        uint32_t *h_blk = (uint32_t *) (hi + cnt * stride);
+        const uint8_t *hm = ho + cnt * pstride;
+
+        for (size_t i = 0; i < cnt; i++)
+            memcpy(hi + i * stride, src[lo + i], block_size);
+        CU(cudaMemcpyAsync(di, hi, cnt * stride, cudaMemcpyHostToDevice, ctx->stream));
+        h2d += cnt * stride;
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->busy, 0));
+        rc = compress_device_locked(ctx, ctx->stream, cnt, method, level_or_accel, di, stride, block_size, comp, cstride,
+                                    (uint32_t) cstride, d_cs, d_cst);
+        if (rc != CRYOGPU_OK)
+            return rc;
+        CU(cudaMemcpyAsync(ho + cnt * pstride + cnt * 4, d_cs, cnt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        d2h += cnt * 4;
+        /* the block numbers, in the order cryo_preserve takes them: block by block, page by page */
+        const uint32_t *h_cs = (const uint32_t *) (hm + cnt * 4);
+
+        for (size_t i = 0; i < cnt; i++)
+        {
+            const uint32_t np = pg_pages_needed(h_cs[i]);
+
+            h_blk[i * cap_pages] = first_blkno[lo + i];
+            for (uint32_t k = 1; k < cap_pages; k++)
+                h_blk[i * cap_pages + k] = k < np ? alloc(arg) : PG_INVALID;
+        }
+        CU(cudaMemcpyAsync(di + cnt * stride, h_blk, cnt * cap_pages * 4, cudaMemcpyHostToDevice, ctx->stream));
+        h2d += cnt * cap_pages * 4;
+        k_pages_split<<<(unsigned) cnt, 256, 0, ctx->stream>>>(comp, cstride, d_cs, d_cst, (uint32_t) method, created_xid,
+                                                              (uint32_t *) (di + cnt * stride), cap_pages, dout, pstride, d_np,
+                                                              d_st);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(ctx->busy, ctx->stream));
+        CU(cudaMemcpyAsync(ho + cnt * pstride, dm, meta, cudaMemcpyDeviceToHost, ctx->stream));
+        for (size_t i = 0; i < cnt; i++)
+        {
+            const uint32_t np = pg_pages_needed(h_cs[i]);
+
+            CU(cudaMemcpyAsync(ho + i * pstride, dout + i * pstride, (size_t) np * PG_PAGE, cudaMemcpyDeviceToHost, ctx->stream));
+            d2h += (size_t) np * PG_PAGE;
+        }
+        CU(cudaStreamSynchronize(ctx->stream));
+        d2h += meta;
+        memcpy(npages + lo, hm, cnt * 4);
+        memcpy(comp_size + lo, hm + cnt * 4, cnt * 4);
+        memcpy(status + lo, hm + cnt * 8, cnt * 4);
+        for (size_t i = 0; i < cnt; i++)
+            if (status[lo + i] == CRYOGPU_ST_OK)
+                for (uint32_t k = 0; k < npages[lo + i]; k++)
+                {
+                    void *p = page_ptr(arg, h_blk[i * cap_pages + k]);
+
+                    if (!p)
+                        return fail(CRYOGPU_E_ARG, "page_ptr returned NULL for block %u", h_blk[i * cap_pages + k]);
+                    memcpy(p, ho + i * pstride + (size_t) k * PG_PAGE, PG_PAGE);
+                }
+    }
+    ctx->last_h2d = h2d;
+    ctx->last_d2h = d2h;
+    return CRYOGPU_OK;
+}
+
 /* ----------------------------------------------------- tuple-level work (f-4) */
 
 extern "C" int

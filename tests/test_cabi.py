@@ -86,3 +86,25 @@ def test_host_shim_compiles_against_the_reference_headers(tmp_path):
          "-include", os.path.join(ref, "storage.h"),
          os.path.join(ROOT, "pg_cryogen_b200", "host", "compression.c"),
          "-o", str(tmp_path / "compat.o")])
+
+
+def test_batch_harness_library_loads_and_exports():
+    """pg_cryogen_b200/libcryo_batch.so (cryo_batch.h: the batched callers) loads on a box
+    without a GPU and exports every function its header declares; no compute call is made."""
+    import ctypes as C
+    import os
+    import re
+    here = os.path.dirname(os.path.abspath(__file__))
+    hdr = open(os.path.join(here, "..", "pg_cryogen_b200", "host", "cryo_batch.h")).read()
+    names = set(re.findall(r"\b(cryo_(?:batch|memrel)_[a-z_]+)\(", hdr))
+    assert len(names) >= 20
+    L = C.CDLL(os.path.join(here, "..", "pg_cryogen_b200", "libcryo_batch.so"))
+    for n in names:
+        getattr(L, n)
+    # the in-memory relation needs no device
+    L.cryo_memrel_create.restype = C.c_void_p
+    L.cryo_memrel_create.argtypes = [C.c_uint32]
+    L.cryo_memrel_destroy.argtypes = [C.c_void_p]
+    r = L.cryo_memrel_create(4)
+    assert r
+    L.cryo_memrel_destroy(r)
