@@ -149,6 +149,16 @@ int cryogpu_compress_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_a
                           uint32_t *dst_size, int32_t *status);
 
 /*
+ * The host decompress call returns a sparse block as its non-zero 4 KiB pages and fills the rest of the
+ * caller's block with zeros itself.  on != 0: the caller declares that its destination blocks are PRIVATE
+ * ANONYMOUS memory (malloc, palloc, .bss -- the reference's per-backend cache, cache.c:49, is; shared_buffers
+ * and file mappings are NOT), and the library then returns the whole OS pages of a zero run to the kernel
+ * (madvise MADV_DONTNEED: they read as zeros again, on demand) instead of writing them.  Off by default;
+ * CRYOGPU_ZERO_UNMAP=1 in the environment turns it on for every context.  Ignored for pinned destinations.
+ */
+int cryogpu_set_zero_by_unmap(cryogpu_ctx *ctx, int on);
+
+/*
  * Bytes the last cryogpu_decompress_host call on this context moved over the bus.  The call
  * returns only the 4 KiB pages of a decoded block that hold a non-zero byte and zero-fills the
  * rest of the caller's block on the host (a cryo block of narrow rows is ~98 % zeros,

@@ -47,6 +47,7 @@ _PROTOS = {
     "cryogpu_compress_device": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p,
                                           C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint64,
                                           C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cryogpu_set_zero_by_unmap": (C.c_int, [C.c_void_p, C.c_int]),
     "cryogpu_last_transfer_bytes": (None, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "cryogpu_zstd_pipeline_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "cryogpu_lz4_route_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

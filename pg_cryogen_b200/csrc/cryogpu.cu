@@ -24,6 +24,9 @@
 #define CRYO_HAVE_SSE2 1
 #endif
 
+#include <sys/mman.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -942,6 +945,7 @@ struct cryogpu_ctx
     DevBuf       h_stage[2], h_sp[2];
     HostPool    *pool = nullptr;
     int          sparse = -1;           /* -1 unset, 0 off, 1 on (CRYOGPU_SPARSE_D2H) */
+    int          zero_unmap = -1;       /* -1 unset (CRYOGPU_ZERO_UNMAP, default off), 0 off, 1 on (cryogpu_set_zero_by_unmap) */
     uint64_t     last_h2d = 0, last_d2h = 0;
     size_t       last_zp_n = 0;         /* frames of the last decompress_device call that took the pipeline */
     size_t       last_lz_n = 0;         /* blocks of the last decompress_device call that were routed per block (0: not routed) */
@@ -1954,6 +1958,30 @@ chunk_blocks(uint32_t block_size)
     return c < 1 ? 1 : c;
 }
 
+/*
+ * Chunk of the host decompress call.  A chunk is one batch for the kernels, and a batch of a few hundred
+ * blocks or less is latency-bound (a whole table in 128-block chunks spent 12 of its 16 ms there): a large
+ * call is cut into about four chunks (two lanes, so copies and kernels still overlap) of at most 1 GiB.
+ * CRYOGPU_HOST_CHUNK overrides (blocks).
+ */
+static size_t
+decompress_chunk_blocks(uint32_t block_size, size_t n)
+{
+    static long forced = -1;
+
+    if (forced < 0)
+    {
+        const char *e = getenv("CRYOGPU_HOST_CHUNK");
+
+        forced = e && atol(e) > 0 ? atol(e) : 0;
+    }
+    if (forced)
+        return (size_t) forced;
+    const size_t lo = chunk_blocks(block_size), hi = std::max<size_t>(lo, ((size_t) 1 << 30) / block_size);
+
+    return std::min(hi, std::max(lo, (n + 3) / 4));
+}
+
 static bool
 is_pinned(const void *p)
 {
@@ -1977,6 +2005,27 @@ sparse_enabled(cryogpu_ctx *ctx)
         ctx->sparse = (e && strcmp(e, "0") == 0) ? 0 : 1;
     }
     return ctx->sparse == 1;
+}
+
+static bool
+zero_unmap_enabled(cryogpu_ctx *ctx)
+{
+    if (ctx->zero_unmap < 0)
+    {
+        const char *e = getenv("CRYOGPU_ZERO_UNMAP");
+
+        ctx->zero_unmap = (e && strcmp(e, "1") == 0) ? 1 : 0;
+    }
+    return ctx->zero_unmap == 1;
+}
+
+extern "C" int
+cryogpu_set_zero_by_unmap(cryogpu_ctx *ctx, int on)
+{
+    if (!ctx)
+        return fail(CRYOGPU_E_ARG, "ctx is NULL");
+    ctx->zero_unmap = on ? 1 : 0;
+    return CRYOGPU_OK;
 }
 
 static HostPool *
@@ -2021,8 +2070,38 @@ zero_fill(uint8_t *p, size_t n)
 }
 
 /* place one sparse block: non-zero pages from the packed staging buffer, zeros elsewhere */
+/*
+ * A run of zero bytes in a caller's block.  unmap (cryogpu_set_zero_by_unmap): the caller has said that its
+ * blocks are private anonymous memory (malloc / palloc / .bss: the reference's cache, cache.c:49, is), so the
+ * whole OS pages inside the run are given back to the kernel instead of being written: MADV_DONTNEED makes
+ * them read as zeros again, on demand, and a scan that only follows item ids never touches them.  The
+ * first failure (a locked or special mapping) turns it off for the rest of the call.
+ */
 static void
-place_sparse_block(uint8_t *dst, uint32_t block_size, const uint32_t *bits, const uint8_t *pages)
+zero_range(uint8_t *p, size_t n, std::atomic<int> *unmap)
+{
+    static const size_t os_page = (size_t) sysconf(_SC_PAGESIZE);
+
+    if (unmap && unmap->load(std::memory_order_relaxed) && n >= 16 * os_page)
+    {
+        uint8_t *a = (uint8_t *) (((uintptr_t) p + os_page - 1) & ~(uintptr_t) (os_page - 1));
+        uint8_t *b = (uint8_t *) (((uintptr_t) p + n) & ~(uintptr_t) (os_page - 1));
+
+        if (b > a && madvise(a, (size_t) (b - a), MADV_DONTNEED) == 0)
+        {
+            if (a > p)
+                memset(p, 0, (size_t) (a - p));
+            if (p + n > b)
+                memset(b, 0, (size_t) (p + n - b));
+            return;
+        }
+        unmap->store(0, std::memory_order_relaxed);
+    }
+    zero_fill(p, n);
+}
+
+static void
+place_sparse_block(uint8_t *dst, uint32_t block_size, const uint32_t *bits, const uint8_t *pages, std::atomic<int> *unmap)
 {
     const uint32_t npages = (block_size + SP_PAGE - 1) / SP_PAGE;
     uint32_t       p = 0;
@@ -2043,7 +2122,7 @@ place_sparse_block(uint8_t *dst, uint32_t block_size, const uint32_t *bits, cons
             pages += (size_t) (q - p) * SP_PAGE;
         }
         else
-            zero_fill(dst + lo, hi - lo);
+            zero_range(dst + lo, hi - lo, unmap);
         p = q;
     }
 }
@@ -2065,7 +2144,7 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
 
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventSynchronize(ctx->busy));        /* a device-resident call may still be using the work areas */
-    const size_t   chunk = chunk_blocks(block_size);
+    const size_t   chunk = decompress_chunk_blocks(block_size, n);
     const uint64_t stride = ((uint64_t) block_size + 15) & ~(uint64_t) 15;
     const bool     dst_pinned = is_pinned(dst[0]);
     /* sparse return pays when a batch is worth a second kernel and blocks have whole pages */
@@ -2074,6 +2153,7 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
     cudaStream_t   lanes[2] = {ctx->stream, ctx->stream2};
     size_t         pending_lo[2] = {0, 0}, pending_n[2] = {0, 0};
     uint64_t       h2d = 0, d2h = 0;
+    std::atomic<int> unmap{zero_unmap_enabled(ctx) && !dst_pinned ? 1 : 0};
 
     /* dense return of lane l's chunk, enqueued on its stream */
     auto dense_d2h = [&](int l, size_t lo, size_t cnt) -> int {
@@ -2154,7 +2234,7 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
 
         host_pool(ctx)->run(cnt, [&](size_t i) {
             place_sparse_block((uint8_t *) dst[lo + i], block_size, h_bits + i * SP_WORDS,
-                               pages + (size_t) h_off[i] * SP_PAGE);
+                               pages + (size_t) h_off[i] * SP_PAGE, &unmap);
         });
         return CRYOGPU_OK;
     };
