@@ -27,7 +27,8 @@ class CryoGPUError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libcryogpu.so")
+    """libcryogpu.so beside this file; CRYOGPU_LIB names another build of it (A/B runs of development variants)."""
+    return os.environ.get("CRYOGPU_LIB") or os.path.join(_HERE, "libcryogpu.so")
 
 
 _PROTOS = {

@@ -406,26 +406,31 @@ k_flag_unknown_methods(const int32_t *methods, size_t n, uint32_t *out_size, int
     }
 }
 
+/* persistent: the warps of one CTA per SM take (block, segment) items from a queue (lz4_encode.cuh) */
 __global__ void __launch_bounds__(LZ4E_THREADS)
 k_lz4_encode(const uint8_t *src, uint64_t src_stride, uint32_t block_size, uint8_t *dst,
              uint64_t dst_stride, uint32_t dst_cap, int accel, uint32_t *dst_size,
-             int32_t *status, uint8_t *scratch, uint64_t scratch_stride)
+             int32_t *status, uint8_t *scratch, uint64_t scratch_stride, uint32_t n, uint32_t *queue, uint32_t *done)
 {
-    const uint32_t b = blockIdx.x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    lz4_encode_block(src + b * src_stride, block_size, dst + b * dst_stride, dst_cap, accel,
-                     dst_size + b, status + b, scratch + b * scratch_stride);
+    lz4_encode_worker(src, src_stride, block_size, dst, dst_stride, dst_cap, accel, dst_size, status, scratch,
+                      scratch_stride, n, queue, done,
+                      reinterpret_cast<uint16_t *>(CRYO_SMEM_BASE() + warp * LZ4E_HASH_BYTES), lane);
 }
 
-/* persistent: one CTA per SM walks the batch; scratch is per CTA, not per block */
+/* persistent: the warps of one CTA per SM take (frame, 64 KiB block) items from a queue (zstd_encode.cuh) */
 __global__ void __launch_bounds__(ZSTDE_THREADS)
 k_zstd_encode(const uint8_t *src, uint64_t src_stride, uint32_t block_size, uint8_t *dst,
               uint64_t dst_stride, uint32_t dst_cap, int level, uint32_t *dst_size,
-              int32_t *status, uint8_t *scratch, uint64_t scratch_stride, uint32_t n)
+              int32_t *status, uint8_t *scratch, uint64_t scratch_stride, uint32_t n, uint32_t *queue, uint32_t *done,
+              uint32_t *bmeta)
 {
-    for (uint32_t b = blockIdx.x; b < n; b += gridDim.x)
-        zstd_encode_frame(src + b * src_stride, block_size, dst + b * dst_stride, dst_cap, level,
-                          dst_size + b, status + b, scratch + blockIdx.x * scratch_stride);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    zstd_encode_worker(src, src_stride, block_size, dst, dst_stride, dst_cap, level, dst_size, status,
+                       scratch + blockIdx.x * scratch_stride + (size_t) warp * ZSE_SCR_PER_WARP, n, queue, done, bmeta,
+                       CRYO_SMEM_BASE() + warp * ZSE_PER_WARP, lane);
 }
 
 
@@ -508,6 +513,15 @@ k_page_compact(const uint8_t *out, uint64_t stride, uint32_t block_size, uint32_
             for (uint32_t i = lane; i < len; i += 32)
                 dst[i] = src[i];
     }
+}
+
+/* CTAs worth launching for the LZ4 encoder: one per LZ4E_WARPS work items */
+static size_t
+lz4e_items(uint32_t block_size, size_t n)
+{
+    uint32_t seg;
+
+    return (n * lz4e_seg_count(block_size, &seg) + LZ4E_WARPS - 1) / LZ4E_WARPS;
 }
 
 /* ---- page chains (cryo_pages.cuh): one CTA per cryo block ---- */
@@ -1386,29 +1400,79 @@ cryogpu_decompress_device(cryogpu_ctx *ctx, size_t n, const int32_t *d_methods,
     return CRYOGPU_OK;
 }
 
-/* the launch of one batched compression on st; ctx->mu is held and st already waits for ctx->busy */
+/* 64 KiB zstd blocks per frame, and CTAs worth launching for the zstd encoder (one per ZSE_WARPS work items) */
+static size_t
+zstde_blocks(uint32_t block_size)
+{
+    return ZSE_MAXBLK;                  /* bmeta rows are ZSE_MAXBLK wide whatever the block size */
+}
+
+static size_t
+zstde_grid(uint32_t block_size, size_t n, int sm_count)
+{
+    const size_t nblk = block_size ? ((size_t) block_size + ZSE_BLOCK - 1) / ZSE_BLOCK : 1;
+
+    return std::max<size_t>(1, std::min<size_t>((n * nblk + ZSE_WARPS - 1) / ZSE_WARPS, (size_t) sm_count));
+}
+
+/* scratch behind one batched compression of n blocks: LZ4 per block (+ the work queue and the per-block counts),
+ * zstd per CTA of the persistent grid */
+static size_t
+compress_scratch_bytes(int method, uint32_t block_size, size_t n, int sm_count)
+{
+    if (method == CRYOGPU_LZ4)
+        return n * lz4e_scratch_bytes(block_size) + ((n * 4 + 256 + 255) & ~(size_t) 255);
+    return zstde_grid(block_size, n, sm_count) * zstde_scratch_bytes(block_size) + ((n * 4 + 256 + 255) & ~(size_t) 255) +
+           n * (size_t) zstde_blocks(block_size) * 4;
+}
+
+/* the launches of one batched compression on st; scr: compress_scratch_bytes() of device memory, 256-byte aligned */
+static int
+launch_compress(cudaStream_t st, size_t n, int method, int level_or_accel, const uint8_t *d_src, uint64_t src_stride,
+                uint32_t block_size, uint8_t *d_dst, uint64_t dst_stride, uint32_t dst_cap, uint32_t *d_dst_size,
+                int32_t *d_status, uint8_t *scr, int sm_count)
+{
+    if (method == CRYOGPU_LZ4)
+    {
+        const size_t per = lz4e_scratch_bytes(block_size), qbytes = (n * 4 + 256 + 255) & ~(size_t) 255;
+        uint32_t    *queue = (uint32_t *) (scr + n * per);      /* [0]: next work item; [64 + b]: finished segments of block b */
+
+        CU(cudaMemsetAsync(queue, 0, qbytes, st));
+        k_lz4_encode<<<(unsigned) std::min<size_t>(lz4e_items(block_size, n), (size_t) sm_count), LZ4E_THREADS, LZ4E_SMEM, st>>>(
+            d_src, src_stride, block_size, d_dst, dst_stride, dst_cap, level_or_accel, d_dst_size, d_status, scr, per,
+            (uint32_t) n, queue, queue + 64);
+    }
+    else
+    {
+        /* per CTA scratch | queue [0], finished blocks per frame [64 + f] | bytes of every block [f * ZSE_MAXBLK + b] */
+        const size_t grid = zstde_grid(block_size, n, sm_count), qbytes = (n * 4 + 256 + 255) & ~(size_t) 255;
+        uint32_t    *queue = (uint32_t *) (scr + grid * zstde_scratch_bytes(block_size));
+        uint32_t    *bmeta = (uint32_t *) ((uint8_t *) queue + qbytes);
+
+        if (block_size > ZSE_MAXBLK * (uint64_t) ZSE_BLOCK)
+            return fail(CRYOGPU_E_ARG, "block_size above 128 MiB");
+        CU(cudaMemsetAsync(queue, 0, qbytes, st));
+        k_zstd_encode<<<(unsigned) grid, ZSTDE_THREADS, ZSTDE_SMEM, st>>>(
+            d_src, src_stride, block_size, d_dst, dst_stride, dst_cap, level_or_accel, d_dst_size, d_status, scr,
+            zstde_scratch_bytes(block_size), (uint32_t) n, queue, queue + 64, bmeta);
+    }
+    CU(cudaGetLastError());
+    return CRYOGPU_OK;
+}
+
+/* one batched compression on st with the context's scratch; ctx->mu is held and st already waits for ctx->busy */
 static int
 compress_device_locked(cryogpu_ctx *ctx, cudaStream_t st, size_t n, int method, int level_or_accel,
                        const uint8_t *d_src, uint64_t src_stride, uint32_t block_size,
                        uint8_t *d_dst, uint64_t dst_stride, uint32_t dst_cap,
                        uint32_t *d_dst_size, int32_t *d_status)
 {
-    const size_t per = method == CRYOGPU_LZ4 ? lz4e_scratch_bytes(block_size) : zstde_scratch_bytes(block_size);
-    const size_t zgrid = std::min<size_t>(n, (size_t) ctx->sm_count);
-    int          rc = dev_reserve(ctx->scratch, (method == CRYOGPU_LZ4 ? n : zgrid) * per);
+    int rc = dev_reserve(ctx->scratch, compress_scratch_bytes(method, block_size, n, ctx->sm_count));
 
     if (rc != CRYOGPU_OK)
         return rc;
-    if (method == CRYOGPU_LZ4)
-        k_lz4_encode<<<(unsigned) n, LZ4E_THREADS, LZ4E_SMEM, st>>>(
-            d_src, src_stride, block_size, d_dst, dst_stride, dst_cap, level_or_accel, d_dst_size,
-            d_status, (uint8_t *) ctx->scratch.p, per);
-    else
-        k_zstd_encode<<<(unsigned) zgrid, ZSTDE_THREADS, ZSTDE_SMEM, st>>>(
-            d_src, src_stride, block_size, d_dst, dst_stride, dst_cap, level_or_accel, d_dst_size,
-            d_status, (uint8_t *) ctx->scratch.p, per, (uint32_t) n);
-    CU(cudaGetLastError());
-    return CRYOGPU_OK;
+    return launch_compress(st, n, method, level_or_accel, d_src, src_stride, block_size, d_dst, dst_stride, dst_cap,
+                           d_dst_size, d_status, (uint8_t *) ctx->scratch.p, ctx->sm_count);
 }
 
 extern "C" int
@@ -2368,8 +2432,8 @@ cryogpu_compress_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel
     const size_t   chunk = chunk_blocks(block_size);
     const uint64_t sstride = ((uint64_t) block_size + 15) & ~(uint64_t) 15;
     const uint64_t dstride = (bound + 15) & ~(uint64_t) 15;
-    const size_t   per = method == CRYOGPU_LZ4 ? lz4e_scratch_bytes(block_size)
-                                               : zstde_scratch_bytes(block_size);
+    const size_t   lane_scratch = (compress_scratch_bytes(method, block_size, std::min(chunk, n), ctx->sm_count) + 255) &
+                                  ~(size_t) 255;
     const bool     src_pinned = is_pinned(src[0]);
     cudaStream_t   lanes[2] = {ctx->stream, ctx->stream2};
     size_t         pending_lo[2] = {0, 0}, pending_n[2] = {0, 0};
@@ -2407,7 +2471,7 @@ cryogpu_compress_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel
             (rc = dev_reserve(ctx->d_meta[lane], cnt * 8)) != CRYOGPU_OK ||
             (rc = host_reserve(ctx->h_meta[lane], cnt * 8)) != CRYOGPU_OK ||
             (rc = host_reserve(ctx->h_out[lane], cnt * dstride)) != CRYOGPU_OK ||
-            (rc = dev_reserve(ctx->scratch, 2 * chunk * per)) != CRYOGPU_OK)
+            (rc = dev_reserve(ctx->scratch, 2 * lane_scratch)) != CRYOGPU_OK)
             return rc;
         if (!src_pinned && (rc = host_reserve(ctx->h_in[lane], cnt * sstride)) != CRYOGPU_OK)
             return rc;
@@ -2425,20 +2489,13 @@ cryogpu_compress_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel
                                cudaMemcpyHostToDevice, st));
         }
         uint8_t *dm = (uint8_t *) ctx->d_meta[lane].p;
-        uint8_t *scr = (uint8_t *) ctx->scratch.p + (size_t) lane * chunk * per;
+        uint8_t *scr = (uint8_t *) ctx->scratch.p + (size_t) lane * lane_scratch;
 
-        if (method == CRYOGPU_LZ4)
-            k_lz4_encode<<<(unsigned) cnt, LZ4E_THREADS, LZ4E_SMEM, st>>>(
-                (uint8_t *) ctx->d_in[lane].p, sstride, block_size, (uint8_t *) ctx->d_out[lane].p,
-                dstride, (uint32_t) bound, level_or_accel, (uint32_t *) dm, (int32_t *) (dm + cnt * 4),
-                scr, per);
-        else
-            k_zstd_encode<<<(unsigned) std::min<size_t>(cnt, (size_t) ctx->sm_count), ZSTDE_THREADS,
-                            ZSTDE_SMEM, st>>>(
-                (uint8_t *) ctx->d_in[lane].p, sstride, block_size, (uint8_t *) ctx->d_out[lane].p,
-                dstride, (uint32_t) bound, level_or_accel, (uint32_t *) dm, (int32_t *) (dm + cnt * 4),
-                scr, per, (uint32_t) cnt);
-        CU(cudaGetLastError());
+        rc = launch_compress(st, cnt, method, level_or_accel, (uint8_t *) ctx->d_in[lane].p, sstride, block_size,
+                             (uint8_t *) ctx->d_out[lane].p, dstride, (uint32_t) bound, (uint32_t *) dm,
+                             (int32_t *) (dm + cnt * 4), scr, ctx->sm_count);
+        if (rc != CRYOGPU_OK)
+            return rc;
         CU(cudaMemcpyAsync(ctx->h_meta[lane].p, dm, cnt * 8, cudaMemcpyDeviceToHost, st));
         /* compressed sizes are unknown until the kernel ends: bring back whole slots when the
          * batch is tiny, otherwise sizes first and then only the used prefix of every slot */

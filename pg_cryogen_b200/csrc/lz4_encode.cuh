@@ -22,9 +22,10 @@
  *     step = (acceleration << 6 + attempts) >> 6.
  * Every warp writes the body of its segment's sequences to a scratch stream.  A
  * literal run is just input bytes, so runs that straddle segment boundaries need no
- * fix-up pass: after a CTA barrier the final layout is a prefix sum over at most
- * LZ4E_SEGS pieces, and all warps copy "token + extension + literals from the input
- * + body from scratch" into place with coalesced 16-byte stores.
+ * fix-up pass: once the last segment of a block is done the final layout is a prefix
+ * sum over at most LZ4E_SEGS pieces, and the warp that finished it copies "token +
+ * extension + literals from the input + body from scratch" into place with coalesced
+ * 16-byte stores.  Segments are work items of a queue (lz4_encode_worker): no CTA barrier.
  */
 #pragma once
 #include "cryo_common.cuh"
@@ -114,7 +115,44 @@ CRYO_DEV void lz4e_segment(const uint8_t *in, uint32_t len, uint32_t hist, int a
     for (uint32_t i = lane; i < (1u << LZ4E_HASHLOG) / 8; i += 32)
         reinterpret_cast<uint4 *>(table)[i] = make_uint4(0, 0, 0, 0);
     __syncwarp();
+    /*
+     * History.  The table holds positions as 16 bits, counted from H bytes before the segment.  A block of
+     * the usual size is cut into 64 KiB segments -- LZ4's whole window -- and H is 0; a small block (the
+     * 64 KiB blocks of BASELINE.json's acceleration sweep become 4 KiB segments) would lose most of its
+     * matches at the segment boundaries, so the warp first enters every position of the bytes before its
+     * segment into the table (inserts only: cheap beside the search), most recent last, as liblz4's single
+     * walk would have left them.
+     */
+    const uint32_t H = hist + len <= 65535u ? hist : (len < 65535u ? 65535u - len : 0u);
 
+    if (len > LZ4E_MFLIMIT && H)
+    {
+        /* every hstep-th position: 1 up to acceleration 2, then wider, as liblz4's own walk skips more the higher
+         * the acceleration; four loads in flight per lane */
+        const uint32_t hstep = accel <= 2 ? 1u : accel <= 8 ? 2u : accel <= 16 ? 4u : 8u;
+
+        for (uint32_t q0 = 0; q0 < H; q0 += 128u * hstep)
+        {
+            uint32_t v[4];
+
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++)
+            {
+                const uint32_t q = q0 + (32u * u + lane) * hstep;
+
+                v[u] = q < H ? lz4e_ld4(in + (int32_t) q - (int32_t) H) : 0u;
+            }
+#pragma unroll
+            for (uint32_t u = 0; u < 4; u++)
+            {
+                const uint32_t q = q0 + (32u * u + lane) * hstep;
+
+                if (q < H)
+                    table[(v[u] * 2654435761u) >> (32 - LZ4E_HASHLOG)] = (uint16_t) q;
+            }
+        }
+        __syncwarp();
+    }
     if (len > LZ4E_MFLIMIT)
     {
         const uint32_t mflimit = len - LZ4E_MFLIMIT;      /* last position a match may start at */
@@ -145,17 +183,18 @@ CRYO_DEV void lz4e_segment(const uint8_t *in, uint32_t len, uint32_t hist, int a
             const uint32_t step = attempts >> 6;
             const uint32_t pos = lane == 0 ? p : p + 1 + (lane - 1) * step;
             const bool     valid = pos <= mflimit;
-            uint32_t v = 0, h = 0, cand = 0;
+            uint32_t v = 0, h = 0;
+            int32_t  cand = 0;              /* relative to the segment: negative = in the bytes before it */
             bool     hit = false;
 
             if (valid)
             {
                 v = lz4e_ld4(in + pos);
                 h = (v * 2654435761u) >> (32 - LZ4E_HASHLOG);
-                cand = table[h];
+                cand = (int32_t) table[h] - (int32_t) H;
             }
             if (valid)
-                hit = cand < pos && lz4e_ld4(in + cand) == v;
+                hit = cand < (int32_t) pos && lz4e_ld4(in + cand) == v;
             /* the probes of one group cannot see each other through the table; a probe whose
              * 4 bytes repeat the previous probe's (runs, short periods) matches it directly */
             {
@@ -164,7 +203,7 @@ CRYO_DEV void lz4e_segment(const uint8_t *in, uint32_t len, uint32_t hist, int a
                 if (valid && !hit && lane > 0 && pv == v)
                 {
                     hit = true;
-                    cand = lane == 1 ? p : pos - step;
+                    cand = (int32_t) (lane == 1 ? p : pos - step);
                 }
             }
             uint32_t m = __ballot_sync(CRYO_FULL, hit);
@@ -174,7 +213,7 @@ CRYO_DEV void lz4e_segment(const uint8_t *in, uint32_t len, uint32_t hist, int a
             /* insert the probed positions up to and including the first hit; the ones behind
              * it will be probed again after the match and must still see older candidates */
             if (valid && (m & ((1u << lane) - 1u)) == 0)
-                table[h] = (uint16_t) pos;
+                table[h] = (uint16_t) (pos + H);
             __syncwarp();
             if (m == 0)
             {
@@ -184,8 +223,8 @@ CRYO_DEV void lz4e_segment(const uint8_t *in, uint32_t len, uint32_t hist, int a
             }
             const int      k = __ffs((int) m) - 1;
             uint32_t       mpos = k == 0 ? p : p + 1 + (uint32_t) (k - 1) * step;
-            uint32_t       mcand = __shfl_sync(CRYO_FULL, cand, k);
-            uint32_t       off = mpos - mcand;
+            int32_t        mcand = __shfl_sync(CRYO_FULL, cand, k);
+            uint32_t       off = (uint32_t) ((int32_t) mpos - mcand);
             const bool     cont = cont_off != 0;
 
             if (cont)
@@ -200,13 +239,13 @@ CRYO_DEV void lz4e_segment(const uint8_t *in, uint32_t len, uint32_t hist, int a
 
             for (; !cont;)
             {
-                bool eq = mpos >= anchor + 1 + lane && mcand >= 1 + lane &&
-                          in[mpos - 1 - lane] == in[mcand - 1 - lane];
+                bool eq = mpos >= anchor + 1 + lane && mcand - (int32_t) (1 + lane) >= -(int32_t) H &&
+                          in[mpos - 1 - lane] == in[mcand - 1 - (int32_t) lane];
                 uint32_t ne = ~__ballot_sync(CRYO_FULL, eq);
                 uint32_t back = ne ? (uint32_t) __ffs((int) ne) - 1u : 32u;
 
                 mpos -= back;
-                mcand -= back;
+                mcand -= (int32_t) back;
                 if (back < 32)
                     break;
             }
@@ -288,7 +327,7 @@ CRYO_DEV void lz4e_segment(const uint8_t *in, uint32_t len, uint32_t hist, int a
             attempts = start_attempts;
             /* like liblz4, remember the position two bytes before the end of the match */
             if (lane == 0 && p >= 2 && p - 2 <= mflimit)
-                table[(lz4e_ld4(in + p - 2) * 2654435761u) >> (32 - LZ4E_HASHLOG)] = (uint16_t) (p - 2);
+                table[(lz4e_ld4(in + p - 2) * 2654435761u) >> (32 - LZ4E_HASHLOG)] = (uint16_t) (p - 2 + H);
             __syncwarp();
         }
     }
@@ -301,17 +340,117 @@ CRYO_DEV void lz4e_segment(const uint8_t *in, uint32_t len, uint32_t hist, int a
     }
 }
 
-/*
- * Compress one block.  Called by every thread of the CTA.  scratch: lz4e_scratch_bytes(n)
- * of global memory private to this CTA, 16-byte aligned.
- */
-CRYO_DEV void lz4_encode_block(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t dst_cap,
-                               int accel, uint32_t *dst_size, int32_t *status, uint8_t *scratch)
+/* segments of a block of n bytes: at most LZ4E_MAXSEG bytes each, at least LZ4E_WARPS of them when the block allows */
+CRYO_HD uint32_t lz4e_seg_count(uint32_t n, uint32_t *seg_len)
 {
-    uint8_t  *smem = CRYO_SMEM_BASE();
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint32_t *sh_total = reinterpret_cast<uint32_t *>(smem + LZ4E_META);
+    uint32_t nseg = (n + LZ4E_MAXSEG - 1) / LZ4E_MAXSEG;
 
+    if (nseg < LZ4E_WARPS)
+        nseg = n >= LZ4E_WARPS * 1024u ? LZ4E_WARPS : (n >= 1024u ? n / 1024u : 1u);
+    const uint32_t seg = ((n + nseg - 1) / nseg + 15u) & ~15u;
+
+    *seg_len = seg;
+    return n ? (n + seg - 1) / seg : 1u;
+}
+
+/*
+ * Layout and copy of one block whose segments are all done, by ONE warp.  A segment with a match owns one
+ * piece = token + ll-ext + literals + body; its literals start where the previous piece's last match ended
+ * (literal runs are plain input bytes, so runs that cross segment boundaries need no fix-up).
+ */
+CRYO_DEV void lz4e_finish_block(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t dst_cap, uint32_t *dst_size,
+                                int32_t *status, uint8_t *scratch, uint32_t lane)
+{
+    uint32_t       seg;
+    const uint32_t nseg = lz4e_seg_count(n, &seg);
+    const size_t   stream_bytes = (((size_t) n + n / 255 + 96 * lz4e_nsegs(n) + 1024) + 15) / 16 * 16;
+    Lz4eSeg       *meta = reinterpret_cast<Lz4eSeg *>(scratch + stream_bytes);
+    const uint32_t seg_stride = seg + seg / 255 + 64;
+    uint32_t       out = 0, carry_start = 0;
+
+    /* positions: serial over at most nseg pieces, every lane the same arithmetic (the metadata is in L2) */
+    for (uint32_t s = 0; s < nseg; s++)
+    {
+        const Lz4eSeg *ms = meta + s;
+
+        if (ms->ml0 < 0)
+            continue;
+        const uint32_t LL = s * seg + ms->first_match - carry_start;
+
+        out += 1 + lz4e_extlen(LL) + LL + ms->body;
+        carry_start = s * seg + ms->tail_start;
+    }
+    const uint32_t total = out + 1 + lz4e_extlen(n - carry_start) + (n - carry_start);
+
+    if (total > dst_cap)
+    {
+        if (lane == 0)
+        {
+            *dst_size = 0;
+            *status = ST_OUTPUT;
+        }
+        return;
+    }
+    out = 0;
+    carry_start = 0;
+    for (uint32_t s = 0; s < nseg; s++)
+    {
+        const Lz4eSeg *ms = meta + s;
+
+        if (ms->ml0 < 0)
+            continue;
+        const uint32_t LL = s * seg + ms->first_match - carry_start, m0 = (uint32_t) ms->ml0;
+        uint8_t *d = dst + out;
+        uint32_t o = 1;
+
+        if (lane == 0)
+            d[0] = (uint8_t) (((LL < 15 ? LL : 15u) << 4) | (m0 < 15 ? m0 : 15u));
+        if (LL >= 15)
+        {
+            lz4e_put_ext(d + o, LL, lane);
+            o += lz4e_extlen(LL);
+        }
+        team_copy(d + o, src + carry_start, LL, lane, 32);
+        team_copy(d + o + LL, scratch + (size_t) s * seg_stride, ms->body, lane, 32);
+        out += o + LL + ms->body;
+        carry_start = s * seg + ms->tail_start;
+    }
+    {
+        /* closing sequence: literals only (the last 5+ bytes of the block are in it) */
+        const uint32_t LL = n - carry_start;
+        uint8_t *d = dst + out;
+        uint32_t o = 1;
+
+        if (lane == 0)
+            d[0] = (uint8_t) ((LL < 15 ? LL : 15u) << 4);
+        if (LL >= 15)
+        {
+            lz4e_put_ext(d + o, LL, lane);
+            o += lz4e_extlen(LL);
+        }
+        team_copy(d + o, src + carry_start, LL, lane, 32);
+    }
+    if (lane == 0)
+    {
+        *dst_size = total;
+        *status = ST_OK;
+    }
+}
+
+/*
+ * The encoder's work loop, one warp.  Work items are (block, segment) pairs handed out in order from a
+ * queue in global memory; the warp that finishes the last segment of a block lays the block out.  With one
+ * CTA per block (round 1) fifteen warps waited at a barrier for the one whose segment holds the tuples of
+ * a sparse cryo block (68 % of the stall samples, profiles/r01g_other_kernels_ncu_summary.txt); here they take
+ * segments of the next blocks instead.
+ *   queue[0]: next item; done[b]: finished segments of block b (both zeroed by the caller);
+ *   scratch: lz4e_scratch_bytes(n) per block; table: this warp's LZ4E_HASH_BYTES of shared memory.
+ */
+CRYO_DEV void lz4_encode_worker(const uint8_t *src, uint64_t src_stride, uint32_t n, uint8_t *dst, uint64_t dst_stride,
+                                uint32_t dst_cap, int accel, uint32_t *dst_size, int32_t *status, uint8_t *scratch,
+                                uint64_t scratch_stride, uint32_t nblocks, uint32_t *queue, uint32_t *done,
+                                uint16_t *table, uint32_t lane)
+{
     if (accel < 1)
         accel = 1;                      /* liblz4: acceleration < 1 means 1 */
     if (accel > 65537)
@@ -323,104 +462,39 @@ CRYO_DEV void lz4_encode_block(const uint8_t *src, uint32_t n, uint8_t *dst, uin
      * kind stays within the 1.10 x tolerance of DESIGN.md section 1 at every acceleration. */
     if (accel > 2)
         accel = (accel + 1) / 2;
-    /* segments: at most LZ4E_MAXSEG bytes each, at least one per warp when the block allows */
-    uint32_t nseg = (n + LZ4E_MAXSEG - 1) / LZ4E_MAXSEG;
-
-    if (nseg < LZ4E_WARPS)
-        nseg = n >= LZ4E_WARPS * 1024u ? LZ4E_WARPS : (n >= 1024u ? n / 1024u : 1u);
-    const uint32_t seg = ((n + nseg - 1) / nseg + 15u) & ~15u;
+    uint32_t       seg;
+    const uint32_t nseg = lz4e_seg_count(n, &seg);
     const size_t   stream_bytes = (((size_t) n + n / 255 + 96 * lz4e_nsegs(n) + 1024) + 15) / 16 * 16;
-    Lz4eSeg       *meta = reinterpret_cast<Lz4eSeg *>(scratch + stream_bytes);
     const uint32_t seg_stride = seg + seg / 255 + 64;
+    const uint64_t items = (uint64_t) nblocks * nseg;
 
-    nseg = n ? (n + seg - 1) / seg : 1;
-    for (uint32_t s = warp; s < nseg; s += LZ4E_WARPS)
+    for (;;)
     {
-        uint32_t lo = s * seg, len = n - lo < seg ? n - lo : seg;
-
-        lz4e_segment(src + lo, len, lo, accel, scratch + (size_t) s * seg_stride,
-                     reinterpret_cast<uint16_t *>(smem + warp * LZ4E_HASH_BYTES), meta + s, lane);
-    }
-    __threadfence_block();
-    __syncthreads();
-
-    /* layout: a segment with a match owns one piece = token + ll-ext + literals + body; its
-     * literals start where the previous piece's last match ended (literal runs are plain
-     * input bytes, so runs that cross segment boundaries need no fix-up).  Serial, <= nseg. */
-    if (tid == 0)
-    {
-        uint32_t out = 0, carry_start = 0;
-
-        for (uint32_t s = 0; s < nseg; s++)
-        {
-            Lz4eSeg *ms = meta + s;
-
-            if (ms->ml0 < 0)
-            {
-                ms->at = 0xFFFFFFFFu;
-                continue;
-            }
-            ms->lit0 = carry_start;
-            ms->LL = s * seg + ms->first_match - carry_start;
-            ms->at = out;
-            out += 1 + lz4e_extlen(ms->LL) + ms->LL + ms->body;
-            carry_start = s * seg + ms->tail_start;
-        }
-        sh_total[0] = out;                              /* the closing literal run starts here */
-        sh_total[1] = carry_start;                      /* ... with this input position */
-        sh_total[2] = out + 1 + lz4e_extlen(n - carry_start) + (n - carry_start);
-    }
-    __syncthreads();
-    const uint32_t total = sh_total[2];
-
-    if (total > dst_cap)
-    {
-        if (tid == 0)
-        {
-            *dst_size = 0;
-            *status = ST_OUTPUT;
-        }
-        return;
-    }
-    for (uint32_t s = warp; s < nseg; s += LZ4E_WARPS)
-    {
-        const Lz4eSeg *ms = meta + s;
-
-        if (ms->at == 0xFFFFFFFFu)
-            continue;
-        const uint32_t LL = ms->LL, m0 = (uint32_t) ms->ml0;
-        uint8_t *d = dst + ms->at;
-        uint32_t o = 1;
+        uint32_t w = 0;
 
         if (lane == 0)
-            d[0] = (uint8_t) (((LL < 15 ? LL : 15u) << 4) | (m0 < 15 ? m0 : 15u));
-        if (LL >= 15)
-        {
-            lz4e_put_ext(d + o, LL, lane);
-            o += lz4e_extlen(LL);
-        }
-        team_copy(d + o, src + ms->lit0, LL, lane, 32);
-        team_copy(d + o + LL, scratch + (size_t) s * seg_stride, ms->body, lane, 32);
-    }
-    if (warp == (nseg % LZ4E_WARPS))
-    {
-        /* closing sequence: literals only (the last 5+ bytes of the block are in it) */
-        const uint32_t at = sh_total[0], lit0 = sh_total[1], LL = n - lit0;
-        uint8_t *d = dst + at;
-        uint32_t o = 1;
+            w = atomicAdd(queue, 1u);
+        w = __shfl_sync(CRYO_FULL, w, 0);
+        if (w >= items)
+            return;
+        const uint32_t b = w / nseg, s = w % nseg;
+        const uint8_t *bsrc = src + b * src_stride;
+        uint8_t       *bscr = scratch + b * scratch_stride;
+        Lz4eSeg       *meta = reinterpret_cast<Lz4eSeg *>(bscr + stream_bytes);
+        const uint32_t lo = s * seg, len = n - lo < seg ? n - lo : seg;
+
+        lz4e_segment(bsrc + lo, len, lo, accel, bscr + (size_t) s * seg_stride, table, meta + s, lane);
+        __syncwarp();
+        __threadfence();                /* the segment's stream and metadata before the count */
+        uint32_t fin = 0;
 
         if (lane == 0)
-            d[0] = (uint8_t) ((LL < 15 ? LL : 15u) << 4);
-        if (LL >= 15)
+            fin = atomicAdd(done + b, 1u);
+        fin = __shfl_sync(CRYO_FULL, fin, 0);
+        if (fin == nseg - 1u)
         {
-            lz4e_put_ext(d + o, LL, lane);
-            o += lz4e_extlen(LL);
+            __threadfence();            /* ... and the other warps' after it */
+            lz4e_finish_block(bsrc, n, dst + b * dst_stride, dst_cap, dst_size + b, status + b, bscr, lane);
         }
-        team_copy(d + o, src + lit0, LL, lane, 32);
-    }
-    if (tid == 0)
-    {
-        *dst_size = total;
-        *status = ST_OK;
     }
 }

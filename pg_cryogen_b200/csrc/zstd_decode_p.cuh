@@ -1347,6 +1347,7 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
                 __nanosleep(256);                                                            \
             }                                                                                \
         seen_ = __shfl_sync(CRYO_FULL, seen_, 0);                                            \
+        __threadfence();        /* every lane's later reads of stage 0's output after lane 0's acquire */ \
         if (seen_ < skipped)                                                                 \
         {                                                                                    \
             uint32_t at_ = 0;                                                                \

@@ -83,6 +83,7 @@
 #else
 #define ZSE_HD __host__ __device__ static inline
 #endif
+/* global scratch of one CTA (per warp: sequences, literals, the block's body) */
 ZSE_HD size_t zstde_scratch_bytes(uint32_t block_size)
 {
     (void) block_size;
@@ -1560,114 +1561,86 @@ CRYO_DEV ZseBlockOut zse_block(const uint8_t *in, uint32_t len, const ZseParams 
     return R;
 }
 
-/* ---- one frame ------------------------------------------------------------------ */
+/* ---- frames ------------------------------------------------------------------------ */
+
+/* bytes of the frame header for a content size of n (single segment, content size field of 1 / 2 / 4 bytes) */
+CRYO_DEV uint32_t zse_frame_header_size(uint32_t n)
+{
+    return n < 256u ? 6u : n < 65536u + 256u ? 7u : 9u;
+}
+
+/* overlap-safe move of n bytes to a LOWER address by one warp: 512 bytes per step, read before written */
+CRYO_DEV void zse_move_down(uint8_t *dst, const uint8_t *src, uint32_t n, uint32_t lane)
+{
+    if (dst == src)
+        return;
+    for (uint32_t i0 = 0; i0 < n; i0 += 512u)
+    {
+        uint8_t v[16];
+
+#pragma unroll
+        for (uint32_t q = 0; q < 16; q++)
+            v[q] = i0 + 32u * q + lane < n ? src[i0 + 32u * q + lane] : (uint8_t) 0;
+        __syncwarp();
+#pragma unroll
+        for (uint32_t q = 0; q < 16; q++)
+            if (i0 + 32u * q + lane < n)
+                dst[i0 + 32u * q + lane] = v[q];
+        __syncwarp();
+    }
+}
 
 /*
- * Compress src[0, n) into one zstd frame at dst.  Called by every thread of the CTA.
- * scratch: zstde_scratch_bytes() of global memory private to this CTA, 16-byte aligned.
+ * The encoder's work loop, one warp.  Work items are (frame, 64 KiB block) pairs handed out in order from a
+ * queue in global memory.  A block is written where it would start if every block before it were stored Raw
+ * (frame header + b x (64 KiB + 3): inside cryogpu_compress_bound); the warp that finishes the last block of
+ * a frame writes the frame header and closes the gaps, moving the blocks down in order.  With one CTA per
+ * frame (round 1) fourteen warps waited at a barrier for the two whose blocks hold the tuples of a sparse
+ * cryo block (84 % of the stall samples, profiles/r01g_other_kernels_ncu_summary.txt); here they take blocks
+ * of the next frames instead.
+ *   queue[0]: next item; done[f]: finished blocks of frame f (zeroed by the caller); bmeta[f * ZSE_MAXBLK + b]:
+ *   bytes of block b with its header; scr: this warp's ZSE_SCR_PER_WARP bytes of global scratch; smem: this
+ *   warp's ZSE_PER_WARP bytes.
  */
-CRYO_DEV void zstd_encode_frame(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t dst_cap, int level,
-                                uint32_t *dst_size, int32_t *status, uint8_t *scratch)
+#define ZSE_MAXBLK 2048u                /* block_size <= 128 MiB */
+
+CRYO_DEV void zstd_encode_worker(const uint8_t *src, uint64_t src_stride, uint32_t n, uint8_t *dst, uint64_t dst_stride,
+                                 uint32_t dst_cap, int level, uint32_t *dst_size, int32_t *status, uint8_t *scr,
+                                 uint32_t nframes, uint32_t *queue, uint32_t *done, uint32_t *bmeta, uint8_t *smem,
+                                 uint32_t lane)
 {
-    uint8_t  *smem = CRYO_SMEM_BASE();
-    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint32_t *ctl = reinterpret_cast<uint32_t *>(smem + ZSE_CTL);       /* [0..15] type|size, [16..31] at, [32] pos, [33] fail */
     const ZseParams P = zse_params(level);
-    const uint32_t nblk = n ? (n + ZSE_BLOCK - 1) / ZSE_BLOCK : 1u;
-    uint8_t  *scr = scratch + (size_t) warp * ZSE_SCR_PER_WARP;
+    const uint32_t nblk = n ? (n + ZSE_BLOCK - 1) / ZSE_BLOCK : 1u, hdr = zse_frame_header_size(n);
+    const uint64_t items = (uint64_t) nframes * nblk;
+    const bool     fits = dst_cap >= 16u && (uint64_t) hdr + (uint64_t) n + 3ull * nblk <= dst_cap;
 
-    /* frame header: magic, descriptor (single segment, content size), content size */
-    if (tid == 0)
+    for (;;)
     {
-        uint32_t o = 0;
+        uint32_t w = 0;
 
-        ctl[33] = 0;
-        if (dst_cap < 16)
-            ctl[33] = 1;
-        else
-        {
-            dst[o++] = 0x28;
-            dst[o++] = 0xB5;
-            dst[o++] = 0x2F;
-            dst[o++] = 0xFD;
-            if (n < 256)
-            {
-                dst[o++] = 0x20;
-                dst[o++] = (uint8_t) n;
-            }
-            else if (n < 65536 + 256)
-            {
-                dst[o++] = 0x60;
-                dst[o++] = (uint8_t) (n - 256);
-                dst[o++] = (uint8_t) ((n - 256) >> 8);
-            }
-            else
-            {
-                dst[o++] = 0xA0;
-                dst[o++] = (uint8_t) n;
-                dst[o++] = (uint8_t) (n >> 8);
-                dst[o++] = (uint8_t) (n >> 16);
-                dst[o++] = (uint8_t) (n >> 24);
-            }
-        }
-        ctl[32] = o;
-    }
-    __syncthreads();
-    for (uint32_t b0 = 0; b0 < nblk; b0 += ZSE_WARPS)
-    {
-        const uint32_t b = b0 + warp;
-        ZseBlockOut    R;
+        if (lane == 0)
+            w = atomicAdd(queue, 1u);
+        w = __shfl_sync(CRYO_FULL, w, 0);
+        if (w >= items)
+            return;
+        const uint32_t f = w / nblk, b = w % nblk;
+        const uint8_t *fsrc = src + f * src_stride;
+        uint8_t       *fdst = dst + f * dst_stride;
+        const uint32_t lo = b * ZSE_BLOCK, len = n - lo < ZSE_BLOCK ? n - lo : ZSE_BLOCK;
 
-        R.type = 0;
-        R.size = 0;
-        R.byte = 0;
-        if (b < nblk && ctl[33] == 0)
+        if (fits)
         {
-            const uint32_t lo = b * ZSE_BLOCK, len = n - lo < ZSE_BLOCK ? n - lo : ZSE_BLOCK;
-
-            R = zse_block(src + lo, len, P, smem + warp * ZSE_PER_WARP, scr, lane);
-            if (lane == 0)
-            {
-                ctl[warp] = R.type | (R.size << 2);
-                ctl[16 + warp] = R.type == 2 || R.type == 0 ? R.size : 1u;
-            }
-        }
-        else if (lane == 0)
-        {
-            ctl[warp] = 0xFFFFFFFFu;
-            ctl[16 + warp] = 0;
-        }
-        __syncthreads();
-        if (tid == 0)
-        {
-            uint32_t pos = ctl[32];
-
-            for (uint32_t w = 0; w < ZSE_WARPS; w++)
-            {
-                uint32_t bytes = ctl[16 + w];
-
-                if (ctl[w] == 0xFFFFFFFFu)
-                    continue;
-                ctl[16 + w] = pos;
-                pos += 3 + bytes;
-            }
-            if (pos > dst_cap)
-                ctl[33] = 1;
-            ctl[32] = pos;
-        }
-        __syncthreads();
-        if (b < nblk && ctl[33] == 0)
-        {
-            const uint32_t lo = b * ZSE_BLOCK, len = n - lo < ZSE_BLOCK ? n - lo : ZSE_BLOCK;
-            uint8_t       *d = dst + ctl[16 + warp];
+            const ZseBlockOut R = zse_block(fsrc + lo, len, P, smem, scr, lane);
+            uint8_t       *d = fdst + hdr + (size_t) b * (ZSE_BLOCK + 3u);
             const uint32_t last = b + 1 == nblk ? 1u : 0u;
             const uint32_t hsize = R.type == 2 ? R.size : len;
             const uint32_t h = last | (R.type << 1) | (hsize << 3);
+            const uint32_t bytes = 3u + (R.type == 1 ? 1u : R.type == 0 ? len : R.size);
 
             if (lane < 3)
                 d[lane] = (uint8_t) (h >> (8 * lane));
             if (R.type == 0)
-                team_copy(d + 3, src + lo, len, lane, 32);
+                team_copy(d + 3, fsrc + lo, len, lane, 32);
             else if (R.type == 1)
             {
                 if (lane == 0)
@@ -1675,20 +1648,70 @@ CRYO_DEV void zstd_encode_frame(const uint8_t *src, uint32_t n, uint8_t *dst, ui
             }
             else
                 team_copy(d + 3, scr + ZSE_SCR_OUT, R.size, lane, 32);
+            if (lane == 0)
+                bmeta[(size_t) f * ZSE_MAXBLK + b] = bytes;
         }
-        __syncthreads();
-    }
-    if (tid == 0)
-    {
-        if (ctl[33])
+        __syncwarp();
+        __threadfence();                /* the block and its size before the count */
+        uint32_t fin = 0;
+
+        if (lane == 0)
+            fin = atomicAdd(done + f, 1u);
+        fin = __shfl_sync(CRYO_FULL, fin, 0);
+        if (fin != nblk - 1u)
+            continue;
+        __threadfence();                /* ... and the other warps' after it */
+        if (!fits)
         {
-            *dst_size = 0;
-            *status = ST_OUTPUT;
+            if (lane == 0)
+            {
+                dst_size[f] = 0;
+                status[f] = ST_OUTPUT;
+            }
+            continue;
         }
-        else
+        /* frame header: magic, descriptor (single segment, content size), content size */
+        if (lane == 0)
         {
-            *dst_size = ctl[32];
-            *status = ST_OK;
+            uint32_t o = 0;
+
+            fdst[o++] = 0x28;
+            fdst[o++] = 0xB5;
+            fdst[o++] = 0x2F;
+            fdst[o++] = 0xFD;
+            if (n < 256)
+            {
+                fdst[o++] = 0x20;
+                fdst[o++] = (uint8_t) n;
+            }
+            else if (n < 65536 + 256)
+            {
+                fdst[o++] = 0x60;
+                fdst[o++] = (uint8_t) (n - 256);
+                fdst[o++] = (uint8_t) ((n - 256) >> 8);
+            }
+            else
+            {
+                fdst[o++] = 0xA0;
+                fdst[o++] = (uint8_t) n;
+                fdst[o++] = (uint8_t) (n >> 8);
+                fdst[o++] = (uint8_t) (n >> 16);
+                fdst[o++] = (uint8_t) (n >> 24);
+            }
+        }
+        uint32_t pos = hdr;
+
+        for (uint32_t k = 0; k < nblk; k++)
+        {
+            const uint32_t bytes = bmeta[(size_t) f * ZSE_MAXBLK + k];
+
+            zse_move_down(fdst + pos, fdst + hdr + (size_t) k * (ZSE_BLOCK + 3u), bytes, lane);
+            pos += bytes;
+        }
+        if (lane == 0)
+        {
+            dst_size[f] = pos;
+            status[f] = ST_OK;
         }
     }
 }

@@ -135,9 +135,12 @@ emu_lz4_encode(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t dst_cap, i
     uint8_t *sc = (uint8_t *) ((((uintptr_t) scr.data() + 63) & ~(uintptr_t) 63));
     int32_t status = -1;
 
+    uint32_t queue[65] = {0};           /* [0]: next work item; [64]: finished segments of the block */
+
     memcpy(in, src, n);
     emu::launch(dim3(1), dim3(LZ4E_THREADS), LZ4E_SMEM, [&]() {
-        lz4_encode_block(in, n, o, dst_cap, accel, dst_size, &status, sc);
+        lz4_encode_worker(in, 0, n, o, 0, dst_cap, accel, dst_size, &status, sc, 0, 1, queue, queue + 64,
+                          reinterpret_cast<uint16_t *>(CRYO_SMEM_BASE() + (threadIdx.x >> 5) * LZ4E_HASH_BYTES), threadIdx.x & 31);
     });
     if (status == 0)
         memcpy(dst, o, *dst_size);
@@ -158,9 +161,15 @@ emu_zstd_encode(const uint8_t *src, uint32_t n, uint8_t *dst, uint32_t dst_cap, 
     uint8_t *sc = (uint8_t *) ((((uintptr_t) scr.data() + 63) & ~(uintptr_t) 63));
     int32_t status = -1;
 
+    uint32_t queue[65] = {0};           /* [0]: next work item; [64]: finished blocks of the frame */
+    std::vector<uint32_t> bmeta(ZSE_MAXBLK, 0xCDCDCDCD);
+
     memcpy(in, src, n);
     emu::launch(dim3(1), dim3(ZSTDE_THREADS), ZSTDE_SMEM, [&]() {
-        zstd_encode_frame(in, n, o, dst_cap, level, dst_size, &status, sc);
+        const uint32_t warp = threadIdx.x >> 5;
+
+        zstd_encode_worker(in, 0, n, o, 0, dst_cap, level, dst_size, &status, sc + (size_t) warp * ZSE_SCR_PER_WARP, 1, queue,
+                           queue + 64, bmeta.data(), CRYO_SMEM_BASE() + warp * ZSE_PER_WARP, threadIdx.x & 31);
     });
     if (status == 0)
         memcpy(dst, o, *dst_size);
