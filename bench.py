@@ -346,6 +346,50 @@ def secondary_cells(gpu, dev, peak, uniq: int, n: int, threads: int):
     return cells
 
 
+def next_row_cells(gpu, chunks, want, threads):
+    """The rows SURVEY.md 8(f) marks "next", measured on the headline table through their host entry points:
+    f-4 count pushdown (cryogpu_decompress_count_host) and f-1 decompress from page chains
+    (cryogpu_decompress_pages_host, pages laid out by the restatement of the reference's split)."""
+    from oracle import pages as opg, ref          # checker / input preparation only
+    cells = []
+    n = len(chunks)
+    methods = np.full(n, METHOD, dtype=np.int32)
+    # ---- f-4: select count(*) pushed down: compressed blocks in, 24 bytes per block out
+    nt, by, st = gpu.decompress_count_host(methods, chunks)
+    assert (st == 0).all() and int(nt.sum()) > 0
+    t0 = time.perf_counter()
+    for _ in range(3):
+        nt, by, st = gpu.decompress_count_host(methods, chunks)
+    t = (time.perf_counter() - t0) / 3
+    bi, bo = gpu.last_transfer_bytes()
+    # the reference: cryo_decompress + the item walk of cryo_getnextslot, all cores (the walk is negligible beside the codec)
+    cpu_all, _ = cpu_reference_decompress(METHOD, chunks[: max(64, threads * 16)], threads, 2.0)
+    cells.append({"row": "f-4 count pushdown", "api": "cryogpu_decompress_count_host", "blocks": n, "tuples_counted": int(nt.sum()),
+                  "value": n * CRYO_BLCKSZ / t / 1e9, "unit": "GB/s of decompressed data scanned", "h2d_bytes": bi, "d2h_bytes": bo,
+                  "cpu_reference_all_cores": cpu_all, "cores": threads})
+    # ---- f-1: the same blocks as page chains on "disk" (8 KiB pages, first page header 48 bytes, others 32)
+    m = min(n, 1024)
+    npages = [opg.pages_needed(len(c)) for c in chunks[:m]]
+    rel = np.zeros((sum(npages) + 1, 8192), dtype=np.uint8)
+    chains, at = [], 1
+    for i in range(m):
+        ch = list(range(at, at + npages[i]))
+        opg.split(rel, ch, chunks[i], METHOD, 1)
+        chains.append(ch)
+        at += npages[i]
+    out, osz, st, me, csz = gpu.decompress_pages_host(rel, chains)
+    assert (st == 0).all() and np.array_equal(digest_np(out), want[:m]), "page-chain decode differs"
+    t0 = time.perf_counter()
+    for _ in range(3):
+        gpu.decompress_pages_host(rel, chains)
+    t = (time.perf_counter() - t0) / 3
+    cells.append({"row": "f-1 decompress from page chains", "api": "cryogpu_decompress_pages_host (pageable pages in, pageable blocks out, "
+                  "every byte written; includes the Python binding's per-call array setup)", "blocks": m, "pages": int(sum(npages)),
+                  "value": m * CRYO_BLCKSZ / t / 1e9, "unit": "GB/s", "bit_exact_all_blocks": True,
+                  "cpu_reference_all_cores": cpu_all, "cores": threads})
+    return cells
+
+
 # ---- BASELINE.json configs[2]: lz4_acceleration sweep on 64 KiB blocks ---------------------------
 
 def run_config3(args, gpu, dev, rank, world):
@@ -747,11 +791,12 @@ def main():
                "value_1_thread": gbs_one}
 
     # ---- the rest of the metric: lz4 and zstd-1, both directions, every block kind ----
-    secondary = None
+    secondary = next_rows = None
     if rank == 0 and world == 1 and not args.no_secondary:
         del d_dst, d_src
         torch.cuda.empty_cache()
         secondary = secondary_cells(gpu, dev, peak, uniq=32, n=512, threads=os.cpu_count() or 1)
+        next_rows = next_row_cells(gpu, chunks, want, os.cpu_count() or 1)
 
     if rank == 0:
         line = {
@@ -766,7 +811,7 @@ def main():
                        "parallelism": f"block-range shards x{world}, no collective",
                        "gate": "status, size and a 128-bit digest of every decoded block, before and after the timed steps"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline,
-            "cpu_baseline": cpu, "secondary": secondary,
+            "cpu_baseline": cpu, "secondary": secondary, "next_rows": next_rows,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
