@@ -278,3 +278,24 @@ def test_zstd_pipeline_random_frames_small_capacity(gpu, oracle_port):
         assert want_n == plain[k].size and np.array_equal(want[:want_n], plain[k])
     frames, fallback = gpu.zstd_pipeline_stats()
     assert frames == len(comp) and fallback <= len(comp) // 4, (frames, fallback)
+
+
+def test_host_api_zero_runs_returned_to_the_kernel(gpu, oracle_ref):
+    """cryogpu_set_zero_by_unmap: for destinations in private anonymous memory the zero runs of sparse blocks
+    are given back to the kernel (madvise) instead of being written; the caller's blocks must read exactly as
+    the reference's output whatever they held before, with the option on and off, and for dense blocks too."""
+    blocks = np.stack([bg.make_block("S", "hex", 90 + i) for i in range(10)] +
+                      [bg.make_block("M", "lowcard", 77), bg.make_block("D", "hex", 78), np.zeros(CRYO_BLCKSZ, dtype=np.uint8)])
+    methods = [i & 1 for i in range(blocks.shape[0])]
+    comp = [oracle_ref.compress(m, 1, b)[0][0] for m, b in zip(methods, blocks)]
+    for on in (1, 0, 1):
+        assert gpu.lib.cryogpu_set_zero_by_unmap(gpu.handle, on) == 0
+        out = np.full((blocks.shape[0], CRYO_BLCKSZ), 0x5A, dtype=np.uint8)     # pageable, full of stale bytes
+        out, osz, st = gpu.decompress_host(methods, comp, out=out)
+        assert (st == 0).all() and (osz == CRYO_BLCKSZ).all()
+        assert np.array_equal(out, blocks), on
+        # and again into the same (now partly unmapped) destination
+        out[:, ::4096] = 0xA5
+        out, osz, st = gpu.decompress_host(methods, comp, out=out)
+        assert (st == 0).all() and np.array_equal(out, blocks), on
+    gpu.lib.cryogpu_set_zero_by_unmap(gpu.handle, 0)
