@@ -80,6 +80,23 @@ __device__ long long cx_prof_last;
 #define CXP_COUNT(i, v)
 #endif
 
+/*
+ * A run of more than CX_LANE bytes is moved by a whole warp.  Left to the warp that holds the sequence, a chunk
+ * of few long sequences (a literal-heavy block: two dozen sequences of 600 literal bytes per chunk, all of them
+ * in warp 0) kept one warp busy and thirty-one waiting: 1.1 M of the 3.9 M cycles of a dense hex block.  Such runs
+ * are posted as jobs and taken by all warps in turn; what does not fit the list stays with the owning warp.
+ */
+#ifndef CX_JOBS
+#define CX_JOBS    384u
+#endif
+struct CxJob
+{
+    uint32_t    pos, len;               /* output position, bytes */
+    uint32_t    x;                      /* literals: fill byte or ~0u (copy from p); match: offset */
+    uint32_t    kind;                   /* 0: literals, 1: match */
+    const uint8_t *p;                   /* literals to copy */
+};
+
 /* shared-memory control block of one CTA */
 struct CxSh
 {
@@ -87,6 +104,8 @@ struct CxSh
     uint32_t cut;                       /* first sequence of the chunk that is not executed in it */
     uint32_t err;                       /* (sequence index << 8 | status) of the first failing sequence, ~0u: none */
     uint32_t bcast[4];
+    uint32_t njobs;                     /* jobs posted for the chunk (may exceed CX_JOBS: those stay with their warp) */
+    CxJob    jobs[CX_JOBS];
 };
 
 /* per-thread view; every field is uniform over the CTA */
@@ -297,6 +316,24 @@ CRYO_DEV void cx_bulk(Cx &cx, uint32_t ll, const uint8_t *lit, int rle_byte, uin
     if (ml)
     {
         __syncthreads();                /* the match may read the literals and the drained tail */
+        if (off == 1u && ml >= CX_HIST)
+        {
+            /* a run of one byte that covers the whole history window (the zero run of a sparse block): the ring's
+             * history is that byte, no need to read it back from global memory */
+            const uint8_t  b = CX_LDCG(cx.out + cx.pos - 1u);
+            const uint32_t w = (uint32_t) b * 0x01010101u;
+
+            team_fill_byte(cx.out + cx.pos, b, ml, tid, CX_THREADS);
+            cx.pos += ml;
+            const uint32_t lo = cx.pos - CX_HIST, a0 = lo & ~15u;
+
+            for (uint32_t a = a0 + 16u * tid; a < cx.pos; a += 16u * CX_THREADS)
+                st16(cx.ring + (a & CX_RMASK), make_uint4(w, w, w, w));
+            cx.flushed = cx.pos & ~15u;
+            cx.ring_lo = lo;
+            __syncthreads();
+            return;
+        }
         cx_bulk_match(cx, off, ml, tid);
         cx.pos += ml;
     }
@@ -330,6 +367,7 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
     {
         sh->cut = n;
         sh->err = ~0u;
+        sh->njobs = 0;
     }
     __syncthreads();
     {
@@ -361,6 +399,46 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
 
         if (bad && lane == (uint32_t) __ffs((int) bad) - 1u)
             atomicMin(&sh->err, (tid << 8) | (uint32_t) e);
+    }
+    /* runs for a whole warp are posted as jobs (not in a chunk that is one bulk operation) */
+    bool own_lit = false, own_match = false;    /* ... unless the list is full: then the owning warp moves them */
+
+    if (!alone && tid < k)
+    {
+        if (ll > CX_LANE)
+        {
+            const uint32_t slot = atomicAdd(&sh->njobs, 1u);
+
+            if (slot < CX_JOBS)
+            {
+                CxJob &j = sh->jobs[slot];
+
+                j.pos = start;
+                j.len = ll;
+                j.x = rle_byte >= 0 ? (uint32_t) rle_byte : ~0u;
+                j.kind = 0;
+                j.p = lit;
+            }
+            else
+                own_lit = true;
+        }
+        if (ml > CX_LANE && ml < CX_BIG)
+        {
+            const uint32_t slot = atomicAdd(&sh->njobs, 1u);
+
+            if (slot < CX_JOBS)
+            {
+                CxJob &j = sh->jobs[slot];
+
+                j.pos = mpos;
+                j.len = ml;
+                j.x = off;
+                j.kind = 1;
+                j.p = nullptr;
+            }
+            else
+                own_match = true;
+        }
     }
     __syncthreads();
     if (sh->err != ~0u)
@@ -412,7 +490,20 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
             for (uint32_t i = 0; i < ll; i++)
                 cx.ring[(start + i) & CX_RMASK] = lit[i];
     }
-    for (uint32_t m = __ballot_sync(CRYO_FULL, mine && ll > CX_LANE); m; m &= m - 1)
+    const uint32_t njobs = sh->njobs < CX_JOBS ? sh->njobs : CX_JOBS;
+
+    for (uint32_t q = warp; q < njobs; q += CX_WARPS)
+    {
+        const CxJob &j = sh->jobs[q];
+
+        if (j.kind != 0)
+            continue;
+        if (j.x != ~0u)
+            cx_ring_fill(cx, j.pos, (uint8_t) j.x, j.len, lane, 32);
+        else
+            cx_ring_put(cx, j.pos, j.p, j.len, lane, 32);
+    }
+    for (uint32_t m = __ballot_sync(CRYO_FULL, own_lit); m; m &= m - 1)
     {
         const int      j = __ffs((int) m) - 1;
         const uint32_t jl = __shfl_sync(CRYO_FULL, ll, j), js = __shfl_sync(CRYO_FULL, start, j);
@@ -458,12 +549,36 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
             }
         }
     }
-    for (uint32_t m = __ballot_sync(CRYO_FULL, mine && ml > CX_LANE); m; m &= m - 1)
+    /* the longer ones: a warp each, from the job list, then what did not fit it */
+    for (uint32_t q = warp;; q += CX_WARPS)
     {
-        const int      j = __ffs((int) m) - 1;
-        const uint32_t jm = __shfl_sync(CRYO_FULL, ml, j), jo = __shfl_sync(CRYO_FULL, off, j);
-        const uint32_t jp = __shfl_sync(CRYO_FULL, mpos, j);
+        uint32_t jm, jo, jp;
 
+        if (q < njobs)
+        {
+            const CxJob &j = sh->jobs[q];
+
+            if (j.kind != 1)
+                continue;
+            jm = j.len;
+            jo = j.x;
+            jp = j.pos;
+        }
+        else
+        {
+            /* the owning warp's own: one per pass of this loop */
+            const uint32_t m = __ballot_sync(CRYO_FULL, own_match);
+
+            if (m == 0)
+                break;
+            const int j = __ffs((int) m) - 1;
+
+            jm = __shfl_sync(CRYO_FULL, ml, j);
+            jo = __shfl_sync(CRYO_FULL, off, j);
+            jp = __shfl_sync(CRYO_FULL, mpos, j);
+            if ((int) lane == j)
+                own_match = false;
+        }
         if (jo > CX_FAR)
         {
             for (uint32_t i = lane; i < jm; i += 32)
@@ -508,6 +623,11 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
             CXP_COUNT(16, 1)
             uint32_t any = 0;
 
+            /* two jumps per barrier: the second one sees whatever the other warps have written meanwhile (old or
+             * new, both valid), and a quarter of the executor's time went into waiting at the round barrier */
+#pragma unroll 1
+            for (uint32_t pass = 0; pass < 2u; pass++)
+            {
 #pragma unroll
             for (uint32_t which = 0; which < CX_TPW; which++)
             {
@@ -553,7 +673,8 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
                     }
                 }
                 rows[which] = r;
-                any |= r;
+                any = pass ? any | r : any;
+            }
             }
             if (!CX_SYNC_OR(any != 0u))
                 break;

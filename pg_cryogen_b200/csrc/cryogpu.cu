@@ -2328,10 +2328,19 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
         /* work areas by the size of this call (the drop-in's calls are one block each, from every backend);
          * a missing one only selects the kernels that do without it */
         void *zpbuf = nullptr, *lzw = nullptr;
+        bool  any_zstd = false, any_lz4 = false;       /* the methods are the host's here: no zstd work area (2.2 x the
+                                                        * chunk's output) for a chunk without a zstd block */
 
-        if (zstd_kernel_variant() == 3 && dev_reserve(ctx->zp[lane], zp_bytes(std::min(chunk, n), block_size)) == CRYOGPU_OK)
+        for (size_t i = 0; i < cnt; i++)
+        {
+            any_zstd = any_zstd || methods[lo + i] == CRYOGPU_ZSTD;
+            any_lz4 = any_lz4 || methods[lo + i] == CRYOGPU_LZ4;
+        }
+        if (any_zstd && zstd_kernel_variant() == 3 &&
+            dev_reserve(ctx->zp[lane], zp_bytes(std::min(chunk, n), block_size)) == CRYOGPU_OK)
             zpbuf = ctx->zp[lane].p;
-        if (block_size <= LZ4C_MAXCAP && dev_reserve(ctx->lzw[lane], lz4c_bytes(std::min(chunk, n), ctx->sm_count)) == CRYOGPU_OK)
+        if (any_lz4 && block_size <= LZ4C_MAXCAP &&
+            dev_reserve(ctx->lzw[lane], lz4c_bytes(std::min(chunk, n), ctx->sm_count)) == CRYOGPU_OK)
             lzw = ctx->lzw[lane].p;
         cudaGetLastError();
         const size_t sp_bytes = (cnt * (SP_WORDS + 1) + 1) * 4;
@@ -2366,15 +2375,18 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
 
         k_flag_unknown_methods<<<(unsigned) ((cnt + 255) / 256), 256, 0, st>>>(
             (int32_t *) (dm + cnt * 12), cnt, (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20));
-        launch_lz4_decode(st, cnt, (int32_t *) (dm + cnt * 12), (uint8_t *) ctx->d_in[lane].p,
-                          (uint64_t *) dm, (uint32_t *) (dm + cnt * 8),
-                          (uint8_t *) ctx->d_out[lane].p, stride, block_size,
-                          (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20), lzw, ctx->sm_count);
-        launch_zstd_decode(st, cnt, (int32_t *) (dm + cnt * 12), (uint8_t *) ctx->d_in[lane].p,
-                           (uint64_t *) dm, (uint32_t *) (dm + cnt * 8),
-                           (uint8_t *) ctx->d_out[lane].p, stride, block_size,
-                           (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20), scr,
-                           ctx->predef, zpbuf, ctx->zaux[lane], ctx->zev[lane], ctx->sm_count);
+        /* (a chunk without blocks of a method does not launch that method's kernels: the drop-in's one-block call) */
+        if (any_lz4)
+            launch_lz4_decode(st, cnt, (int32_t *) (dm + cnt * 12), (uint8_t *) ctx->d_in[lane].p,
+                              (uint64_t *) dm, (uint32_t *) (dm + cnt * 8),
+                              (uint8_t *) ctx->d_out[lane].p, stride, block_size,
+                              (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20), lzw, ctx->sm_count);
+        if (any_zstd)
+            launch_zstd_decode(st, cnt, (int32_t *) (dm + cnt * 12), (uint8_t *) ctx->d_in[lane].p,
+                               (uint64_t *) dm, (uint32_t *) (dm + cnt * 8),
+                               (uint8_t *) ctx->d_out[lane].p, stride, block_size,
+                               (uint32_t *) (dm + cnt * 16), (int32_t *) (dm + cnt * 20), scr,
+                               ctx->predef, zpbuf, ctx->zaux[lane], ctx->zev[lane], ctx->sm_count);
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(hm + cnt * 16, dm + cnt * 16, cnt * 8, cudaMemcpyDeviceToHost, st));
         d2h += cnt * 8;

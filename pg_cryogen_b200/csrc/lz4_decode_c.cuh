@@ -10,8 +10,8 @@
  *
  *   stage   the next LZ4C_REGION bytes of the stream -> shared memory, one bulk copy by the
  *           copy engine (cp.async.bulk global -> shared, completion on an mbarrier)
- *   walk    lane l starts at byte 64 * (l - 1) of the region AS IF a token started there and walks to
- *           the end of its own 64-byte segment, recording the token starts it visits there (a bitmap).
+ *   walk    lane l starts at byte 60 * (l - 1) of the region AS IF a token started there and walks to
+ *           the end of its own 60-byte segment, recording the token starts it visits there (a bitmap).
  *           A chain that starts at a wrong byte meets the true chain after a few tokens and
  *           then follows it (the token stream self-synchronises), so most of every lane's walk
  *           is the true chain;
@@ -30,11 +30,19 @@
 #pragma once
 #include "cryo_cx.cuh"
 
-#define LZ4C_SEG        64u
+/*
+ * Bytes of stream per lane.  Not 64: the lanes of a warp start their walks one segment apart, and with
+ * 64-byte segments every one of their shared-memory reads fell on the same two banks (16-way conflicts
+ * for as long as the lanes advance in step -- inside the 4 030 length-extension bytes of a sparse block's
+ * zero run, for good: that walk took 245 K cycles).  15 words is odd: the starts of 32 consecutive
+ * segments fall on 32 different banks.  (The visited-token bitmap of a segment is one 64-bit word.)
+ */
+#define LZ4C_SEG        60u
 #define LZ4C_LANES      (CX_THREADS < 512u ? CX_THREADS : 512u)
 #define LZ4C_REGION     (LZ4C_SEG * LZ4C_LANES)         /* stream bytes whose tokens one round parses */
 #define LZ4C_STAGE      (LZ4C_REGION + 1024u)           /* staged bytes: the region, its 16-byte alignment, look-ahead */
 #define LZ4C_MAXHOPS    24u
+#define LZ4C_SERIAL     64u             /* tokens one thread walks before the region is parsed speculatively */
 #define LZ4C_SEQCAP     (LZ4C_REGION / 3u + 64u)        /* a sequence that is not the last takes >= 3 bytes */
 #define LZ4C_MAXCAP     ((1u << 22) - 1u)               /* record fields are 22 bits */
 #define LZ4C_BAD        0xFFFFFFFFu
@@ -68,6 +76,8 @@ struct Lz4cParse
     uint32_t    stop_pos;
     uint32_t    bad;                            /* emit found a malformed token on the true chain */
     uint32_t    saw_last;
+    uint32_t    ser_cnt, ser_pos, ser_flags;    /* the serial walk: records, where it stopped, 1: malformed 2: last sequence seen 4: it covered the region */
+    uint32_t    ffmap[(LZ4C_STAGE / 16u + 31u) / 32u];  /* bit g: the 16 staged bytes of group g are all 0xFF (and before the stream's end) */
 };
 #define LZ4C_SMEM       (LZ4C_OFF_PARSE + (uint32_t) sizeof(Lz4cParse))
 static_assert(LZ4C_SMEM <= 232448u, "one CTA's shared memory on sm_100");
@@ -76,6 +86,7 @@ struct Lz4cIn
 {
     const uint8_t *base;        /* 16-byte aligned address at or before the stream */
     const uint8_t *stage;       /* shared: base[sbase, sbase + slen) */
+    const uint32_t *ffmap;      /* shared: which 16-byte groups of the stage are all 0xFF (Lz4cParse) */
     uint32_t    sbase, slen;
     uint32_t    end;            /* stream end in `base` coordinates */
 };
@@ -123,12 +134,37 @@ CRYO_DEV bool lz4c_extension(const Lz4cIn &in, uint32_t &q, uint32_t &len)
     {
         if (q >= in.end)
             return false;
+        /* whole groups of 0xFF at once from the map: a lane alone takes ~300 cycles per 16-byte step below (a chain of
+         * dependent instructions), and every lane that starts inside a long run scans to its end */
+        {
+            const uint32_t r = q - in.sbase;
+
+            if ((r & 15u) == 0u && r < in.slen)
+            {
+                const uint32_t g = r >> 4, w = ~(in.ffmap[g >> 5] >> (g & 31u));
+                uint32_t       n = w ? (uint32_t) __ffs((int) w) - 1u : 32u;
+
+                if (n > 32u - (g & 31u))
+                    n = 32u - (g & 31u);
+                if (n)
+                {
+                    len += n * 16u * 255u;
+                    q += 16u * n;
+                    if (len > (1u << 24))
+                        return false;
+                    continue;
+                }
+            }
+        }
         const unsigned long long a = lz4c_ld8(in, q), b = lz4c_ld8(in, q + 8u);
 
         if (a == ~0ull && b == ~0ull && q + 16u <= in.end)
         {
-            len += 16u * 255u;
-            q += 16u;
+            /* sixteen more; or only up to the next group boundary of the stage, so that the map takes over */
+            const uint32_t mis = (q - in.sbase) & 15u, step = mis && q - in.sbase < in.slen ? 16u - mis : 16u;
+
+            len += step * 255u;
+            q += step;
             if (len > (1u << 24))
                 return false;
             continue;
@@ -186,6 +222,78 @@ CRYO_DEV void lz4c_tok(const Lz4cIn &in, uint32_t p, Lz4cTok &t)
     q += 2;
     if (ml == 15u && !lz4c_extension(in, q, ml))
         return;
+    t.ml = ml + 4u;
+    t.next = q;
+    t.st = 0;
+}
+
+/*
+ * The same for the one thread of the serial walk: byte loads, no 64-bit assembly -- a lone thread runs one
+ * dependent instruction every 5-6 cycles, and lz4c_tok's 150 instructions per literal-heavy token came to 800.
+ */
+CRYO_DEV void lz4c_tok_serial(const Lz4cIn &in, uint32_t p, Lz4cTok &t)
+{
+    const uint32_t tk = lz4c_byte(in, p);
+    uint32_t q = p + 1, ll = tk >> 4, ml = tk & 15u;
+
+    t.st = 2;
+    t.ml = 0;
+    t.off = 0;
+    t.next = LZ4C_BAD;
+    if (ll == 15u)
+        for (;;)
+        {
+            /* at a group boundary of the stage the map-driven scan takes over (long runs of 0xFF) */
+            if (((q - in.sbase) & 15u) == 0u)
+            {
+                if (!lz4c_extension(in, q, ll))
+                    return;
+                break;
+            }
+            if (q >= in.end)
+                return;
+            const uint32_t x = lz4c_byte(in, q++);
+
+            ll += x;
+            if (x != 255u)
+                break;
+            if (ll > (1u << 24))
+                return;
+        }
+    t.ll = ll;
+    t.lit = q;
+    if (ll > in.end - q)
+        return;
+    q += ll;
+    if (q == in.end)
+    {
+        t.st = 1;
+        t.next = in.end;
+        return;
+    }
+    if (q + 2u > in.end)
+        return;
+    t.off = lz4c_byte(in, q) | (lz4c_byte(in, q + 1u) << 8);
+    q += 2;
+    if (ml == 15u)
+        for (;;)
+        {
+            if (((q - in.sbase) & 15u) == 0u)
+            {
+                if (!lz4c_extension(in, q, ml))
+                    return;
+                break;
+            }
+            if (q >= in.end)
+                return;
+            const uint32_t x = lz4c_byte(in, q++);
+
+            ml += x;
+            if (x != 255u)
+                break;
+            if (ml > (1u << 24))
+                return;
+        }
     t.ml = ml + 4u;
     t.next = q;
     t.st = 0;
@@ -265,9 +373,60 @@ CRYO_DEV void lz4c_extend(const Lz4cIn &in, const Lz4cParse *ps, uint32_t rp, ui
  * among them.
  */
 CRYO_DEV uint32_t lz4c_parse_round(const Lz4cIn &in, Lz4cParse *ps, CxSh *sh, uint32_t rp, uint32_t re,
-                                   unsigned long long *gseq, uint32_t &next_rp, int &st, bool &saw_last, uint32_t tid)
+                                   unsigned long long *gseq, uint32_t &next_rp, int &st, bool &saw_last, uint32_t tid,
+                                   bool try_serial)
 {
     const uint32_t l = tid;
+
+    /*
+     * A region of few tokens -- long literal runs, the zero run of a sparse block -- is crossed by the true chain in a
+     * few hops, while the lanes of the speculative walk hop through literal bytes and merge nowhere.  When the region
+     * before this one was sparse, one thread first walks the chain; if LZ4C_SERIAL tokens do not cover the region the
+     * speculative parse takes over (its records overwrite these).  A lone thread needs ~760 cycles per token (a chain
+     * of dependent instructions at one per ~6 cycles), which is what the speculative parse costs per token at 55
+     * tokens per region: the serial walk only wins below that, and removes the repairs of irregular links there.
+     */
+    if (try_serial)
+    {
+        if (tid == 0)
+        {
+            uint32_t p = rp, cnt = 0, flags = 0;
+
+            while (p < re && cnt < LZ4C_SERIAL)
+            {
+                Lz4cTok t;
+
+                lz4c_tok_serial(in, p, t);
+                if (t.st == 2 || t.ll > LZ4C_MAXCAP || t.ml > LZ4C_MAXCAP)
+                {
+                    flags |= 1u;
+                    break;
+                }
+                gseq[cnt++] = (unsigned long long) t.ll | ((unsigned long long) t.ml << 22) |
+                              ((unsigned long long) t.off << 44) | ((unsigned long long) (t.st == 1) << 63);
+                if (t.st == 1)
+                    flags |= 2u;
+                p = t.next;
+                if (cnt == 16u && p - rp < 512u)
+                    break;              /* dense after all: 16 tokens in less than 512 bytes */
+            }
+            if (p >= re || (flags & 1u))
+                flags |= 4u;
+            ps->ser_cnt = cnt;
+            ps->ser_pos = p;
+            ps->ser_flags = flags;
+        }
+        __syncthreads();
+        const uint32_t flags = ps->ser_flags;
+
+        if (flags & 4u)
+        {
+            st = (flags & 1u) ? ST_INPUT : ST_OK;
+            saw_last = (flags & 2u) != 0;
+            next_rp = ps->ser_pos;
+            return ps->ser_cnt;
+        }
+    }
     const bool     lane_on = l < LZ4C_LANES && rp + l * LZ4C_SEG < re;
     const uint32_t segstart = rp + l * LZ4C_SEG;
     const uint32_t segend = segstart + LZ4C_SEG < re ? segstart + LZ4C_SEG : re;
@@ -448,6 +607,7 @@ CRYO_DEV void lz4c_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
     in.base = src - delta;
     in.end = csize + delta;
     in.stage = stage;
+    in.ffmap = ps->ffmap;
     in.sbase = 0;
     in.slen = 0;
     if (csize == 0)
@@ -465,6 +625,7 @@ CRYO_DEV void lz4c_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
         cx_prof_last = clock64();
 #endif
     uint32_t rp = delta;
+    bool     sparse = true;             /* (try the serial walk on the first region) */
 
     while (err == ST_OK && rp < in.end)
     {
@@ -499,11 +660,31 @@ CRYO_DEV void lz4c_decode_block(const uint8_t *src, uint32_t csize, uint8_t *out
         }
         phase ^= 1u;
 #endif
+        /* the all-0xFF map of the staged bytes (lz4c_extension) */
+        for (uint32_t g0 = 0; g0 < (LZ4C_STAGE / 16u + 31u) / 32u * 32u; g0 += CX_THREADS)
+        {
+            const uint32_t g = g0 + tid;
+            bool           ff = false;
+
+            if (16u * g + 16u <= in.slen && in.sbase + 16u * g + 16u <= in.end)
+            {
+                const uint4 v = ld16(stage + 16u * g);
+
+                ff = (v.x & v.y & v.z & v.w) == 0xFFFFFFFFu;
+            }
+            const uint32_t m = __ballot_sync(CRYO_FULL, ff);
+
+            if ((tid & 31u) == 0 && (g >> 5) < (LZ4C_STAGE / 16u + 31u) / 32u)
+                ps->ffmap[g >> 5] = m;
+        }
+        __syncthreads();
         CXP(0)
         const uint32_t re = in.end - rp < LZ4C_REGION ? in.end : rp + LZ4C_REGION;
         uint32_t next_rp = in.end;
         bool     saw_last = false;
-        const uint32_t nseq = lz4c_parse_round(in, ps, sh, rp, re, gseq, next_rp, err, saw_last, tid);
+        const uint32_t nseq = lz4c_parse_round(in, ps, sh, rp, re, gseq, next_rp, err, saw_last, tid, sparse);
+
+        sparse = nseq <= LZ4C_SERIAL;   /* the next region probably looks like this one */
 
         if (err != ST_OK)
             break;

@@ -29,12 +29,21 @@ def main():
                 torch.cuda.synchronize()
                 ts.append(time.perf_counter() - t0)
             ts = np.sort(np.array(ts[10:])) * 1e6
+            # the call the drop-in makes: host pointers, one block (cryogpu_decompress_host behind cryo_decompress)
+            hs = []
+            out = np.zeros((1, 1 << 20), dtype=np.uint8)
+            for it in range(reps // 2 + 5):
+                t0 = time.perf_counter()
+                g.decompress_host([method], c, out=out)
+                hs.append(time.perf_counter() - t0)
+            hs = np.sort(np.array(hs[5:])) * 1e6
+            okh = np.array_equal(out[0], blk[0])
             rb, ro, rs = ref.pack(c)
             ref.decompress([method], rb, ro, rs, nthreads=1)
             cpu1 = ref.decompress([method], rb, ro, rs, nthreads=1, reps=5)[2] / 5 * 1e6
             ok = int(d_st[0].item()) == 0 and np.array_equal(d_dst[0].cpu().numpy(), blk[0])
             print(f"one block {'lz4 ' if method == 0 else 'zstd'} {kind}/{pl:8s} csize {len(c[0]):7d}: GPU p50 {ts[len(ts)//2]:8.1f} us p99 {ts[int(len(ts)*0.99)]:8.1f} us"
-                  f" | reference CPU 1 thread {cpu1:8.1f} us | exact={ok}", flush=True)
+                  f" | host-pointer call p50 {hs[len(hs)//2]:8.1f} us | reference CPU 1 thread {cpu1:8.1f} us | exact={ok and okh}", flush=True)
 
 if __name__ == "__main__":
     main()
