@@ -44,6 +44,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# hardware work queues for the streams of the process (default 8): the pipeline's three streams must not share one
+# (cryogpu_init sets this too, but torch creates the CUDA context first here)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 CRYO_BLCKSZ = 1 << 20
 COMP_LZ4, COMP_ZSTD = 0, 1

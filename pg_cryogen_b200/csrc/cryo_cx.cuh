@@ -45,7 +45,8 @@
 #define CX_HIST    65536u               /* history reloaded into the ring after a bulk operation (LZ4: offsets <= 65535) */
 #define CX_FAR     49152u               /* a match from further back is copied when it is met (CX_FAR + CX_BIG < 65536, CX_FAR >= CX_SPAN) */
 #define CX_PAT     1024u                /* pattern staging for periodic fills (k * off >= 512, + 32) */
-#define CX_TPW     ((CX_SPAN / 512u + CX_WARPS - 1u) / CX_WARPS)    /* 512-byte tiles of a chunk per warp (1 with 1 024 threads) */
+#define CX_TPW     ((CX_SPAN / 512u + CX_WARPS - 1u) / CX_WARPS)    /* sixteen 32-byte rows of a chunk per warp, times this (1 with 1 024 threads) */
+#define CX_ROWSTEP (32u * CX_WARPS)     /* bytes between two rows of one warp */
 
 #ifdef CRYO_EMU
 #define CX_LDCG(p) (*(p))
@@ -611,12 +612,23 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
      * the end of a round only tells whether any byte is left (bar.red.or).
      */
     {
-        const uint32_t ntiles = (kpos - pos0 + 511u) >> 9;
-        uint32_t       rows[CX_TPW];    /* per tile of this warp (warp, warp + CX_WARPS, ...): rows with unresolved bytes */
+        /* rows of 32 bytes are dealt out to the warps in turn (row R to warp R mod CX_WARPS), so that a chunk of any
+         * size keeps every warp busy: with one 512-byte tile per warp a 9 KB chunk of a dense block left 14 of 32 warps
+         * idle.  Bit b of rows[which]: row warp + CX_WARPS * (16 * which + b) has unresolved bytes. */
+        const uint32_t nrows = (kpos - pos0 + 31u) >> 5;
+        uint32_t       rows[CX_TPW];
 
 #pragma unroll
         for (uint32_t which = 0; which < CX_TPW; which++)
-            rows[which] = warp + which * CX_WARPS < ntiles ? 0xFFFFu : 0u;
+        {
+            uint32_t m = 0;
+
+#pragma unroll
+            for (uint32_t b = 0; b < 16; b++)
+                if (warp + CX_WARPS * (16u * which + b) < nrows)
+                    m |= 1u << b;
+            rows[which] = m;
+        }
 
         for (;;)
         {
@@ -632,7 +644,7 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
             for (uint32_t which = 0; which < CX_TPW; which++)
             {
                 uint32_t       r = rows[which];
-                const uint32_t base = ((warp + which * CX_WARPS) << 9) + lane;
+                const uint32_t base = ((warp + CX_WARPS * 16u * which) << 5) + lane;    /* byte of this lane in row slot 0 */
 
                 if (r == 0)
                     continue;
@@ -646,28 +658,28 @@ CRYO_DEV uint32_t cx_chunk(Cx &cx, uint32_t n, uint32_t ll, uint32_t ml, uint32_
 
 #pragma unroll
                     for (uint32_t q = 0; q < 4; q++)
-                        d[q] = cx.dl[base + 32u * (h + q)];
+                        d[q] = cx.dl[base + CX_ROWSTEP * (h + q)];
 #pragma unroll
                     for (uint32_t q = 0; q < 4; q++)
                     {
-                        const uint32_t idx = base + 32u * (h + q);
+                        const uint32_t idx = base + CX_ROWSTEP * (h + q);
 
                         ds[q] = (d[q] != 0u && d[q] <= idx) ? (uint32_t) cx.dl[idx - d[q]] : 0u;
                     }
                     CX_COMPILER_FENCE();        /* the values are read after the distances */
 #pragma unroll
                     for (uint32_t q = 0; q < 4; q++)
-                        v[q] = (d[q] != 0u && ds[q] == 0u) ? cx_src(cx, pos0 + base + 32u * (h + q) - d[q], lo) : (uint8_t) 0;
+                        v[q] = (d[q] != 0u && ds[q] == 0u) ? cx_src(cx, pos0 + base + CX_ROWSTEP * (h + q) - d[q], lo) : (uint8_t) 0;
 #pragma unroll
                     for (uint32_t q = 0; q < 4; q++)
                         if (d[q] != 0u && ds[q] == 0u)
-                            cx.ring[(pos0 + base + 32u * (h + q)) & CX_RMASK] = v[q];
+                            cx.ring[(pos0 + base + CX_ROWSTEP * (h + q)) & CX_RMASK] = v[q];
                     __threadfence_block();      /* the values before the cleared distances */
 #pragma unroll
                     for (uint32_t q = 0; q < 4; q++)
                     {
                         if (d[q] != 0u)
-                            cx.dl[base + 32u * (h + q)] = (uint16_t) (ds[q] == 0u ? 0u : d[q] + ds[q]);
+                            cx.dl[base + CX_ROWSTEP * (h + q)] = (uint16_t) (ds[q] == 0u ? 0u : d[q] + ds[q]);
                         if (__ballot_sync(CRYO_FULL, d[q] != 0u && ds[q] != 0u) == 0u)
                             r &= ~(1u << (h + q));
                     }

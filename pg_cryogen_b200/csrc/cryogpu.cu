@@ -216,16 +216,31 @@ k_zp_prefill(const ZpArgs a)
      */
     __shared__ __align__(128) uint8_t pat[ZP0_CHUNK];
     __shared__ uint32_t spec[ZP_MAXB];
+    __shared__ uint32_t next_f;
     int      cur = -1;                  /* byte the pattern holds */
     uint32_t prev_f = ~0u, prev_did = 0;
+    uint32_t *counter = reinterpret_cast<uint32_t *>(a.seq_alloc) + 4;  /* zeroed with seq_alloc */
 
-    for (uint32_t f = blockIdx.x; f < a.n; f += gridDim.x)
+    /*
+     * Frames are handed out by a counter, not by blockIdx: the CTAs of this kernel do not all become resident at
+     * once beside the executor's (in some states of the process a third of them start a millisecond late, and
+     * with a fixed share of the frames each the stage then took 1.76 ms instead of 0.75, profiles/README.md); the
+     * ones that are running take whatever is next.
+     */
+    for (;;)
     {
+        __syncthreads();
+        if (threadIdx.x == 0)
+            next_f = atomicAdd(counter, 1u);
+        __syncthreads();
+        const uint32_t f = next_f;
+
+        if (f >= a.n)
+            break;
         const uint32_t nb = a.fr[(size_t) f * ZP_FF];
         const uint8_t *in = a.src + a.src_off[f];
         uint8_t *out = a.dst + (size_t) f * a.dst_stride;
 
-        __syncthreads();
         if (threadIdx.x == 0)
             zp_frame_positions(a, f, spec);     /* exact: stage 3b has measured the Compressed blocks */
         __syncthreads();
@@ -704,7 +719,7 @@ zp_carve(ZpArgs &a, void *base, size_t n, uint32_t cap)
     p += zp_al(n * 4);
     a.seqbase = (uint64_t *) p;
     p += zp_al(n * 8);
-    a.seq_alloc = (unsigned long long *) p;         /* + 8: work counter of k_zp_execute_c, + 12: cxcount */
+    a.seq_alloc = (unsigned long long *) p;         /* + 8: work counter of k_zp_execute_c, + 12: cxcount, + 16: work counter of k_zp_prefill */
     a.cxcount = (uint32_t *) p + 3;
     p += 256;
     a.blk = (uint32_t *) p;
@@ -783,7 +798,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             a.pf_hint |= 4u;
         else if (exec_choice == 1)
             a.pf_hint |= 8u;
-        cudaMemsetAsync(a.seq_alloc, 0, 16, st);
+        cudaMemsetAsync(a.seq_alloc, 0, 32, st);       /* + the work counters of k_zp_execute_c and k_zp_prefill */
         k_zp_parse<<<(unsigned) ((n + 31) / 32), 32, 0, st>>>(a);
         /*
          * literals (st) and sequences (aux 0) are independent of each other and bound by latency.
@@ -996,6 +1011,27 @@ host_reserve(DevBuf &b, size_t bytes)
     return CRYOGPU_OK;
 }
 
+/*
+ * The side streams of lane l of the pipeline (and, for lane 1, the second stream of the host calls).  Lane 1 is
+ * made when a host call first needs a second chunk in flight: every stream alive takes a share of the hardware
+ * work queues (see cryogpu_init).  zaux[l][1] carries the raw / RLE stage, whose CTAs must become resident
+ * before the executor's (profiles/r01e_arrangements.txt): highest priority, so they win whenever an SM has room.
+ */
+static int
+make_lane_streams(cryogpu_ctx *ctx, int l)
+{
+    int lo_pri = 0, hi_pri = 0;
+
+    if (ctx->zaux[l][0])
+        return CRYOGPU_OK;
+    CU(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    if (l == 1 && !ctx->stream2)
+        CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++)
+        CU(cudaStreamCreateWithPriority(&ctx->zaux[l][k], cudaStreamNonBlocking, k == 1 ? hi_pri : lo_pri));
+    return CRYOGPU_OK;
+}
+
 static int
 set_kernel_attrs(cryogpu_ctx *ctx)
 {
@@ -1083,6 +1119,13 @@ cryogpu_init(int device, cryogpu_ctx **out)
     if (!out)
         return fail(CRYOGPU_E_ARG, "cryogpu_init: ctx is NULL");
     *out = nullptr;
+    /*
+     * Streams are mapped onto hardware work queues, 8 by default; streams that share a queue serialise, and the
+     * pipeline wants its three streams (caller's, sequence chain, raw / RLE stage) on different queues.  Only
+     * effective before the process's CUDA context exists (a PostgreSQL backend's first codec call); a host
+     * application that initialises CUDA earlier sets the variable itself (bench.py does).
+     */
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int n = cryogpu_device_count();
 
     if (n <= 0)
@@ -1101,7 +1144,6 @@ cryogpu_init(int device, cryogpu_ctx **out)
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->busy, cudaEventDisableTiming) != cudaSuccess)
@@ -1110,21 +1152,13 @@ cryogpu_init(int device, cryogpu_ctx **out)
         return fail(CRYOGPU_E_CUDA, "stream/event creation failed: %s",
                     cudaGetErrorString(cudaGetLastError()));
     }
+    if (make_lane_streams(ctx, 0) != CRYOGPU_OK)
+    {
+        delete ctx;
+        return CRYOGPU_E_CUDA;
+    }
     for (int l = 0; l < 2; l++)
     {
-        for (int k = 0; k < 2; k++)
-        {
-            /* zaux[l][1] carries the raw / RLE stage, whose CTAs must become resident before the executor's
-             * (profiles/r01e_arrangements.txt): highest priority, so they win whenever an SM has room */
-            int lo_pri = 0, hi_pri = 0;
-
-            cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
-            if (cudaStreamCreateWithPriority(&ctx->zaux[l][k], cudaStreamNonBlocking, k == 1 ? hi_pri : lo_pri) != cudaSuccess)
-            {
-                delete ctx;
-                return fail(CRYOGPU_E_CUDA, "stream creation failed: %s", cudaGetErrorString(cudaGetLastError()));
-            }
-        }
         for (int k = 0; k < 4; k++)
             if (cudaEventCreateWithFlags(&ctx->zev[l][k], cudaEventDisableTiming) != cudaSuccess)
             {
@@ -1150,7 +1184,8 @@ cryogpu_shutdown(cryogpu_ctx *ctx)
         return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->stream2);
+    if (ctx->stream2)
+        cudaStreamSynchronize(ctx->stream2);
     cudaFree(ctx->scratch.p);
     cudaFree(ctx->zp[0].p);
     cudaFree(ctx->zp[1].p);
@@ -1175,11 +1210,13 @@ cryogpu_shutdown(cryogpu_ctx *ctx)
         cudaEventDestroy(ctx->ev[i]);
     }
     cudaStreamDestroy(ctx->stream);
-    cudaStreamDestroy(ctx->stream2);
+    if (ctx->stream2)
+        cudaStreamDestroy(ctx->stream2);
     for (int l = 0; l < 2; l++)
     {
         for (int k = 0; k < 2; k++)
-            cudaStreamDestroy(ctx->zaux[l][k]);
+            if (ctx->zaux[l][k])
+                cudaStreamDestroy(ctx->zaux[l][k]);
         for (int k = 0; k < 4; k++)
             cudaEventDestroy(ctx->zev[l][k]);
     }
@@ -2214,6 +2251,13 @@ cryogpu_decompress_host(cryogpu_ctx *ctx, size_t n, const int32_t *methods,
     /* sparse return pays when a batch is worth a second kernel and blocks have whole pages */
     const bool     sparse = sparse_enabled(ctx) && n >= 4 && block_size >= 16 * SP_PAGE &&
                             block_size <= SP_MAXPAGES * SP_PAGE;
+    if (n > chunk)
+    {
+        int rc = make_lane_streams(ctx, 1);     /* a second chunk will be in flight */
+
+        if (rc != CRYOGPU_OK)
+            return rc;
+    }
     cudaStream_t   lanes[2] = {ctx->stream, ctx->stream2};
     size_t         pending_lo[2] = {0, 0}, pending_n[2] = {0, 0};
     uint64_t       h2d = 0, d2h = 0;
@@ -2447,6 +2491,13 @@ cryogpu_compress_host(cryogpu_ctx *ctx, size_t n, int method, int level_or_accel
     const size_t   lane_scratch = (compress_scratch_bytes(method, block_size, std::min(chunk, n), ctx->sm_count) + 255) &
                                   ~(size_t) 255;
     const bool     src_pinned = is_pinned(src[0]);
+    if (n > chunk)
+    {
+        int rc = make_lane_streams(ctx, 1);     /* a second chunk will be in flight */
+
+        if (rc != CRYOGPU_OK)
+            return rc;
+    }
     cudaStream_t   lanes[2] = {ctx->stream, ctx->stream2};
     size_t         pending_lo[2] = {0, 0}, pending_n[2] = {0, 0};
 

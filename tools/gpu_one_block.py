@@ -1,6 +1,7 @@
 """dev probe: latency of the call the reference makes (cache.c:178: ONE block per call) through
 cryogpu_decompress_device, per method and block kind, beside the reference's compression.c on one host thread."""
 import os, sys, time
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import numpy as np, torch
 sys.path.insert(0, ".")
 from pg_cryogen_b200 import CryoGPU, blockgen as bg

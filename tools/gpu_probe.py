@@ -1,13 +1,21 @@
 """dev probe: time batched decode on the GPU (not a bench; see bench.py)."""
 import os, sys, time
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import numpy as np, torch
 sys.path.insert(0, ".")
 from pg_cryogen_b200 import CryoGPU, blockgen as bg
 from pg_cryogen_b200.codec import pack_chunks
 from oracle import ref
 
+_shared = None
+
 def probe(method, level, kind, payload, n):
-    g = CryoGPU(0)
+    global _shared
+    if os.environ.get("PROBE_SHARED_CTX"):
+        _shared = _shared or CryoGPU(0)
+        g = _shared
+    else:
+        g = CryoGPU(0)
     uniq = min(n, 32)
     blocks = bg.make_blocks(kind, payload, 0, uniq)
     comp, sizes, _ = ref.compress(method, level, blocks, nthreads=8)
@@ -34,7 +42,7 @@ def probe(method, level, kind, payload, n):
     good = np.array_equal(d_dst[:uniq].cpu().numpy(), blocks)
     gbs = n * (1 << 20) / ms / 1e6
     alg = (n * (1 << 20) + int(sz.astype(np.int64).sum())) / ms / 1e6
-    print(f"method={method} level={level} {kind}/{payload} n={n}: {ms:.3f} ms  {gbs:.1f} GB/s out, {alg:.1f} GB/s algorithmic, status_ok={ok} exact={good}", flush=True)
+    print(f"method={method} level={level} {kind}/{payload} n={n}: {ms:.3f} ms  {gbs:.1f} GB/s out, {alg:.1f} GB/s algorithmic, status_ok={ok} exact={good}" + (f" dst=0x{d_dst.data_ptr():x} src=0x{d_src.data_ptr():x}" if os.environ.get("PROBE_PTRS") else ""), flush=True)
 
 if __name__ == "__main__":
     # usage: gpu_probe.py N [method:level:kind:payload ...]

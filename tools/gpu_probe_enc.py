@@ -1,5 +1,6 @@
 """dev probe: time batched compression on the GPU and report the ratio vs the reference."""
 import os, sys
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import numpy as np, torch
 sys.path.insert(0, ".")
 from pg_cryogen_b200 import CryoGPU, blockgen as bg

@@ -1,6 +1,7 @@
 """dev probe (BASELINE.json configs[4]): latency of small mixed batches through cryogpu_decompress_device,
 p50 / p99 over 200 calls per batch size, for the default zstd path and the warp-per-frame kernel."""
 import os, sys, time
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import numpy as np, torch
 sys.path.insert(0, ".")
 from pg_cryogen_b200 import CryoGPU, blockgen as bg
