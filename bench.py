@@ -367,9 +367,10 @@ def next_row_cells(gpu, chunks, want, threads):
     bi, bo = gpu.last_transfer_bytes()
     # the reference: cryo_decompress + the item walk of cryo_getnextslot, all cores (the walk is negligible beside the codec)
     cpu_all, _ = cpu_reference_decompress(METHOD, chunks[: max(64, threads * 16)], threads, 2.0)
+    cpu_one, _ = cpu_reference_decompress(METHOD, chunks[:64], 1, 1.0)     # one backend = one thread
     cells.append({"row": "f-4 count pushdown", "api": "cryogpu_decompress_count_host", "blocks": n, "tuples_counted": int(nt.sum()),
                   "value": n * CRYO_BLCKSZ / t / 1e9, "unit": "GB/s of decompressed data scanned", "h2d_bytes": bi, "d2h_bytes": bo,
-                  "cpu_reference_all_cores": cpu_all, "cores": threads})
+                  "cpu_reference_all_cores": cpu_all, "cpu_reference_one_thread": cpu_one, "cores": threads})
     # ---- f-1: the same blocks as page chains on "disk" (8 KiB pages, first page header 48 bytes, others 32)
     m = min(n, 1024)
     npages = [opg.pages_needed(len(c)) for c in chunks[:m]]
@@ -389,7 +390,96 @@ def next_row_cells(gpu, chunks, want, threads):
     cells.append({"row": "f-1 decompress from page chains", "api": "cryogpu_decompress_pages_host (pageable pages in, pageable blocks out, "
                   "every byte written; includes the Python binding's per-call array setup)", "blocks": m, "pages": int(sum(npages)),
                   "value": m * CRYO_BLCKSZ / t / 1e9, "unit": "GB/s", "bit_exact_all_blocks": True,
-                  "cpu_reference_all_cores": cpu_all, "cores": threads})
+                  "cpu_reference_all_cores": cpu_all, "cpu_reference_one_thread": cpu_one, "cores": threads})
+    cells += batched_caller_cells(gpu, threads)
+    return cells
+
+
+def batched_caller_cells(gpu, threads):
+    """f-3 / f-2 through pg_cryogen_b200/host/cryo_batch.c over its in-memory relation: COPY of S-kind tuples with
+    64 blocks per flush call, then a sequential scan with a read-ahead of 64 blocks."""
+    import ctypes as C
+    from oracle import ref
+    from pg_cryogen_b200 import blockgen as bg
+
+    class RelOps(C.Structure):
+        _fields_ = [("rel", C.c_void_p), ("nblocks", C.c_void_p), ("read_page", C.c_void_p), ("extend", C.c_void_p)]
+    L = C.CDLL(os.path.join(ROOT, "pg_cryogen_b200", "libcryo_batch.so"))
+    L.cryo_memrel_create.restype = C.c_void_p
+    L.cryo_memrel_create.argtypes = [C.c_uint32]
+    L.cryo_memrel_ops.restype = RelOps
+    L.cryo_memrel_ops.argtypes = [C.c_void_p]
+    L.cryo_memrel_destroy.argtypes = [C.c_void_p]
+    L.cryo_batch_writer_create.restype = C.c_void_p
+    L.cryo_batch_writer_create.argtypes = [C.c_void_p, C.POINTER(RelOps), C.c_int, C.c_int, C.c_int, C.c_uint32]
+    L.cryo_batch_insert_many.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.cryo_batch_flush.argtypes = [C.c_void_p]
+    L.cryo_batch_writer_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
+    L.cryo_batch_writer_destroy.argtypes = [C.c_void_p]
+    L.cryo_batch_writer_flush_seconds.restype = C.c_double
+    L.cryo_batch_writer_flush_seconds.argtypes = [C.c_void_p]
+    L.cryo_batch_cache_create.restype = C.c_void_p
+    L.cryo_batch_cache_create.argtypes = [C.c_void_p, C.c_int]
+    L.cryo_batch_cache_destroy.argtypes = [C.c_void_p]
+    L.cryo_batch_cache_stats.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint64)] * 3
+    L.cryo_batch_scan_begin.restype = C.c_void_p
+    L.cryo_batch_scan_begin.argtypes = [C.c_void_p, C.POINTER(RelOps), C.c_int]
+    L.cryo_batch_scan_next.restype = C.POINTER(C.c_uint8)
+    L.cryo_batch_scan_next.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+    L.cryo_batch_scan_end.argtypes = [C.c_void_p]
+    nblocks, per = 512, bg.KINDS["S"][0]
+    tuples = np.concatenate([bg.make_tuples("S", "hex", 5000 + b, per) for b in range(nblocks)])
+    rel = L.cryo_memrel_create(nblocks * 4 + 64)
+    ops = L.cryo_memrel_ops(rel)
+    cells = []
+    w = L.cryo_batch_writer_create(gpu.handle, C.byref(ops), METHOD, LEVEL, 64, 7)
+    t0 = time.perf_counter()
+    rc = L.cryo_batch_insert_many(w, tuples.ctypes.data, tuples.shape[1], tuples.shape[0])
+    rc = rc or L.cryo_batch_flush(w)
+    t = time.perf_counter() - t0
+    assert rc == 0
+    calls, blocks, pages = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    L.cryo_batch_writer_stats(w, C.byref(calls), C.byref(blocks), C.byref(pages))
+    t_flush = L.cryo_batch_writer_flush_seconds(w)
+    L.cryo_batch_writer_destroy(w)
+    plain = np.stack([bg.pack_block(tuples[b * per:(b + 1) * per]) for b in range(min(64, nblocks))])
+    cpu_c, _ = cpu_reference_compress(METHOD, LEVEL, plain, threads, 1.0)
+    cpu_c1, _ = cpu_reference_compress(METHOD, LEVEL, plain[:16], 1, 0.5)
+    cells.append({"row": "f-3 batched flush on COPY", "api": "cryo_batch_insert / cryo_batch_flush (host/cryo_batch.c) -> "
+                  "cryogpu_compress_pages_alloc_host, 64 blocks per device call; value = the flush calls (compress, page "
+                  "split, copies both ways), as the reference beside it is cryo_compress alone",
+                  "blocks": int(blocks.value), "device_calls": int(calls.value), "pages_written": int(pages.value),
+                  "value": blocks.value * CRYO_BLCKSZ / t_flush / 1e9, "unit": "GB/s of block data",
+                  "value_with_tuple_inserts": blocks.value * CRYO_BLCKSZ / t / 1e9,
+                  "cpu_reference_all_cores": cpu_c, "cpu_reference_one_thread": cpu_c1, "cores": threads})
+    cache = L.cryo_batch_cache_create(gpu.handle, 128)
+    for attempt in range(2):                            # the second pass is the timed one (work areas are warm)
+        L.cryo_batch_cache_destroy(cache)
+        cache = L.cryo_batch_cache_create(gpu.handle, 128)
+        scan = L.cryo_batch_scan_begin(cache, C.byref(ops), 64)
+        bno, xid, err = C.c_uint32(0), C.c_uint32(0), C.c_int(0)
+        got, first = 0, None
+        t0 = time.perf_counter()
+        while True:
+            d = L.cryo_batch_scan_next(scan, C.byref(bno), C.byref(xid), C.byref(err))
+            if not d:
+                break
+            if first is None:
+                first = np.ctypeslib.as_array(d, shape=(CRYO_BLCKSZ,)).copy()
+            got += 1
+        t = time.perf_counter() - t0
+        L.cryo_batch_scan_end(scan)
+    assert err.value == 0 and got == blocks.value and np.array_equal(first, plain[0]), (err.value, got)
+    L.cryo_batch_cache_stats(cache, C.byref(calls), C.byref(blocks), C.byref(pages))
+    pc = ref.compress(METHOD, LEVEL, plain, nthreads=threads)[0]
+    cpu_d, _ = cpu_reference_decompress(METHOD, pc, threads, 1.0)
+    cpu_d1, _ = cpu_reference_decompress(METHOD, pc[:16], 1, 0.5)
+    cells.append({"row": "f-2 batched cache fill / read-ahead", "api": "cryo_batch_scan_next (host/cryo_batch.c) -> "
+                  "cryogpu_decompress_pages_host, read-ahead 64 blocks per device call, every byte of every block written",
+                  "blocks": got, "device_calls": int(calls.value), "value": got * CRYO_BLCKSZ / t / 1e9, "unit": "GB/s",
+                  "cpu_reference_all_cores": cpu_d, "cpu_reference_one_thread": cpu_d1, "cores": threads})
+    L.cryo_batch_cache_destroy(cache)
+    L.cryo_memrel_destroy(rel)
     return cells
 
 

@@ -1550,6 +1550,9 @@ cryogpu_compress_device(cryogpu_ctx *ctx, size_t n, int method, int level_or_acc
 
 /* ------------------------------------------------------------ page chains */
 
+static HostPool *host_pool(cryogpu_ctx *ctx);
+static bool is_pinned(const void *p);
+
 extern "C" uint32_t
 cryogpu_pages_needed(uint64_t compressed_size)
 {
@@ -1660,7 +1663,7 @@ cryogpu_compress_pages_device(cryogpu_ctx *ctx, size_t n, int method, int level_
  * pinned memory in chunks, the device calls above, results back.  Sized for the cache-fill and flush calls
  * (tens of blocks), not pipelined like cryogpu_decompress_host.
  */
-#define PG_HOST_CHUNK 32u
+#define PG_HOST_CHUNK 128u
 
 extern "C" int
 cryogpu_decompress_pages_host(cryogpu_ctx *ctx, size_t n, const void *const *pages, const uint32_t *page_blkno,
@@ -1713,12 +1716,14 @@ cryogpu_decompress_pages_host(cryogpu_ctx *ctx, size_t n, const void *const *pag
         uint8_t  *ho = (uint8_t *) ctx->h_out[0].p, *dout = (uint8_t *) ctx->d_out[0].p;
         uint32_t *h_slot = (uint32_t *) (hi + pg_bytes), *h_blk = h_slot + ne, *h_coff = h_blk + ne;
 
-        for (uint32_t e = 0; e < ne; e++)
-        {
-            memcpy(hi + (size_t) e * PG_PAGE, pages[e0 + e], PG_PAGE);
-            h_slot[e] = e;
-            h_blk[e] = page_blkno[e0 + e];
-        }
+        host_pool(ctx)->run((ne + 255) / 256, [&](size_t part) {
+            for (uint32_t e = (uint32_t) part * 256u; e < ne && e < (uint32_t) (part + 1) * 256u; e++)
+            {
+                memcpy(hi + (size_t) e * PG_PAGE, pages[e0 + e], PG_PAGE);
+                h_slot[e] = e;
+                h_blk[e] = page_blkno[e0 + e];
+            }
+        });
         for (size_t i = 0; i <= cnt; i++)
             h_coff[i] = chain_off[lo + i] - e0;
         CU(cudaMemcpyAsync(di, hi, pg_bytes + meta_in, cudaMemcpyHostToDevice, ctx->stream));
@@ -1731,7 +1736,16 @@ cryogpu_decompress_pages_host(cryogpu_ctx *ctx, size_t n, const void *const *pag
                                              (uint32_t *) (dm + cnt * 12), ctx->stream);
         if (rc != CRYOGPU_OK)
             return rc;
-        CU(cudaMemcpyAsync(ho, dout, cnt * stride + meta_out, cudaMemcpyDeviceToHost, ctx->stream));
+        const bool dst_pinned = is_pinned(dst[lo]);     /* the batched cache's slots are: straight into them */
+
+        if (dst_pinned)
+        {
+            CU(cudaMemcpyAsync(ho + cnt * stride, dout + cnt * stride, meta_out, cudaMemcpyDeviceToHost, ctx->stream));
+            for (size_t i = 0; i < cnt; i++)
+                CU(cudaMemcpyAsync(dst[lo + i], dout + i * stride, block_size, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        else
+            CU(cudaMemcpyAsync(ho, dout, cnt * stride + meta_out, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         d2h += cnt * stride + meta_out;
         const uint8_t *hm = ho + cnt * stride;
@@ -1741,9 +1755,12 @@ cryogpu_decompress_pages_host(cryogpu_ctx *ctx, size_t n, const void *const *pag
         memcpy(methods + lo, hm + cnt * 8, cnt * 4);
         if (comp_size)
             memcpy(comp_size + lo, hm + cnt * 12, cnt * 4);
-        for (size_t i = 0; i < cnt; i++)
-            if (status[lo + i] == CRYOGPU_ST_OK)
-                memcpy(dst[lo + i], ho + i * stride, out_size[lo + i]);
+        /* into the caller's blocks with the context's host threads (one thread moves ~6 GB/s) */
+        if (!dst_pinned)
+            host_pool(ctx)->run(cnt, [&](size_t i) {
+                if (status[lo + i] == CRYOGPU_ST_OK)
+                    memcpy(dst[lo + i], ho + i * stride, out_size[lo + i]);
+            });
     }
     ctx->last_h2d = h2d;
     ctx->last_d2h = d2h;
@@ -1875,9 +1892,14 @@ cryogpu_compress_pages_alloc_host(cryogpu_ctx *ctx, size_t n, int method, int le
         uint32_t *h_blk = (uint32_t *) (hi + cnt * stride);
         const uint8_t *hm = ho + cnt * pstride;
 
-        for (size_t i = 0; i < cnt; i++)
-            memcpy(hi + i * stride, src[lo + i], block_size);
-        CU(cudaMemcpyAsync(di, hi, cnt * stride, cudaMemcpyHostToDevice, ctx->stream));
+        if (is_pinned(src[lo]))                         /* the batched writer's blocks are */
+            for (size_t i = 0; i < cnt; i++)
+                CU(cudaMemcpyAsync(di + i * stride, src[lo + i], block_size, cudaMemcpyHostToDevice, ctx->stream));
+        else
+        {
+            host_pool(ctx)->run(cnt, [&](size_t i) { memcpy(hi + i * stride, src[lo + i], block_size); });
+            CU(cudaMemcpyAsync(di, hi, cnt * stride, cudaMemcpyHostToDevice, ctx->stream));
+        }
         h2d += cnt * stride;
         CU(cudaStreamWaitEvent(ctx->stream, ctx->busy, 0));
         rc = compress_device_locked(ctx, ctx->stream, cnt, method, level_or_accel, di, stride, block_size, comp, cstride,

@@ -2,10 +2,12 @@
  * cryo_batch.c -- batched cache fill / read-ahead and batched flush around libcryogpu (cryo_batch.h).
  * Host logic only: every byte of codec work happens in libcryogpu's kernels.
  */
+#define _POSIX_C_SOURCE 200809L     /* clock_gettime */
 #include "cryo_batch.h"
 
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #define INVALID_BLOCK 0xFFFFFFFFu
 /* page header fields, storage.h:26-67 */
@@ -382,6 +384,7 @@ struct CryoBatchWriter
     int         nfull;
     int         started;        /* the current block has a reserved page */
     uint64_t    calls, blocks, pages;
+    double      flush_seconds;  /* spent in the device calls (compress + split + copies), for benchmarks */
 };
 
 /* cryo_init_page, storage.c:15-21 */
@@ -464,8 +467,13 @@ flush_blocks(CryoBatchWriter *w, int n)
 
     if (np && st)
     {
+        struct timespec t0, t1;
+
+        clock_gettime(CLOCK_MONOTONIC, &t0);
         rc = cryogpu_compress_pages_alloc_host(w->gpu, (size_t) n, w->method, w->level, (const void *const *) w->data,
                                                CRYO_BATCH_BLCKSZ, w->target_block, alloc_cb, ptr_cb, w, w->xid, np, np + n, st);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        w->flush_seconds += (double) (t1.tv_sec - t0.tv_sec) + 1e-9 * (double) (t1.tv_nsec - t0.tv_nsec);
         w->calls++;
         for (int i = 0; rc == 0 && i < n; i++)
         {
@@ -510,6 +518,22 @@ cryo_batch_insert(CryoBatchWriter *w, const void *tuple, uint32_t len, uint32_t 
     return 0;
 }
 
+/* `count` tuples of `len` bytes each, back to back at `tuples`: the loop of cryo_multi_insert_internal (pg_cryogen.c:626-650) */
+int
+cryo_batch_insert_many(CryoBatchWriter *w, const void *tuples, uint32_t len, uint32_t count)
+{
+    uint32_t tb, tp;
+
+    for (uint32_t i = 0; i < count; i++)
+    {
+        int rc = cryo_batch_insert(w, (const char *) tuples + (size_t) i * len, len, &tb, &tp);
+
+        if (rc != 0)
+            return rc;
+    }
+    return 0;
+}
+
 int
 cryo_batch_flush(CryoBatchWriter *w)
 {
@@ -529,6 +553,12 @@ cryo_batch_writer_stats(const CryoBatchWriter *w, uint64_t *calls, uint64_t *blo
         *blocks = w->blocks;
     if (pages)
         *pages = w->pages;
+}
+
+double
+cryo_batch_writer_flush_seconds(const CryoBatchWriter *w)
+{
+    return w->flush_seconds;
 }
 
 void

@@ -89,9 +89,11 @@ CryoBatchWriter *cryo_batch_writer_create(cryogpu_ctx *gpu, const CryoRelOps *op
  * block is queued (not flushed) and a new one started.  Returns 0 and the item pointer (block, 1-based
  * position), or -1 when the tuple cannot fit an empty block. */
 int         cryo_batch_insert(CryoBatchWriter *w, const void *tuple, uint32_t len, uint32_t *tid_block, uint32_t *tid_pos);
+int         cryo_batch_insert_many(CryoBatchWriter *w, const void *tuples, uint32_t len, uint32_t count);
 /* flush_modify_state for everything queued plus the current block: one device call.  Returns 0 or a cryogpu call code. */
 int         cryo_batch_flush(CryoBatchWriter *w);
 void        cryo_batch_writer_stats(const CryoBatchWriter *w, uint64_t *calls, uint64_t *blocks, uint64_t *pages);
+double      cryo_batch_writer_flush_seconds(const CryoBatchWriter *w);   /* time spent in the device calls */
 void        cryo_batch_writer_destroy(CryoBatchWriter *w);
 
 /* an in-memory relation for tests and benchmarks (a stand-in for the buffer manager) */
