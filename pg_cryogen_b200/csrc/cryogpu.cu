@@ -167,6 +167,12 @@ k_zstd_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_
 #ifndef ZP_EXEC_PREFETCH_DEFAULT
 #define ZP_EXEC_PREFETCH_DEFAULT 0
 #endif
+#ifndef ZP_EARLY_CTAS_DEFAULT
+#define ZP_EARLY_CTAS_DEFAULT 0         /* CTAs of the early pass of the raw / RLE stage (0: no early pass -- measured slower, see launch_zstd_decode) */
+#endif
+#ifndef ZP_EARLY_PCT_DEFAULT
+#define ZP_EARLY_PCT_DEFAULT 40         /* share of the batch's frames it takes, from the end */
+#endif
 
 /* phase-split pipeline (default zstd path): zstd_decode_p.cuh */
 __global__ void __launch_bounds__(32)
@@ -201,10 +207,9 @@ zp0_bulk_store_hint(uint8_t *dst, const uint8_t *smem_src, uint32_t bytes, uint6
 
 #define ZP0_THREADS 128u                /* few registers beside the executor's three CTAs per SM */
 
-__global__ void __launch_bounds__(ZP0_THREADS)
-k_zp_prefill(const ZpArgs a)
+template <bool EARLY>
+__device__ __forceinline__ void zp_prefill_body(const ZpArgs &a)
 {
-    ZP_TL_BEGIN(1)
     /*
      * Persistent, one CTA per SM.  Frames are taken in index order, which is the order the
      * executor's CTAs are dispatched in.  RLE blocks (the zero runs of sparse cryo blocks: 73 % of
@@ -219,7 +224,7 @@ k_zp_prefill(const ZpArgs a)
     __shared__ uint32_t next_f;
     int      cur = -1;                  /* byte the pattern holds */
     uint32_t prev_f = ~0u, prev_did = 0;
-    uint32_t *counter = reinterpret_cast<uint32_t *>(a.seq_alloc) + 4;  /* zeroed with seq_alloc */
+    uint32_t *counter = reinterpret_cast<uint32_t *>(a.seq_alloc) + (EARLY ? 5 : 4);    /* zeroed with seq_alloc */
 
     /*
      * Frames are handed out by a counter, not by blockIdx: the CTAs of this kernel do not all become resident at
@@ -233,16 +238,22 @@ k_zp_prefill(const ZpArgs a)
         if (threadIdx.x == 0)
             next_f = atomicAdd(counter, 1u);
         __syncthreads();
-        const uint32_t f = next_f;
-
-        if (f >= a.n)
+        if (next_f >= (EARLY ? a.early_frames : a.n))
             break;
+        /* the early pass works from the end of the batch, whose frames stage 4 reaches last */
+        const uint32_t f = EARLY ? a.n - 1u - next_f : next_f;
         const uint32_t nb = a.fr[(size_t) f * ZP_FF];
         const uint8_t *in = a.src + a.src_off[f];
         uint8_t *out = a.dst + (size_t) f * a.dst_stride;
 
-        if (threadIdx.x == 0)
-            zp_frame_positions(a, f, spec);     /* exact: stage 3b has measured the Compressed blocks */
+        if (threadIdx.x < 32u)
+        {
+            /* EARLY: guessed by stage 1; otherwise exact: stage 3b has measured the Compressed blocks */
+            const uint32_t at = zp_frame_positions_warp<EARLY>(a, f, threadIdx.x);
+
+            if (threadIdx.x < ZP_MAXB)
+                spec[threadIdx.x] = at;
+        }
         __syncthreads();
         uint32_t did = 0;
 
@@ -309,7 +320,8 @@ k_zp_prefill(const ZpArgs a)
             {
                 asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
                 asm volatile("fence.proxy.async;" ::: "memory");
-                zp_stage0_done(a, prev_f << 8, prev_did);
+                if (!EARLY)
+                    zp_stage0_done(a, prev_f << 8, prev_did);
             }
         }
         prev_f = f;
@@ -319,9 +331,46 @@ k_zp_prefill(const ZpArgs a)
     {
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
-        zp_stage0_done(a, prev_f << 8, prev_did);
+        if (!EARLY)
+            zp_stage0_done(a, prev_f << 8, prev_did);
     }
+}
+
+__global__ void __launch_bounds__(ZP0_THREADS)
+k_zp_prefill(const ZpArgs a)
+{
+    ZP_TL_BEGIN(1)
+    zp_prefill_body<false>(a);
     ZP_TL_END(1)
+}
+
+/*
+ * The same stage BEFORE the entropy stages have measured anything, beside them (they are bound by the latency of
+ * their serial chains and leave HBM idle): every raw / RLE block at the position stage 1 guessed for it.  A guess
+ * that turns out wrong costs nothing but the bytes: the late pass writes that block again where it belongs, and
+ * every other byte of the frame's declared size is written by stage 4 after this kernel has ended.
+ */
+__global__ void __launch_bounds__(ZP0_THREADS)
+k_zp_prefill_early(const ZpArgs a)
+{
+    ZP_TL_BEGIN(13)
+    zp_prefill_body<true>(a);
+    ZP_TL_END(13)
+}
+
+/* the compressed frames into L2 ahead of the stages that read them lane by lane (hints only) */
+__global__ void __launch_bounds__(256)
+k_zp_prefetch_src(const ZpArgs a)
+{
+    const uint32_t f = blockIdx.x * 8u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+
+    if (f >= a.n || a.methods[f] != ZP_METHOD_ZSTD)
+        return;
+    const uint8_t *p = a.src + a.src_off[f];
+    const uint32_t n = a.src_size[f];
+
+    for (uint32_t o = 128u * lane; o < n; o += 4096u)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
 }
 
 __global__ void __launch_bounds__(32 * ZP2A_WARPS)
@@ -333,10 +382,10 @@ k_zp_huftab(const ZpArgs a)
 }
 
 __global__ void __launch_bounds__(32)
-k_zp_literals(const ZpArgs a)
+k_zp_literals(const ZpArgs a, uint32_t split)
 {
     ZP_TL_BEGIN(3)
-    zp_stage2b(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_HUFMASK, threadIdx.x, zp_stage2b(a, g, j, CRYO_SMEM_BASE(), threadIdx.x));
     ZP_TL_END(3)
 }
 
@@ -349,22 +398,27 @@ k_zp_fsetab(const ZpArgs a)
 }
 
 __global__ void __launch_bounds__(32)
-k_zp_sequences_small(const ZpArgs a)
+k_zp_sequences_small(const ZpArgs a, uint32_t split)
 {
     ZP_TL_BEGIN(5)
-    zp_stage3b<ZP3B_SMALL, 0, ZP3B_SMALL_LANES>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_SEQMASK, threadIdx.x,
+                        (zp_stage3b<ZP3B_SMALL, 0, ZP3B_SMALL_LANES>(a, g, j, CRYO_SMEM_BASE(), threadIdx.x)));
     ZP_TL_END(5)
 }
 
 __global__ void __launch_bounds__(32)
-k_zp_sequences_large(const ZpArgs a)
+k_zp_sequences_large(const ZpArgs a, uint32_t split)
 {
     ZP_TL_BEGIN(6)
-    zp_stage3b<ZP3B_LARGE, ZP3B_SMALL, ZP_G>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_SEQMASK, threadIdx.x,
+                        (zp_stage3b<ZP3B_LARGE, ZP3B_SMALL, ZP_G>(a, g, j, CRYO_SMEM_BASE(), threadIdx.x)));
     ZP_TL_END(6)
 }
 
-__global__ void __maxnreg__(72)
+#ifndef ZP4_MAXNREG
+#define ZP4_MAXNREG 72
+#endif
+__global__ void __maxnreg__(ZP4_MAXNREG)
 k_zp_execute(const ZpArgs a)
 {
     ZP_TL_BEGIN(7)
@@ -751,7 +805,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             ZSTDD_SCRATCH_BYTES, predef, (uint32_t) n, nullptr);
     else
     {
-        ZpArgs a;
+        ZpArgs a = {};
         const unsigned ngroups = (unsigned) ((n + ZP_G - 1) / ZP_G);
 
         a.methods = methods;
@@ -819,15 +873,62 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         }
         const unsigned pf_grid = (unsigned) std::min<size_t>(n, (size_t) pf_ctas * sm_count);
 
+        /*
+         * The lane-serial stages: warps per group of ZP_G frames (see ZP_FOR_GROUP_BLOCKS).  As many as one wave
+         * of the device holds, so that a batch whose warps all fit runs as ONE wave (a second, nearly empty wave
+         * doubles the stage: its length is that of the longest chain), and at most one per block index.
+         */
+        static int wave[3] = {0, 0, 0};         /* warps of stage 2b / 3b small / 3b large resident on the device */
+
+        if (wave[0] == 0)
+        {
+            int per_sm[3] = {1, 1, 1};
+
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_zp_literals, 32, ZP2B_SMEM);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_zp_sequences_small, 32,
+                                                          ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES));
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_zp_sequences_large, 32, ZP3B_SMEM(ZP3B_LARGE, ZP_G));
+            for (int k = 0; k < 3; k++)
+                wave[k] = std::max(1, per_sm[k]) * sm_count;
+        }
+        unsigned split[3];
+
+        for (int k = 0; k < 3; k++)
+            split[k] = std::min<unsigned>(ZP_MAXB, std::max<unsigned>(1u, (unsigned) wave[k] / ngroups));
+        /*
+         * The early pass of the raw / RLE stage (aux 1), beside the entropy stages: they are chains of dependent
+         * shared-memory reads that leave HBM idle for a third of the step, and the bulk-copy engine needs one
+         * thread per SM.  The frames are asked into L2 first, so that the window refills of the lane-serial
+         * stages do not queue behind the stores.  CRYOGPU_ZP_EARLY=0 / CRYOGPU_ZP_SRC_PREFETCH=0 switch them off.
+         */
+        static int early_ctas = -1, early_pct = -1, src_prefetch = -1;
+
+        if (early_ctas < 0)
+        {
+            const char *e = getenv("CRYOGPU_ZP_EARLY_CTAS"), *q = getenv("CRYOGPU_ZP_EARLY_PCT"),
+                       *x = getenv("CRYOGPU_ZP_SRC_PREFETCH");
+
+            early_ctas = e ? atoi(e) : ZP_EARLY_CTAS_DEFAULT;
+            early_pct = q ? std::min(100, std::max(0, atoi(q))) : ZP_EARLY_PCT_DEFAULT;
+            src_prefetch = x ? atoi(x) != 0 : 1;
+        }
+        a.early_frames = (early_ctas > 0 && !all_cx) ? (uint32_t) (n * (size_t) early_pct / 100) : 0u;
         cudaEventRecord(ev[0], st);
         cudaStreamWaitEvent(aux[0], ev[0], 0);
+        if (a.early_frames)
+        {
+            cudaStreamWaitEvent(aux[1], ev[0], 0);
+            if (src_prefetch)
+                k_zp_prefetch_src<<<(unsigned) ((n + 7) / 8), 256, 0, aux[1]>>>(a);
+            k_zp_prefill_early<<<(unsigned) std::min<size_t>(a.early_frames, (size_t) early_ctas), ZP0_THREADS, 0, aux[1]>>>(a);
+            cudaEventRecord(ev[3], aux[1]);
+        }
         k_zp_fsetab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP3A_WARPS, ZP3A_SMEM, aux[0]>>>(a);
-        k_zp_sequences_small<<<(unsigned) ((n + ZP3B_SMALL_LANES - 1) / ZP3B_SMALL_LANES) * ZP_MAXB, 32,
-                               ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), aux[0]>>>(a);
-        k_zp_sequences_large<<<ngroups * ZP_MAXB, 32, ZP3B_SMEM(ZP3B_LARGE, ZP_G), aux[0]>>>(a);
+        k_zp_sequences_small<<<ngroups * split[1], 32, ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), aux[0]>>>(a, split[1]);
+        k_zp_sequences_large<<<ngroups * split[2], 32, ZP3B_SMEM(ZP3B_LARGE, ZP_G), aux[0]>>>(a, split[2]);
         cudaEventRecord(ev[1], aux[0]);
         k_zp_huftab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
-        k_zp_literals<<<ngroups * ZP_MAXB, 32, ZP2B_SMEM, st>>>(a);
+        k_zp_literals<<<ngroups * split[0], 32, ZP2B_SMEM, st>>>(a, split[0]);
         cudaStreamWaitEvent(st, ev[1], 0);
         if (all_cx)
             k_zp_execute_c<<<(unsigned) std::min<size_t>(n, (size_t) sm_count), CX_THREADS, ZC_SMEM, st>>>(a, cx_counter);
@@ -837,6 +938,8 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             cudaStreamWaitEvent(aux[1], ev[0], 0);
             k_zp_prefill<<<pf_grid, ZP0_THREADS, 0, aux[1]>>>(a);
             cudaEventRecord(ev[2], aux[1]);
+            if (a.early_frames)
+                cudaStreamWaitEvent(st, ev[3], 0);      /* stage 4 writes over wrong guesses: the early pass must have ended */
             k_zp_execute<<<(unsigned) ((n + ZP4_WARPS - 1) / ZP4_WARPS), ZP4_THREADS, ZP4_SMEM, st>>>(a);
             /*
              * The frames with many sequences, after the warp executor in the same stream.  A CTA of this
@@ -1241,7 +1344,7 @@ cryogpu_zstd_pipeline_stats(cryogpu_ctx *ctx, uint64_t *frames, uint64_t *fallba
     CU(cudaDeviceSynchronize());
     if (ctx->last_zp_n)
     {
-        ZpArgs a;
+        ZpArgs a = {};
         std::vector<uint32_t> fr(ctx->last_zp_n * ZP_FF), flag(ctx->last_zp_n);
 
         zp_carve(a, ctx->zp[0].p, ctx->last_zp_n, ctx->last_zp_cap);

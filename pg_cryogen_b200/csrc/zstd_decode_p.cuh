@@ -34,9 +34,12 @@
 #define ZP_METHOD_ZSTD 1
 #define ZP_MAXB   16u           /* zstd blocks per frame the pipeline takes (1 MiB / 128 KiB = 8) */
 #define ZP_G      8u            /* frames per entropy warp */
-#define ZP_BF     19u           /* u32 fields per block descriptor */
+#define ZP_BF     20u           /* u32 fields per block descriptor */
 #define ZP_PREFILL_MIN 2048u     /* raw / RLE blocks at least this long are written ahead by stage 0 */
-#define ZP_FF     4u            /* u32 fields per frame descriptor: nblk, fcs, has_fcs, route (1: stage 4 by a CTA, zstd_decode_c.cuh) */
+#define ZP_FF     6u            /* u32 fields per frame descriptor: nblk, fcs, has_fcs, route (1: stage 4 by a CTA, zstd_decode_c.cuh),
+                                 * mask of the blocks with Huffman-coded literals, mask of the blocks with sequences */
+#define ZPF_HUFMASK 4u
+#define ZPF_SEQMASK 5u
 #define ZP_CX_SEQS 8192u        /* frames with at least this many sequences take the CTA-per-frame stage 4 */
 
 enum
@@ -58,7 +61,9 @@ enum
     ZPB_HINFO,                  /* written by stage 2a: table log | description bytes << 8 (0: failed) */
     ZPB_SLOGS,                  /* written by stage 3a: ll_log | of_log << 8 | ml_log << 16 | 1 << 31 */
     ZPB_BITOFF,                 /* written by stage 3a: block-relative offset of the sequence bitstream */
-    ZPB_OUTSZ                   /* bytes the block regenerates: stage 1 (raw, RLE, no sequences) or stage 3b (literals + matches) */
+    ZPB_OUTSZ,                  /* bytes the block regenerates: stage 1 (raw, RLE, no sequences) or stage 3b (literals + matches) */
+    ZPB_SPECAT                  /* raw / RLE block that stage 0 may write EARLY: its output position if every Compressed block
+                                 * before it regenerates a full 128 KiB (what libzstd cuts), ~0u: no such guess */
 };
 
 struct ZpArgs
@@ -81,6 +86,7 @@ struct ZpArgs
     uint32_t       *cxlist;     /* frames routed to the CTA-per-frame stage 4, in no particular order */
     uint32_t       *cxcount;    /* how many */
     uint32_t       *pf_done;    /* n; blocks of the frame stage 0 has finished (release / acquire with stage 4) */
+    uint32_t        early_frames; /* the early pass of stage 0 takes the last early_frames frames of the batch (0: there is none) */
     uint32_t        pf_hint;    /* bit 0: stage 0 bulk stores with the L2 evict_first policy; bit 1: stage 4 asks L2 for
                                  * sequences and literals a few loads ahead; bit 2: every frame takes the CTA-per-frame
                                  * stage 4 (small batches); bit 3: none does */
@@ -143,6 +149,8 @@ CRYO_DEV bool zp_parse(const uint8_t *in, uint32_t csize, uint32_t cap, uint64_t
         return false;
 
     uint32_t nb = 0, lit_total = 0, seq_total = 0, hd_off = 0, hd_left = 0, hd_blk = 0;
+    uint32_t hufmask = 0, seqmask = 0;
+    uint64_t spec_at = 0;                       /* where the block would start if the Compressed ones before it were full */
     bool     have_hd = false;
 
     for (;;)
@@ -161,6 +169,9 @@ CRYO_DEV bool zp_parse(const uint8_t *in, uint32_t csize, uint32_t cap, uint64_t
         b[ZPB_KIND] = type;
         b[ZPB_SPECPOS] = (type < 2 && bsize >= ZP_PREFILL_MIN) ? 0u : ~0u;
         b[ZPB_OUTSZ] = bsize;                   /* raw, RLE; Compressed: below and stage 3b */
+        /* a guess is only made inside a declared content size: a frame that decodes rewrites all of it */
+        b[ZPB_SPECAT] = (type < 2 && bsize >= ZP_PREFILL_MIN && fcs_bytes && spec_at + bsize <= fcs) ? (uint32_t) spec_at : ~0u;
+        spec_at += type < 2 ? bsize : ZS_MAXBLOCK;
         if (type == 0)
         {
             if (bsize > csize - ip)
@@ -295,7 +306,12 @@ CRYO_DEV bool zp_parse(const uint8_t *in, uint32_t csize, uint32_t cap, uint64_t
             b[ZPB_LITPOS] = lit_total;
             b[ZPB_SEQPOS] = seq_total;
             if (lt >= 2)
+            {
                 lit_total += (regen + 15u) & ~15u;
+                hufmask |= 1u << nb;
+            }
+            if (nseq)
+                seqmask |= 1u << nb;
             seq_total += nseq;
             if ((uint64_t) lit_total > lit_stride)
                 return false;
@@ -316,6 +332,8 @@ CRYO_DEV bool zp_parse(const uint8_t *in, uint32_t csize, uint32_t cap, uint64_t
     fr[0] = nb;
     fr[1] = (uint32_t) fcs;
     fr[2] = fcs_bytes ? 1u : 0u;
+    fr[ZPF_HUFMASK] = hufmask;
+    fr[ZPF_SEQMASK] = seqmask;
     *seq_total_out = seq_total;
     return true;
 }
@@ -326,6 +344,8 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
     uint32_t *fr = a.fr + (size_t) f * ZP_FF;
 
     fr[0] = 0;
+    fr[ZPF_HUFMASK] = 0;
+    fr[ZPF_SEQMASK] = 0;
     a.flag[f] = 0;
     a.pf_done[f] = 0;
     if (a.methods[f] != ZP_METHOD_ZSTD)
@@ -349,16 +369,54 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
         if (cx)
         {
             for (uint32_t j = 0; j < fr[0]; j++)
+            {
                 a.blk[((size_t) f * ZP_MAXB + j) * ZP_BF + ZPB_SPECPOS] = ~0u;
+                a.blk[((size_t) f * ZP_MAXB + j) * ZP_BF + ZPB_SPECAT] = ~0u;
+            }
             a.cxlist[atomicAdd(a.cxcount, 1u)] = f;
         }
     }
     if (!ok)
     {
         fr[0] = 0;
+        fr[ZPF_HUFMASK] = 0;
+        fr[ZPF_SEQMASK] = 0;
         a.flag[f] = 1;
     }
 }
+
+/*
+ * How the lane-serial stages (2b, 3b) are laid over the grid.  A warp of those stages takes one block
+ * index of ZP_G consecutive frames.  Round 1 launched one warp per (group, block index), sixteen per
+ * group: on the sparse headline table fourteen of the sixteen found nothing and left, and the 862
+ * literal warps that had work did not fit the 740 the shared memory admits at once -- the stage ran
+ * as two waves, the second one a sixth full, and took twice the time of its longest chain.  Now a
+ * warp walks the block indices that have work (the union of its frames' masks, from stage 1) itself,
+ * and `split` warps share the indices of a group by rank; the host picks split so that the grid fits
+ * the device in one wave when it can.
+ */
+CRYO_DEV uint32_t zp_group_mask(const ZpArgs &a, uint32_t g, uint32_t field, uint32_t lane)
+{
+    const uint32_t f = g * ZP_G + (lane & (ZP_G - 1u));
+    const uint32_t m = (f < a.n && a.fr[(size_t) f * ZP_FF] != 0) ? a.fr[(size_t) f * ZP_FF + field] : 0u;
+
+    return __reduce_or_sync(CRYO_FULL, m);
+}
+#define ZP_FOR_GROUP_BLOCKS(a, w, split, field, lane, call)                                  \
+    {                                                                                        \
+        const uint32_t g_ = (w) / (split), c_ = (w) % (split);                               \
+        uint32_t m_ = zp_group_mask((a), g_, (field), (lane));                               \
+                                                                                             \
+        for (uint32_t k_ = 0; m_; m_ &= m_ - 1u, k_++)                                       \
+        {                                                                                    \
+            if (k_ % (split) != c_)                                                          \
+                continue;                                                                    \
+            const uint32_t g = g_, j = (uint32_t) __ffs((int) m_) - 1u;                      \
+                                                                                             \
+            call;                                                                            \
+            __syncwarp();                                                                    \
+        }                                                                                    \
+    }
 
 /* ------------------------------------------------- stage 0: raw / RLE blocks ahead ---- */
 
@@ -396,6 +454,55 @@ CRYO_DEV void zp_frame_positions(const ZpArgs &a, uint32_t f, uint32_t *pos)
             pos[j] = (uint32_t) at;
         at += b[ZPB_OUTSZ];
     }
+}
+
+/* did the early pass of stage 0 (raw / RLE blocks at their guessed positions, ZPB_SPECAT) take frame f */
+CRYO_DEV bool zp_early_frame(const ZpArgs &a, uint32_t f) { return f + a.early_frames >= a.n; }
+
+/* the late pass of stage 0: drop the blocks the early pass wrote at the right place (stage 4 applies the same
+ * test when it steps over them, so the two agree on how many blocks pf_done counts) */
+CRYO_DEV void zp_frame_positions_late(const ZpArgs &a, uint32_t f, uint32_t *pos)
+{
+    zp_frame_positions(a, f, pos);
+    if (zp_early_frame(a, f))
+        for (uint32_t j = 0; j < ZP_MAXB; j++)
+            if (pos[j] != ~0u && a.blk[((size_t) f * ZP_MAXB + j) * ZP_BF + ZPB_SPECAT] == pos[j])
+                pos[j] = ~0u;
+}
+
+/*
+ * The same by one warp, lane = block (what the stage itself uses: a thread walking the sixteen descriptors
+ * one after the other took 10 us per frame, most of the 26 us a CTA spent on a sparse frame).  EARLY: the
+ * guessed positions; otherwise the exact ones without the blocks the early pass placed right.
+ */
+template <bool EARLY>
+CRYO_DEV uint32_t zp_frame_positions_warp(const ZpArgs &a, uint32_t f, uint32_t lane)
+{
+    const uint32_t nb = a.fr[(size_t) f * ZP_FF];
+    const uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + (lane & (ZP_MAXB - 1u))) * ZP_BF;
+    const bool     have = lane < ZP_MAXB && lane < nb;
+
+    if (EARLY)
+        return have ? b[ZPB_SPECAT] : ~0u;
+    const bool     live = a.flag[f] == 0;
+    const uint32_t bsize = have ? b[ZPB_BSIZE] : 0u, specpos = have ? b[ZPB_SPECPOS] : ~0u;
+    const uint32_t specat = have ? b[ZPB_SPECAT] : ~0u;
+    unsigned long long at = have ? b[ZPB_OUTSZ] : 0u;
+
+#pragma unroll
+    for (uint32_t d = 1; d < ZP_MAXB; d <<= 1)
+    {
+        const unsigned long long up = __shfl_up_sync(CRYO_FULL, at, d);
+
+        if (lane >= d)
+            at += up;
+    }
+    at -= have ? b[ZPB_OUTSZ] : 0u;             /* exclusive */
+    uint32_t pos = (have && live && specpos != ~0u && at + bsize <= a.cap) ? (uint32_t) at : ~0u;
+
+    if (zp_early_frame(a, f) && pos == specat)
+        pos = ~0u;
+    return pos;
 }
 
 CRYO_DEV void zp_stage0(const ZpArgs &a, uint32_t item, uint32_t at, uint32_t tid, uint32_t nthr)
@@ -880,6 +987,19 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         a.flag[tf] = 1;
 }
 
+/* the low n bits of v, n = 0 .. 32 */
+CRYO_DEV uint32_t zp_low_bits(uint32_t v, uint32_t n)
+{
+#ifdef CRYO_EMU
+    return n >= 32u ? v : v & ((1u << n) - 1u);
+#else
+    uint32_t r;
+
+    asm("bfe.u32 %0, %1, 0, %2;" : "=r"(r) : "r"(v), "r"(n));
+    return r;
+#endif
+}
+
 /* -------------------------------------------------------------- stage 3: sequences ---- */
 
 /*
@@ -1142,16 +1262,44 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
             act = false;
         }
     }
+    /*
+     * The walk.  What is serial in a sequence bitstream is short: the three states name the cells, the
+     * cells say how many bits the sequence takes, and the next states are three fields of the LAST bits
+     * it takes.  The values of the extra bits (offset, lengths) are not needed to get there.  So the
+     * cursor is a bit position P (the stream is read from its end: bits at and above P are consumed),
+     * any field is fetched by position from the lane's window in shared memory -- two words and a funnel
+     * shift -- and only  cells -> bit counts -> position of the state field -> next states  is a
+     * dependent chain (about a hundred cycles); the fetches of the extra bits, the baselines and the
+     * store hang off it.  Round 1 drew every field from one shift-register accumulator with three
+     * conditional refills per sequence: 154 dependent instructions, 1 300 cycles per sequence.
+     */
     uint32_t *win = reinterpret_cast<uint32_t *>(smem + LANES * CELLS * 4u) + lane * ZP3B_WSTRIDE;
     const uint8_t *abase = src - ((uintptr_t) src & 15u);
     const int32_t  delta = (int32_t) ((uintptr_t) src & 15u);
-    int32_t  npos = act ? (int32_t) ((delta + sn - 1u) & ~3u) : 0;
-    int32_t  g0 = 0;
+    int32_t  P = 0;                             /* bit offset from abase */
+    int32_t  g0 = 0;                            /* the window holds bytes [g0, g0 + ZP3B_WIN) from abase; multiple of 16 */
 
+    if (act)
+    {
+        const uint32_t lastb = src[sn - 1u];
+
+        if (lastb == 0)
+        {
+            bad = true;                         /* no end mark in the last byte */
+            act = false;
+        }
+        else
+            P = 8 * (delta + (int32_t) sn - 1) + zs_highbit(lastb);
+    }
+    if (!act)
+        nseq = 0;
+    const int32_t Pend = 8 * delta;             /* a valid walk ends exactly here */
+
+/* the window, so that the cursor's byte is among its last sixteen (bytes in front of abase read as zero) */
 #define ZP3B_FILL()                                                          \
     {                                                                        \
         __syncwarp();                                                        \
-        g0 = (npos & ~15) - (int32_t) (ZP3B_WIN - 16u);                      \
+        g0 = ((P >> 3) & ~15) - (int32_t) (ZP3B_WIN - 16u);                  \
         _Pragma("unroll") for (int r_ = 0; r_ < 4; r_++)                     \
         {                                                                    \
             uint4 v_[4];                                                     \
@@ -1171,122 +1319,79 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         }                                                                    \
         __syncwarp();                                                        \
     }
-    ZP3B_FILL();
-    uint32_t ahi = 0, alo = 0, cand = 0;        /* accumulator: next bit to read is bit 31 of ahi */
-    int32_t  avail = 0, remaining = 0;
-
-    if (act)
-    {
-        uint32_t w = win[(npos - g0) >> 2];
-        const uint32_t keep = delta + sn - (uint32_t) npos;     /* 1..4 valid low bytes */
-
-        if (keep < 4)
-            w &= (1u << (8u * keep)) - 1u;
-        if (npos < delta)
-            w &= ~0u << (8u * (uint32_t) (delta - npos));
-        if ((w >> (8u * (keep - 1u))) == 0)
-        {
-            bad = true;                         /* no end mark in the last byte */
-            act = false;
-        }
-        else
-        {
-            const int hbit = zs_highbit(w);
-
-            ahi = hbit ? w << (32 - hbit) : 0u;
-            avail = hbit;
-            remaining = (int32_t) ((sn - 1u) * 8u) + (hbit - 8 * (int) (keep - 1u));
-            npos -= 4;
-            cand = win[(npos - g0) >> 2];
-        }
-    }
-    if (!act)
-        nseq = 0;
-#ifdef CRYO_EMU
-#define ZP_SHR_C(x, s) ((s) >= 32 ? 0u : (x) >> (s))
-#define ZP_SHL_C(x, s) ((s) >= 32 ? 0u : (x) << (s))
-#define ZP_FSHL_C(l, h, s) ((s) >= 32 ? (l) : __funnelshift_l((l), (h), (s)))
-#else
-#define ZP_FSHL_C(l, h, s) __funnelshift_lc((l), (h), (uint32_t) (s))
-#define ZP_SHR_C(x, s) __funnelshift_rc((x), 0u, (uint32_t) (s))
-#define ZP_SHL_C(x, s) __funnelshift_lc(0u, (x), (uint32_t) (s))
-#endif
-/* predicated refill to more than 32 valid bits */
-#define ZP3B_REFILL(on)                                                      \
+/* n <= 32 bits whose lowest is bit q of the stream (n == 0: nothing) */
+#define ZP3B_BITS(dst, q, n)                                                 \
     {                                                                        \
-        const bool p_ = (on) && avail <= 32;                                 \
-        ahi |= p_ ? ZP_SHR_C(cand, avail) : 0u;                              \
-        alo = p_ ? ZP_SHL_C(cand, 32 - avail) : alo;                         \
-        avail += p_ ? 32 : 0;                                                \
-        npos -= p_ ? 4 : 0;                                                  \
-        cand = win[(npos - g0) >> 2];                                        \
+        const int32_t   q_ = (q);                                            \
+        const uint32_t *w_ = win + ((q_ >> 5) - (g0 >> 2));                  \
+        dst = zp_low_bits(__funnelshift_r(w_[0], w_[1], (uint32_t) q_ & 31u), (n)); \
     }
-/* nb <= 32 bits out of the accumulator (nb == 0 reads nothing) */
-#define ZP3B_READ(dst, nb)                                                   \
-    {                                                                        \
-        const uint32_t n_ = (nb);                                            \
-        dst = ZP_SHR_C(ahi, 32u - n_);                                       \
-        ahi = ZP_FSHL_C(alo, ahi, n_);                                \
-        alo = ZP_SHL_C(alo, n_);                                             \
-        avail -= (int32_t) n_;                                               \
-    }
+/* four sequences take 4 x 85 bits at most: 43 bytes below the cursor */
 #define ZP3B_ENSURE(on)                                                      \
-    if (__any_sync(CRYO_FULL, (on) && npos - g0 < 12))                       \
     {                                                                        \
-        ZP3B_FILL();                                                         \
-        cand = win[(npos - g0) >> 2];                                        \
+        if (act && P < Pend)                                                 \
+        {                                                                    \
+            bad = true;                         /* read past the start of the stream */ \
+            nseq = 0;                                                        \
+        }                                                                    \
+        if (__any_sync(CRYO_FULL, (on) && (P >> 3) - g0 < 48))               \
+            ZP3B_FILL();                                                     \
     }
+    ZP3B_FILL();
     /* code -> baseline | extra bits << 24, from shared memory in the loop */
     uint32_t *packs = reinterpret_cast<uint32_t *>(smem + LANES * CELLS * 4u + 32u * ZP3B_WSTRIDE * 4u);
 
     for (uint32_t k = lane; k < 36u + 53u; k += 32)
         packs[k] = k < 36u ? CRYO_GLD(ZS_LL_PACK[k]) : CRYO_GLD(ZS_ML_PACK[k - 36u]);
     __syncwarp();
-    /* bits consumed are not counted per read: loaded bits minus what is left says it at the end
-     * (a walk that reads past the start of the stream never gets back to an exact balance) */
-    const int32_t total = remaining, loaded0 = avail, npos0 = npos;
     uint32_t sl = 0, so = 0, sm = 0, mlsum = 0;
 
-    ZP3B_ENSURE(act);
-    ZP3B_REFILL(act);
-    ZP3B_READ(sl, act ? ll_log : 0u);
-    ZP3B_READ(so, act ? of_log : 0u);
-    ZP3B_READ(sm, act ? ml_log : 0u);
+    {
+        /* the initial states: LL, OF, ML (26 bits at most) */
+        const uint32_t n0 = act ? ll_log + of_log + ml_log : 0u;
+        uint32_t t;
+
+        P -= (int32_t) n0;
+        ZP3B_BITS(t, P, n0);
+        sl = act ? t >> (of_log + ml_log) : 0u;
+        so = act ? (t >> ml_log) & ((1u << of_log) - 1u) : 0u;
+        sm = act ? t & ((1u << ml_log) - 1u) : 0u;
+    }
     uint64_t *out = act ? a.seq + a.seqbase[f] + b[ZPB_SEQPOS] : nullptr;
     const uint32_t maxseq = __reduce_max_sync(CRYO_FULL, nseq);
 
 #pragma unroll 1
     for (uint32_t i = 0; i < maxseq; i++)
     {
+        if ((i & 3u) == 0)
+            ZP3B_ENSURE(i < nseq);
         const bool on = i < nseq;
         const bool more = i + 1 < nseq;
-
-        ZP3B_ENSURE(on);
         const uint32_t cl = llt[sl], co = oft[so], cm = mlt[sm];
         const uint32_t xo = co >> 26, xm = cm >> 26, xl = cl >> 26;
+        const uint32_t nbl = (cl >> 8) & 0xFFu, nbm = (cm >> 8) & 0xFFu, nbo = (co >> 8) & 0xFFu;
+        /* offset extra bits (27 at most: beyond any window ZSTD_decompress accepts), then match-length and
+         * literal-length extra bits (16 + 16 at most), then the state updates LL, ML, OF (9 + 9 + 8 at most) */
+        const uint32_t n1 = on ? (xo > 27 ? 27u : xo) : 0u, n2 = on ? xm + xl : 0u, n3 = more ? nbl + nbm + nbo : 0u;
+        const int32_t  Pa = P - (int32_t) n1, Pb = Pa - (int32_t) n2, Pc = Pb - (int32_t) n3;
+        uint32_t t3, ov, t2;
+
+        ZP3B_BITS(t3, Pc, n3);
+        sl = more ? ((cl >> 16) & 0x3FFu) + (t3 >> (nbm + nbo)) : sl;
+        sm = more ? ((cm >> 16) & 0x3FFu) + ((t3 >> nbo) & ((1u << nbm) - 1u)) : sm;
+        so = more ? ((co >> 16) & 0x3FFu) + (t3 & ((1u << nbo) - 1u)) : so;
+        P = Pc;
+        /* off the chain: the values */
+        if (on && xo > 27)
+            bad = true;
+        ZP3B_BITS(ov, Pa, n1);
+        ZP3B_BITS(t2, Pb, n2);
+        ov += 1u << (xo & 31u);
         /* (a lane without work reads stale cells: keep its table indices in range) */
         const uint32_t pl = packs[on ? cl & 0xFFu : 0u], pm = packs[36u + (on ? cm & 0xFFu : 0u)];
-        uint32_t ov, t;
+        const uint32_t ml = (pm & 0xFFFFFFu) + (t2 >> xl);
+        const uint32_t ll = (pl & 0xFFFFFFu) + (t2 & ((1u << xl) - 1u));
 
-        if (on && xo > 27)
-            bad = true;                         /* beyond any window ZSTD_decompress accepts */
-        /* offset extra bits (up to 27) */
-        ZP3B_REFILL(on);
-        ZP3B_READ(ov, on ? (xo > 27 ? 27u : xo) : 0u);
-        ov += 1u << (xo & 31u);
-        /* match-length then literal-length extra bits in one read (16 + 16 at most) */
-        ZP3B_REFILL(on);
-        ZP3B_READ(t, on ? xm + xl : 0u);
-        const uint32_t ml = (pm & 0xFFFFFFu) + (t >> xl);
-        const uint32_t ll = (pl & 0xFFFFFFu) + (t & ((1u << xl) - 1u));
-        /* the three state updates in one read (9 + 9 + 8 bits at most): LL, ML, OF */
-        const uint32_t nbl = (cl >> 8) & 0xFFu, nbm = (cm >> 8) & 0xFFu, nbo = (co >> 8) & 0xFFu;
-
-        ZP3B_REFILL(more);
-        ZP3B_READ(t, more ? nbl + nbm + nbo : 0u);
-        sl = more ? ((cl >> 16) & 0x3FFu) + (t >> (nbm + nbo)) : sl;
-        sm = more ? ((cm >> 16) & 0x3FFu) + ((t >> nbo) & ((1u << nbm) - 1u)) : sm;
-        so = more ? ((co >> 16) & 0x3FFu) + (t & ((1u << nbo) - 1u)) : so;
         if (on)
         {
             out[i] = (uint64_t) ll | ((uint64_t) ml << 17) | ((uint64_t) (ov & 0x1FFFFFFFu) << 35);
@@ -1295,15 +1400,11 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
     }
     if (act)
         a.blk[((size_t) f * ZP_MAXB + j) * ZP_BF + ZPB_OUTSZ] += mlsum;     /* regen + match bytes (< 2^32) */
-    remaining = total - (loaded0 + 8 * (npos0 - npos) - avail);
 #undef ZP3B_FILL
-#undef ZP3B_REFILL
-#undef ZP3B_READ
+#undef ZP3B_BITS
 #undef ZP3B_ENSURE
-#undef ZP_SHR_C
-#undef ZP_SHL_C
-#undef ZP_FSHL_C
-    if (act && remaining != 0)
+    /* every bit under the end mark consumed, no more, no less */
+    if (act && nseq != 0 && P != Pend)
         bad = true;
     if (bad)
         a.flag[f] = 1;
@@ -1404,6 +1505,10 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
             {
                 /* stage 0 writes this block here (it may not have yet): move on without touching
                  * the output, the ring's tail comes from the block's own description */
+                /* written before this kernel started (the early pass of stage 0 guessed its position right):
+                 * nothing to wait for, whoever reads it */
+                const bool early = zp_early_frame(a, f) && b[ZPB_SPECAT] == o.pos;
+
                 wx_drain_all(o, lane);
                 o.pos += bsize;
                 o.flushed = o.pos & ~15u;
@@ -1411,9 +1516,12 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                 if (lane < o.pos - o.flushed)
                     o.ring[(o.flushed + lane) & WX_RMASK] = type == 0 ? in[off + bsize - (o.pos - o.flushed) + lane] : in[off];
                 __syncwarp();
-                skipped++;
-                skipmask |= 1u << j;
-                guard = o.pos;
+                if (!early)
+                {
+                    skipped++;
+                    skipmask |= 1u << j;
+                    guard = o.pos;
+                }
                 /* consecutive RLE blocks of one byte form one range whose content is known */
                 if (type == 1 && rle_hi == o.pos - bsize && rle_byte == in[off] && rle_hi > rle_lo)
                     rle_hi = o.pos;
@@ -1610,93 +1718,74 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                             st16(L.win + w, ld16(L.abase + wb + w));
                     L.wvalid = false;           /* the slow path's window bookkeeping no longer holds */
                     __syncwarp();
-                    {
-                        const uint32_t maxll = __reduce_max_sync(CRYO_FULL, in ? my_ll : 0u);
-                        const uint8_t *ls = L.win + (L.delta + my_lit - wb);
-
-                        const uint32_t nll = in ? my_ll : 0u;
-
-                        for (uint32_t i = 0; i < maxll; i += 4)
-                        {
-#pragma unroll
-                            for (uint32_t q = 0; q < 4; q++)
-                                if (i + q < nll)
-                                    o.ring[(my_start + i + q) & WX_RMASK] = ls[i + q];
-                        }
-                    }
-                    __syncwarp();
                     /*
-                     * Matches.  A source byte is in the ring if it is at or above `floor` (everything
-                     * below o.flushed is in global memory, and floor < o.flushed).  A short match whose
-                     * source ends at or below the start of the run depends on nothing the run writes:
-                     * all of those go first, one per lane, with the global loads of a step issued
-                     * together (match-rich data takes most sources from far behind, and serving them
-                     * one after the other would cost an L2 round trip per sequence).  The others
-                     * follow in order, each a warp-wide move.
+                     * The run byte by byte, 32 consecutive output bytes per step, one per lane (round 1
+                     * gave every lane its own sequence and moved its bytes one after the other: the
+                     * lanes with short sequences idled, and the moves were most of the executor's 84 K
+                     * instructions per sparse frame).  Which sequence a byte belongs to: the ends of the
+                     * sequences that fall into the step's 32 bytes are marked in a word (one warp OR),
+                     * and a lane counts the marks at or below its own byte.  A literal byte comes from
+                     * the window, a match byte from its distance back: the ring holds everything before
+                     * the step (the steps run in order), older bytes are in global memory, and a source
+                     * INSIDE the step is another lane's byte -- those are resolved by pointer jumping
+                     * over the lanes (a chain of overlapping copies of any length takes five rounds).
                      */
                     const uint32_t floor0 = end + 64u > WX_RING ? end + 64u - WX_RING : 0u;
                     const uint32_t floor = floor0 > o.lo ? floor0 : o.lo;
-                    const uint32_t my_sp = my_mpos - my_off;
-                    bool           indep = in && my_ml <= ZP4_LANE_ML && my_sp + my_ml <= pos0;
+                    const uint32_t span = end - pos0;
+                    const uint32_t e_rel = my_epos - pos0;
+                    /* match start | (window index of the first literal - start, biased) of this lane's sequence */
+                    const uint32_t my_pack = ((my_mpos - pos0) & 0xFFFFu) |
+                                             ((L.delta + my_lit - wb + 2048u - (my_start - pos0)) << 16);
+                    uint32_t       seqbase = k0;
 
-                    /* worth a lane-per-sequence pass only if several lanes take part (the first match of
-                     * a run always qualifies) */
-                    if (__popc(__ballot_sync(CRYO_FULL, indep)) < 6)
-                        indep = false;
+                    for (uint32_t R = 0; R < span; R += 32)
                     {
-                        const uint32_t maxml = __reduce_max_sync(CRYO_FULL, indep ? my_ml : 0u);
+                        const uint32_t d = e_rel - R;
+                        const uint32_t marks = __reduce_or_sync(CRYO_FULL, (in && d < 32u) ? 1u << d : 0u);
+                        const uint32_t idx = (seqbase + __popc(marks & (0xFFFFFFFFu >> (31u - lane)))) & 31u;
+                        const uint32_t s_pack = __shfl_sync(CRYO_FULL, my_pack, (int) idx);
+                        const uint32_t s_off = __shfl_sync(CRYO_FULL, my_off, (int) idx);
+                        const uint32_t r = R + lane, p = pos0 + r, x = p - s_off;
+                        const bool     live = r < span, lit = r < (s_pack & 0xFFFFu);
+                        const bool     inside = live && !lit && s_off <= lane;     /* source in this step */
+                        uint32_t       v = 0;
 
-                        for (uint32_t i0 = 0; i0 < maxml; i0 += 16)
+                        seqbase += __popc(marks);
+                        if (live && !inside)
                         {
-                            uint8_t v[16];
-
-#pragma unroll
-                            for (uint32_t q = 0; q < 16; q++)
-                            {
-                                const uint32_t x = my_sp + i0 + q;
-
-                                v[q] = (indep && i0 + q < my_ml) ? (x >= floor ? o.ring[x & WX_RMASK] : o.out[x]) : (uint8_t) 0;
-                            }
-#pragma unroll
-                            for (uint32_t q = 0; q < 16; q++)
-                                if (indep && i0 + q < my_ml)
-                                    o.ring[(my_mpos + i0 + q) & WX_RMASK] = v[q];
+                            if (lit)
+                                v = L.win[r + (s_pack >> 16) - 2048u];
+                            else
+                                v = x >= floor ? o.ring[x & WX_RMASK] : o.out[x];
                         }
-                    }
-                    __syncwarp();
-                    for (uint32_t dep = __ballot_sync(CRYO_FULL, in && !indep); dep; dep &= dep - 1)
-                    {
-                        const int      k = __ffs((int) dep) - 1;
-                        const uint32_t mpos = __shfl_sync(CRYO_FULL, my_mpos, k);
-                        const uint32_t moff = __shfl_sync(CRYO_FULL, my_off, k);
-                        const uint32_t ml = __shfl_sync(CRYO_FULL, my_ml, k);
-                        const uint32_t sp = mpos - moff;
+                        uint32_t pend = __ballot_sync(CRYO_FULL, inside);
 
-                        if (moff >= ml)
+                        if (pend)
                         {
-                            /* no overlap: up to ZP4_BIG_ML / 32 independent moves */
-                            for (uint32_t i = lane; i < ml; i += 32)
+                            uint32_t j = (lane - s_off) & 31u;      /* the lane that holds the source byte */
+                            bool     have_v = !inside;
+
+                            while (pend)
                             {
-                                const uint32_t x = sp + i;
+                                const uint32_t sv = __shfl_sync(CRYO_FULL, v, (int) j);
+                                const uint32_t sj = __shfl_sync(CRYO_FULL, j, (int) j);
 
-                                o.ring[(mpos + i) & WX_RMASK] = x >= floor ? o.ring[x & WX_RMASK] : o.out[x];
-                            }
-                        }
-                        else
-                        {
-                            /* overlap: every byte is one of the moff bytes before mpos */
-                            uint32_t r = lane % moff;
-                            const uint32_t step = 32u % moff;
-
-                            for (uint32_t i = lane; i < ml; i += 32)
-                            {
-                                const uint32_t x = sp + r;
-
-                                o.ring[(mpos + i) & WX_RMASK] = x >= floor ? o.ring[x & WX_RMASK] : o.out[x];
-                                r += step;
-                                r = r >= moff ? r - moff : r;
+                                if (!have_v)
+                                {
+                                    if (!((pend >> j) & 1u))
+                                    {
+                                        v = sv;
+                                        have_v = true;
+                                    }
+                                    else
+                                        j = sj;
+                                }
+                                pend = __ballot_sync(CRYO_FULL, !have_v);
                             }
                         }
+                        if (live)
+                            o.ring[p & WX_RMASK] = (uint8_t) v;
                         __syncwarp();
                     }
                     o.pos = end;

@@ -89,6 +89,7 @@ emu_zstdc_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap,
     a.cxcount = &cxcount;
     a.cxlist = cxlist.data();
     a.pf_done = pf_done.data();
+    a.early_frames = 0;
     a.pf_hint = 4u;                     /* every frame to the CTA-per-frame stage 4 */
     a.lit = (uint8_t *) ((((uintptr_t) lit.data() + 15) & ~(uintptr_t) 15));
     a.lit_stride = lit_stride;
@@ -97,6 +98,8 @@ emu_zstdc_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap,
     a.predef = predef;
     a.huftab = huftab.data();
     a.fsetab = fsetab.data();
+    const unsigned split = 2;           /* warps per group of the lane-serial stages (ZP_FOR_GROUP_BLOCKS) */
+
     emu::launch(dim3(1), dim3(32), 0, [&]() {
         if (threadIdx.x == 0)
             zp_stage1(a, 0);
@@ -104,17 +107,19 @@ emu_zstdc_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap,
     emu::launch(dim3(ZP_MAXB), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
         zp_stage2a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
-    emu::launch(dim3(ZP_MAXB), dim3(32), ZP2B_SMEM, [&]() {
-        zp_stage2b(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    emu::launch(dim3(split), dim3(32), ZP2B_SMEM, [&]() {
+        ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_HUFMASK, threadIdx.x, zp_stage2b(a, g, j, CRYO_SMEM_BASE(), threadIdx.x));
     });
     emu::launch(dim3(ZP_MAXB), dim3(32 * ZP3A_WARPS), ZP3A_SMEM, [&]() {
         zp_stage3a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
-    emu::launch(dim3(ZP_MAXB), dim3(32), ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), [&]() {
-        zp_stage3b<ZP3B_SMALL, 0, ZP3B_SMALL_LANES>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    emu::launch(dim3(split), dim3(32), ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), [&]() {
+        ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_SEQMASK, threadIdx.x,
+                            (zp_stage3b<ZP3B_SMALL, 0, ZP3B_SMALL_LANES>(a, g, j, CRYO_SMEM_BASE(), threadIdx.x)));
     });
-    emu::launch(dim3(ZP_MAXB), dim3(32), ZP3B_SMEM(ZP3B_LARGE, ZP_G), [&]() {
-        zp_stage3b<ZP3B_LARGE, ZP3B_SMALL, ZP_G>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    emu::launch(dim3(split), dim3(32), ZP3B_SMEM(ZP3B_LARGE, ZP_G), [&]() {
+        ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_SEQMASK, threadIdx.x,
+                            (zp_stage3b<ZP3B_LARGE, ZP3B_SMALL, ZP_G>(a, g, j, CRYO_SMEM_BASE(), threadIdx.x)));
     });
     if (getenv("CRYO_EMU_TRACE"))
         fprintf(stderr, "after stages 1-3: flag %u nblk %u route %u\n", flag[0], fr[0], fr[3]);

@@ -250,7 +250,10 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     a.cxcount = &cxcount;
     a.cxlist = cxlist.data();
     a.pf_done = pf_done.data();
-    a.pf_hint = 8u;                     /* every frame to the warp stage 4 (the CTA stage: emu_cx.cpp) */
+    /* every frame to the warp stage 4 (the CTA stage: emu_cx.cpp); bit 4: the early pass of stage 0 runs (ZP_EMU_NO_EARLY: not) */
+    const bool early_pass = getenv("ZP_EMU_NO_EARLY") == nullptr;
+    a.pf_hint = 8u;
+    a.early_frames = early_pass ? ((uint32_t) n + 1u) / 2u : 0u;     /* the last half of the batch */
     a.lit = (uint8_t *) ((((uintptr_t) lit.data() + 15) & ~(uintptr_t) 15));
     a.lit_stride = lit_stride;
     a.seq = seq.data();
@@ -260,6 +263,8 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     a.fsetab = fsetab.data();
 
     const unsigned ngroups = ((unsigned) n + ZP_G - 1) / ZP_G;
+    /* warps per group of the lane-serial stages (ZP_FOR_GROUP_BLOCKS): 1, 3 or 16 by the batch size, so the tests cover each */
+    const unsigned split = n % 3 == 0 ? 1u : n % 3 == 1 ? 3u : ZP_MAXB;
 
     emu::launch(dim3(((unsigned) n + 31) / 32), dim3(32), 0, [&]() {
         const uint32_t f = blockIdx.x * 32 + threadIdx.x;
@@ -276,8 +281,23 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
             for (uint32_t f = blockIdx.x; f < a.n; f += 3)
             {
                 __syncthreads();
+                if (threadIdx.x < 32)
+                {
+                    const uint32_t at = zp_frame_positions_warp<false>(a, f, threadIdx.x);
+
+                    if (threadIdx.x < ZP_MAXB)
+                        pos[threadIdx.x] = at;
+                }
+                __syncthreads();
                 if (threadIdx.x == 0)
-                    zp_frame_positions(a, f, pos);
+                {
+                    uint32_t serial[ZP_MAXB];
+
+                    zp_frame_positions_late(a, f, serial);
+                    for (uint32_t j = 0; j < ZP_MAXB; j++)
+                        if (serial[j] != pos[j])
+                            abort();            /* the warp version and the serial one must agree */
+                }
                 __syncthreads();
                 for (uint32_t j = 0; j < fr[(size_t) f * ZP_FF]; j++)
                 {
@@ -291,21 +311,44 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
             }
         });
     };
+    /* the early pass: raw / RLE blocks at the positions stage 1 guessed, before anything is measured */
+    if (early_pass)
+        emu::launch(dim3(3), dim3(128), 64, [&]() {
+            uint32_t *pos = reinterpret_cast<uint32_t *>(CRYO_SMEM_BASE());
+
+            for (uint32_t f = a.n - a.early_frames + blockIdx.x; f < a.n; f += 3)
+            {
+                __syncthreads();
+                if (threadIdx.x < 32)
+                {
+                    const uint32_t at = zp_frame_positions_warp<true>(a, f, threadIdx.x);
+
+                    if (threadIdx.x < ZP_MAXB)
+                        pos[threadIdx.x] = at;
+                }
+                __syncthreads();
+                for (uint32_t j = 0; j < fr[(size_t) f * ZP_FF]; j++)
+                    if (pos[j] != ~0u)
+                        zp_stage0(a, (f << 8) | j, pos[j], threadIdx.x, 128);
+            }
+        });
     emu::launch(dim3((((unsigned) n + 31) / 32) * ZP_MAXB), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
         zp_stage2a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
-    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP2B_SMEM, [&]() {
-        zp_stage2b(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    emu::launch(dim3(ngroups * split), dim3(32), ZP2B_SMEM, [&]() {
+        ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_HUFMASK, threadIdx.x, zp_stage2b(a, g, j, CRYO_SMEM_BASE(), threadIdx.x));
     });
     emu::launch(dim3((((unsigned) n + 31) / 32) * ZP_MAXB), dim3(32 * ZP3A_WARPS), ZP3A_SMEM, [&]() {
         zp_stage3a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
     });
-    emu::launch(dim3((((unsigned) n + ZP3B_SMALL_LANES - 1) / ZP3B_SMALL_LANES) * ZP_MAXB), dim3(32),
+    emu::launch(dim3(ngroups * split), dim3(32),
                 ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), [&]() {
-        zp_stage3b<ZP3B_SMALL, 0, ZP3B_SMALL_LANES>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+        ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_SEQMASK, threadIdx.x,
+                            (zp_stage3b<ZP3B_SMALL, 0, ZP3B_SMALL_LANES>(a, g, j, CRYO_SMEM_BASE(), threadIdx.x)));
     });
-    emu::launch(dim3(ngroups * ZP_MAXB), dim3(32), ZP3B_SMEM(ZP3B_LARGE, ZP_G), [&]() {
-        zp_stage3b<ZP3B_LARGE, ZP3B_SMALL, ZP_G>(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    emu::launch(dim3(ngroups * split), dim3(32), ZP3B_SMEM(ZP3B_LARGE, ZP_G), [&]() {
+        ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_SEQMASK, threadIdx.x,
+                            (zp_stage3b<ZP3B_LARGE, ZP3B_SMALL, ZP_G>(a, g, j, CRYO_SMEM_BASE(), threadIdx.x)));
     });
     if (!late_prefill)
         prefill();

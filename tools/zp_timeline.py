@@ -43,7 +43,7 @@ if os.environ.get("TL_LZ4_FIRST"):
     torch.cuda.synchronize()
     del l_src
 names = ["parse", "prefill", "huftab", "literals", "fsetab", "seq_small", "seq_large", "execute",
-         "lz4_route", "lz4_warp", "lz4_cta", "execute_cta", "zstd_warp"]
+         "lz4_route", "lz4_warp", "lz4_cta", "execute_cta", "zstd_warp", "prefill_early"]
 for it in range(4):
     L.cryogpu_debug_timeline(None, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
