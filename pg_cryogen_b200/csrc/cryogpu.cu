@@ -374,10 +374,10 @@ k_zp_prefetch_src(const ZpArgs a)
 }
 
 __global__ void __launch_bounds__(32 * ZP2A_WARPS)
-k_zp_huftab(const ZpArgs a)
+k_zp_huftab(const ZpArgs a, uint32_t split)
 {
     ZP_TL_BEGIN(2)
-    zp_stage2a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    ZP_FOR_GROUP_BLOCKS_CTA(a, blockIdx.x, split, ZPF_HUFMASK, threadIdx.x, zp_stage2a(a, g, j, CRYO_SMEM_BASE(), threadIdx.x));
     ZP_TL_END(2)
 }
 
@@ -390,10 +390,10 @@ k_zp_literals(const ZpArgs a, uint32_t split)
 }
 
 __global__ void __launch_bounds__(32 * ZP3A_WARPS)
-k_zp_fsetab(const ZpArgs a)
+k_zp_fsetab(const ZpArgs a, uint32_t split)
 {
     ZP_TL_BEGIN(4)
-    zp_stage3a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    ZP_FOR_GROUP_BLOCKS_CTA(a, blockIdx.x, split, ZPF_SEQMASK, threadIdx.x, zp_stage3a(a, g, j, CRYO_SMEM_BASE(), threadIdx.x));
     ZP_TL_END(4)
 }
 
@@ -878,28 +878,34 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
          * of the device holds, so that a batch whose warps all fit runs as ONE wave (a second, nearly empty wave
          * doubles the stage: its length is that of the longest chain), and at most one per block index.
          */
-        static int wave[3] = {0, 0, 0};         /* warps of stage 2b / 3b small / 3b large resident on the device */
+        static int wave[5] = {0, 0, 0, 0, 0};   /* warps of stage 2b / 3b small / 3b large, CTAs of 2a / 3a resident on the device */
 
         if (wave[0] == 0)
         {
-            int per_sm[3] = {1, 1, 1};
+            int per_sm[5] = {1, 1, 1, 1, 1};
 
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[3], k_zp_huftab, 32 * ZP2A_WARPS, ZP2A_SMEM);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[4], k_zp_fsetab, 32 * ZP3A_WARPS, ZP3A_SMEM);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[0], k_zp_literals, 32, ZP2B_SMEM);
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[1], k_zp_sequences_small, 32,
                                                           ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES));
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[2], k_zp_sequences_large, 32, ZP3B_SMEM(ZP3B_LARGE, ZP_G));
-            for (int k = 0; k < 3; k++)
+            for (int k = 0; k < 5; k++)
                 wave[k] = std::max(1, per_sm[k]) * sm_count;
         }
-        unsigned split[3];
+        unsigned split[5];
 
-        for (int k = 0; k < 3; k++)
+        for (int k = 0; k < 5; k++)
             split[k] = std::min<unsigned>(ZP_MAXB, std::max<unsigned>(1u, (unsigned) wave[k] / ngroups));
         /*
-         * The early pass of the raw / RLE stage (aux 1), beside the entropy stages: they are chains of dependent
-         * shared-memory reads that leave HBM idle for a third of the step, and the bulk-copy engine needs one
-         * thread per SM.  The frames are asked into L2 first, so that the window refills of the lane-serial
-         * stages do not queue behind the stores.  CRYOGPU_ZP_EARLY=0 / CRYOGPU_ZP_SRC_PREFETCH=0 switch them off.
+         * The compressed frames are asked into L2 first (aux 1): the lane-serial stages refill their windows from
+         * them one 256-byte piece per lane at a time, and a refill that goes to HBM stalls 32 chains
+         * (CRYOGPU_ZP_SRC_PREFETCH=0: off).
+         * Optional, off by default (CRYOGPU_ZP_EARLY_CTAS, CRYOGPU_ZP_EARLY_PCT): an early pass of the raw / RLE
+         * stage beside the entropy stages, which leave HBM idle for a third of the step -- the last PCT % of the
+         * frames at the positions stage 1 guessed.  Measured on the headline table: the stores stretch the literal
+         * stage (183 -> 270-300 us) by more than the executor's phase gains, 1.04-1.36 ms per step against 1.02
+         * (profiles/r02_early_pass.txt).
          */
         static int early_ctas = -1, early_pct = -1, src_prefetch = -1;
 
@@ -915,19 +921,22 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         a.early_frames = (early_ctas > 0 && !all_cx) ? (uint32_t) (n * (size_t) early_pct / 100) : 0u;
         cudaEventRecord(ev[0], st);
         cudaStreamWaitEvent(aux[0], ev[0], 0);
+        const bool do_prefetch = src_prefetch && !all_cx;      /* (aux 1 joins st again after the raw / RLE stage) */
+
+        if (a.early_frames || do_prefetch)
+            cudaStreamWaitEvent(aux[1], ev[0], 0);
+        if (do_prefetch)
+            k_zp_prefetch_src<<<(unsigned) ((n + 7) / 8), 256, 0, aux[1]>>>(a);
         if (a.early_frames)
         {
-            cudaStreamWaitEvent(aux[1], ev[0], 0);
-            if (src_prefetch)
-                k_zp_prefetch_src<<<(unsigned) ((n + 7) / 8), 256, 0, aux[1]>>>(a);
             k_zp_prefill_early<<<(unsigned) std::min<size_t>(a.early_frames, (size_t) early_ctas), ZP0_THREADS, 0, aux[1]>>>(a);
             cudaEventRecord(ev[3], aux[1]);
         }
-        k_zp_fsetab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP3A_WARPS, ZP3A_SMEM, aux[0]>>>(a);
+        k_zp_fsetab<<<ngroups * split[4], 32 * ZP3A_WARPS, ZP3A_SMEM, aux[0]>>>(a, split[4]);
         k_zp_sequences_small<<<ngroups * split[1], 32, ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), aux[0]>>>(a, split[1]);
         k_zp_sequences_large<<<ngroups * split[2], 32, ZP3B_SMEM(ZP3B_LARGE, ZP_G), aux[0]>>>(a, split[2]);
         cudaEventRecord(ev[1], aux[0]);
-        k_zp_huftab<<<(unsigned) ((n + 31) / 32) * ZP_MAXB, 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a);
+        k_zp_huftab<<<ngroups * split[3], 32 * ZP2A_WARPS, ZP2A_SMEM, st>>>(a, split[3]);
         k_zp_literals<<<ngroups * split[0], 32, ZP2B_SMEM, st>>>(a, split[0]);
         cudaStreamWaitEvent(st, ev[1], 0);
         if (all_cx)

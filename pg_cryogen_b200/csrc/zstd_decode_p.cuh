@@ -38,6 +38,7 @@
 #define ZP_PREFILL_MIN 2048u     /* raw / RLE blocks at least this long are written ahead by stage 0 */
 #define ZP_FF     6u            /* u32 fields per frame descriptor: nblk, fcs, has_fcs, route (1: stage 4 by a CTA, zstd_decode_c.cuh),
                                  * mask of the blocks with Huffman-coded literals, mask of the blocks with sequences */
+#define ZPB_RLEBYTE ZPB_LHDR     /* RLE blocks: the byte of the run (stage 4 then need not read the frame for it) */
 #define ZPF_HUFMASK 4u
 #define ZPF_SEQMASK 5u
 #define ZP_CX_SEQS 8192u        /* frames with at least this many sequences take the CTA-per-frame stage 4 */
@@ -47,7 +48,7 @@ enum
     ZPB_OFF = 0,                /* frame-relative offset of the block content */
     ZPB_BSIZE,                  /* content bytes (raw, compressed) or run length (RLE) */
     ZPB_KIND,                   /* bits 0-1 block type, 2-3 literal type, 4 four streams, 8-15 modes */
-    ZPB_LHDR,                   /* literals section header bytes */
+    ZPB_LHDR,                   /* literals section header bytes (an RLE block: its byte, ZPB_RLEBYTE) */
     ZPB_REGEN,                  /* literals regenerated size */
     ZPB_LCSIZE,                 /* literals compressed size (tree description included) */
     ZPB_HDOFF,                  /* frame-relative offset of the Huffman tree description in force */
@@ -182,6 +183,7 @@ CRYO_DEV bool zp_parse(const uint8_t *in, uint32_t csize, uint32_t cap, uint64_t
         {
             if (ip + 1 > csize)
                 return false;
+            b[ZPB_RLEBYTE] = in[ip];
             ip += 1;
         }
         else
@@ -402,6 +404,22 @@ CRYO_DEV uint32_t zp_group_mask(const ZpArgs &a, uint32_t g, uint32_t field, uin
 
     return __reduce_or_sync(CRYO_FULL, m);
 }
+/* the table stages (2a, 3a) take a group with a whole CTA: the same walk with a barrier between the calls */
+#define ZP_FOR_GROUP_BLOCKS_CTA(a, w, split, field, tid, call)                               \
+    {                                                                                        \
+        const uint32_t g_ = (w) / (split), c_ = (w) % (split);                               \
+        uint32_t m_ = zp_group_mask((a), g_, (field), (tid) & 31u);                          \
+                                                                                             \
+        for (uint32_t k_ = 0; m_; m_ &= m_ - 1u, k_++)                                       \
+        {                                                                                    \
+            if (k_ % (split) != c_)                                                          \
+                continue;                                                                    \
+            const uint32_t g = g_, j = (uint32_t) __ffs((int) m_) - 1u;                      \
+                                                                                             \
+            call;                                                                            \
+            __syncthreads();                                                                 \
+        }                                                                                    \
+    }
 #define ZP_FOR_GROUP_BLOCKS(a, w, split, field, lane, call)                                  \
     {                                                                                        \
         const uint32_t g_ = (w) / (split), c_ = (w) % (split);                               \
@@ -537,20 +555,29 @@ CRYO_DEV uint32_t zp_ld_acquire(const uint32_t *p)
 #endif
 }
 
+CRYO_DEV void zp_prefetch_l2(const uint8_t *p)
+{
+#ifndef CRYO_EMU
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void) p;
+#endif
+}
+
 /* --------------------------------------------------------------- stage 2: literals ---- */
 
 /*
- * 2a: one CTA per (32 frames x block index): the weights of the 32 trees decoded one lane per
+ * 2a: one CTA per (ZP_G frames x block index): the weights of the trees decoded one lane per
  *     tree, then each table filled by a warp straight into the block's slot of huftab (global,
  *     u16[2048] per slot); log and description length go into the block descriptor.
  * 2b: one warp per (8 frames x block index), 32 lanes = 8 blocks x 4 streams, tables read
  *     through L1.  No shared memory: the stage co-resides with anything.
  */
-#define ZP2A_WARPS      8u
+#define ZP2A_WARPS      4u
 #define ZP2A_LW         708u                    /* per tree: weights 256 | wfse 256 | wcounts 32 | wnext 128; odd word stride */
 #define ZP2A_DESC       176u                    /* staged tree description: 129 bytes at most + alignment slack */
-#define ZP2A_OFF_DESC   (32u * ZP2A_LW)         /* 22 656: multiple of 16 */
-#define ZP2A_OFF_WORK   (ZP2A_OFF_DESC + 32u * ZP2A_DESC)       /* per warp: symstart u16[256] | rankc u32[32] */
+#define ZP2A_OFF_DESC   (ZP_G * ZP2A_LW)        /* 5 664: multiple of 16 */
+#define ZP2A_OFF_WORK   (ZP2A_OFF_DESC + ZP_G * ZP2A_DESC)      /* per warp: symstart u16[256] | rankc u32[32] */
 #define ZP2A_OFF_META   (ZP2A_OFF_WORK + ZP2A_WARPS * 640u)
 #define ZP2A_SMEM       (ZP2A_OFF_META + 128u)
 
@@ -625,19 +652,21 @@ CRYO_DEV uint32_t zp_huf_weights(const uint8_t *src, uint32_t n, uint8_t *weight
 }
 
 /*
- * stage 2a body: one CTA of ZP2A_WARPS warps, block index j of frames [g * 32, g * 32 + 32).
- * Phase A, warp 0: lane i decodes the weights of frame g * 32 + i's tree (a serial chain per
- * tree: 32 of them in lockstep instead of one per warp).  Phase B: the warps share out the 32
- * tables, each filled by a whole warp straight into its global slot.
+ * stage 2a body: one CTA of ZP2A_WARPS warps, block index j of frames [g * ZP_G, g * ZP_G + ZP_G).
+ * Phase A, warp 0: lane i decodes the weights of frame g * ZP_G + i's tree (a serial chain per
+ * tree: ZP_G of them in lockstep instead of one per warp).  Phase B: one table per warp (with 32
+ * frames per CTA, as in round 1, a warp filled four tables one after the other and phase B was
+ * 57 % of the stage; profiles/r02n), filled straight into its global slot.  Called once per
+ * block index the CTA takes (ZP_FOR_GROUP_BLOCKS_CTA): a barrier separates the calls.
  */
 CRYO_DEV void zp_stage2a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem, uint32_t tid)
 {
     const uint32_t warp = tid >> 5, lane = tid & 31u;
     uint32_t *s_nw = reinterpret_cast<uint32_t *>(smem + ZP2A_OFF_META);        /* nw | used << 16, 0: nothing to build */
 
-    if (warp == 0)
+    if (warp == 0 && lane < ZP_G)
     {
-        const uint32_t f = g * 32u + lane;
+        const uint32_t f = g * ZP_G + lane;
         uint32_t meta = 0;
 
         if (f < a.n && a.fr[(size_t) f * ZP_FF] > j)
@@ -669,13 +698,13 @@ CRYO_DEV void zp_stage2a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         s_nw[lane] = meta;
     }
     __syncthreads();
-    for (uint32_t t = warp; t < 32u; t += ZP2A_WARPS)
+    for (uint32_t t = warp; t < ZP_G; t += ZP2A_WARPS)
     {
         const uint32_t meta = s_nw[t];
 
         if (meta == 0)
             continue;
-        const uint32_t f = g * 32u + t;
+        const uint32_t f = g * ZP_G + t;
         int32_t    log = 0;
         const bool ok = zsw_huf_table(smem + t * ZP2A_LW, meta & 0xFFFFu, a.huftab + ((size_t) f * ZP_MAXB + j) * 2048u,
                                       reinterpret_cast<uint16_t *>(smem + ZP2A_OFF_WORK + warp * 640u),
@@ -831,22 +860,28 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
     {                                                                        \
         __syncwarp();                                                        \
         g0 = (npos & ~15) - (int32_t) (ZP2B_WIN - 16u);                      \
-        _Pragma("unroll") for (int r_ = 0; r_ < 4; r_++)                     \
+        _Pragma("unroll") for (int r_ = 0; r_ < 2; r_++)                     \
         {                                                                    \
-            uint4 v_[4];                                                     \
-            _Pragma("unroll") for (int k_ = 0; k_ < 4; k_++)                 \
+            uint4 v_[8];                                                     \
+            _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++)                 \
             {                                                                \
-                const int32_t o_ = g0 + 16 * (4 * r_ + k_);                  \
+                const int32_t o_ = g0 + 16 * (8 * r_ + k_);                  \
                 v_[k_] = (act && o_ >= 0) ? ld16(abase + o_) : make_uint4(0, 0, 0, 0); \
             }                                                                \
-            _Pragma("unroll") for (int k_ = 0; k_ < 4; k_++)                 \
+            _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++)                 \
             {                                                                \
-                uint32_t *w_ = win + 4 * (4 * r_ + k_);                      \
+                uint32_t *w_ = win + 4 * (8 * r_ + k_);                      \
                 w_[0] = v_[k_].x;                                            \
                 w_[1] = v_[k_].y;                                            \
                 w_[2] = v_[k_].z;                                            \
                 w_[3] = v_[k_].w;                                            \
             }                                                                \
+        }                                                                    \
+        /* the bytes of the next refill into L2 meanwhile */                 \
+        if (act && g0 >= 256)                                                \
+        {                                                                    \
+            zp_prefetch_l2(abase + g0 - 128);                                \
+            zp_prefetch_l2(abase + g0 - 256);                                \
         }                                                                    \
         __syncwarp();                                                        \
     }
@@ -913,12 +948,13 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         used += (int32_t) nb_;                                               \
     }
 /* the window must hold the words of the next four symbols (at most two) and the fetch after them */
-#define ZP2B_ENSURE(on)                                                      \
-    if (__any_sync(CRYO_FULL, (on) && npos - g0 < 8))                        \
+#define ZP2B_ENSURE_N(on, bytes)                                             \
+    if (__any_sync(CRYO_FULL, (on) && npos - g0 < (bytes)))                  \
     {                                                                        \
         ZP2B_FILL();                                                         \
         cand = win[(npos - g0) >> 2];                                        \
     }
+#define ZP2B_ENSURE(on) ZP2B_ENSURE_N(on, 8)
     {
         /* head: single symbols until dst + i is 4-byte aligned */
         const uint32_t head = act ? min((uint32_t) ((4u - ((uintptr_t) dst & 3u)) & 3u), cnt) : 0u;
@@ -947,7 +983,10 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
             const bool on = q < quads;
             uint32_t   s0, s1, s2, s3;
 
-            ZP2B_ENSURE(on);
+            /* checked every fourth quad (the vote and its branch sit on every lane's chain): sixteen symbols take
+             * 176 bits, six refills of a word each at most */
+            if ((q & 3u) == 0)
+                ZP2B_ENSURE_N(on, 32);
             ZP2B_REFILL(on);
             ZP2B_DEC(s0, on);
             ZP2B_DEC(s1, on);
@@ -978,6 +1017,7 @@ CRYO_DEV void zp_stage2b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 #undef ZP2B_REFILL
 #undef ZP2B_DEC
 #undef ZP2B_ENSURE
+#undef ZP2B_ENSURE_N
 #undef ZP_SHR_C
 #undef ZP_SHL_C
     /* every bit under the end mark consumed, no more, no less */
@@ -1003,7 +1043,7 @@ CRYO_DEV uint32_t zp_low_bits(uint32_t v, uint32_t n)
 /* -------------------------------------------------------------- stage 3: sequences ---- */
 
 /*
- * 3a: one CTA per (32 frames x block index): the table descriptions of the 32 blocks read one
+ * 3a: one CTA per (ZP_G frames x block index): the table descriptions of the blocks read one
  *     lane per block, then each table built by a warp in shared memory and copied to the
  *     block's slot of fsetab (global, LL u32[512] | OF u32[256] | ML u32[512]); logs and the
  *     bitstream offset go into the descriptor.
@@ -1011,19 +1051,20 @@ CRYO_DEV uint32_t zp_low_bits(uint32_t v, uint32_t n)
  *     through L1, (ll, ml, offset value) written to the frame's sequence area.
  */
 #define ZP3_CELLS       1280u                   /* u32 cells per block slot */
-#define ZP3A_WARPS      8u
+#define ZP3A_WARPS      4u
 #define ZP3A_CNT        388u                    /* per block: counts i16[64] x 3; odd word stride */
 #define ZP3A_DESC       272u                    /* staged table descriptions per block */
-#define ZP3A_OFF_DESC   (32u * ZP3A_CNT)        /* 12 416: multiple of 16 */
-#define ZP3A_OFF_CELLS  (ZP3A_OFF_DESC + 32u * ZP3A_DESC)       /* per warp: u32[512], the table being built */
+#define ZP3A_OFF_DESC   (ZP_G * ZP3A_CNT)       /* 3 104: multiple of 16 */
+#define ZP3A_OFF_CELLS  (ZP3A_OFF_DESC + ZP_G * ZP3A_DESC)      /* per warp: u32[512], the table being built */
 #define ZP3A_OFF_WORK   (ZP3A_OFF_CELLS + ZP3A_WARPS * 2048u)   /* per warp: next u16[64] | cum u16[72] */
 #define ZP3A_OFF_META   (ZP3A_OFF_WORK + ZP3A_WARPS * 272u)
-#define ZP3A_SMEM       (ZP3A_OFF_META + 32u * 16u)
+#define ZP3A_SMEM       (ZP3A_OFF_META + ZP_G * 16u)
 
 /*
- * stage 3a body: one CTA of ZP3A_WARPS warps, block index j of frames [g * 32, g * 32 + 32).
- * Phase A, warp 0: lane i reads the three table descriptions of frame g * 32 + i's block
- * (serial bit parsing: 32 blocks in lockstep).  Phase B: the warps share out the 96 tables;
+ * stage 3a body: one CTA of ZP3A_WARPS warps, block index j of frames [g * ZP_G, g * ZP_G + ZP_G).
+ * Phase A, warp 0: lane i reads the three table descriptions of frame g * ZP_G + i's block
+ * (serial bit parsing: ZP_G blocks in lockstep).  Phase B: the warps share out the 3 * ZP_G tables
+ * (three each; twelve each with 32 frames per CTA, 78 % of the stage in round 1);
  * each is built by a whole warp in shared memory and copied to the block's global slot.
  */
 CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem, uint32_t tid)
@@ -1033,7 +1074,7 @@ CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 
     if (warp == 0)
     {
-        const uint32_t f = g * 32u + lane;
+        const uint32_t f = lane < ZP_G ? g * ZP_G + lane : a.n;
         uint32_t info[3] = {0, 0, 0}, bitoff = 0;   /* info: 1 << 31 | mode << 24 | rle sym or (nsym << 8 | log) */
 
         if (f < a.n && a.fr[(size_t) f * ZP_FF] > j)
@@ -1102,17 +1143,20 @@ CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
                 bitoff = b[ZPB_SEQOFF] + (staged - left);
             }
         }
-        s_meta[4 * lane + 0] = info[0];
-        s_meta[4 * lane + 1] = info[1];
-        s_meta[4 * lane + 2] = info[2];
-        s_meta[4 * lane + 3] = bitoff;
+        if (lane < ZP_G)
+        {
+            s_meta[4 * lane + 0] = info[0];
+            s_meta[4 * lane + 1] = info[1];
+            s_meta[4 * lane + 2] = info[2];
+            s_meta[4 * lane + 3] = bitoff;
+        }
     }
     __syncthreads();
     uint32_t *cell = reinterpret_cast<uint32_t *>(smem + ZP3A_OFF_CELLS + warp * 2048u);
     uint16_t *next = reinterpret_cast<uint16_t *>(smem + ZP3A_OFF_WORK + warp * 272u);
     uint16_t *cum = next + 64;
 
-    for (uint32_t w = warp; w < 96u; w += ZP3A_WARPS)
+    for (uint32_t w = warp; w < 3u * ZP_G; w += ZP3A_WARPS)
     {
         const uint32_t blkno = w / 3u, t = w % 3u;
         const uint32_t info = s_meta[4 * blkno + t];
@@ -1120,7 +1164,7 @@ CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         if (s_meta[4 * blkno] == 0)
             continue;
         const uint32_t mode = (info >> 24) & 3u;
-        const uint32_t f = g * 32u + blkno;
+        const uint32_t f = g * ZP_G + blkno;
         int32_t   logv = 0;
 
         __syncwarp();
@@ -1235,12 +1279,28 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
         const uint32_t *slot = a.fsetab + ((size_t) (g * LANES + (uint32_t) i) * ZP_MAXB + j) * ZP3_CELLS;
         uint32_t *cells = reinterpret_cast<uint32_t *>(smem) + (uint32_t) i * CELLS;
 
-        for (uint32_t k = lane; k < nl; k += 32)
-            cells[k] = slot[k];
-        for (uint32_t k = lane; k < no; k += 32)
-            cells[nl + k] = slot[512u + k];
-        for (uint32_t k = lane; k < nm; k += 32)
-            cells[nl + no + k] = slot[768u + k];
+        /* four loads in flight per lane (one at a time, a block's tables cost ten L2 round trips: a fifth of the
+         * stage's stall samples on the sparse table, profiles/r02n) */
+        for (uint32_t base = 0; base < nl + no + nm; base += 128u)
+        {
+            uint32_t v[4];
+
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++)
+            {
+                const uint32_t k = base + 32u * q + lane;
+
+                v[q] = k >= nl + no + nm ? 0u : slot[k < nl ? k : k < nl + no ? 512u + (k - nl) : 768u + (k - nl - no)];
+            }
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++)
+            {
+                const uint32_t k = base + 32u * q + lane;
+
+                if (k < nl + no + nm)
+                    cells[k] = v[q];
+            }
+        }
     }
     const uint32_t ll_log = logs & 0xFFu, of_log = (logs >> 8) & 0xFFu, ml_log = (logs >> 16) & 0x7Fu;
     const uint32_t *llt = reinterpret_cast<const uint32_t *>(smem) + (lane & (LANES - 1u)) * CELLS;
@@ -1300,22 +1360,28 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
     {                                                                        \
         __syncwarp();                                                        \
         g0 = ((P >> 3) & ~15) - (int32_t) (ZP3B_WIN - 16u);                  \
-        _Pragma("unroll") for (int r_ = 0; r_ < 4; r_++)                     \
+        _Pragma("unroll") for (int r_ = 0; r_ < 2; r_++)                     \
         {                                                                    \
-            uint4 v_[4];                                                     \
-            _Pragma("unroll") for (int k_ = 0; k_ < 4; k_++)                 \
+            uint4 v_[8];                                                     \
+            _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++)                 \
             {                                                                \
-                const int32_t o_ = g0 + 16 * (4 * r_ + k_);                  \
+                const int32_t o_ = g0 + 16 * (8 * r_ + k_);                  \
                 v_[k_] = (act && o_ >= 0) ? ld16(abase + o_) : make_uint4(0, 0, 0, 0); \
             }                                                                \
-            _Pragma("unroll") for (int k_ = 0; k_ < 4; k_++)                 \
+            _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++)                 \
             {                                                                \
-                uint32_t *w_ = win + 4 * (4 * r_ + k_);                      \
+                uint32_t *w_ = win + 4 * (8 * r_ + k_);                      \
                 w_[0] = v_[k_].x;                                            \
                 w_[1] = v_[k_].y;                                            \
                 w_[2] = v_[k_].z;                                            \
                 w_[3] = v_[k_].w;                                            \
             }                                                                \
+        }                                                                    \
+        /* the bytes of the next refill into L2 meanwhile */                 \
+        if (act && g0 >= 256)                                                \
+        {                                                                    \
+            zp_prefetch_l2(abase + g0 - 128);                                \
+            zp_prefetch_l2(abase + g0 - 256);                                \
         }                                                                    \
         __syncwarp();                                                        \
     }
@@ -1412,10 +1478,13 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 
 /* ---------------------------------------------------------------- stage 4: execute ---- */
 
+#ifndef ZP4_WARPS
 #define ZP4_WARPS       8u
+#endif
 #define ZP4_THREADS     (32u * ZP4_WARPS)
 #define ZP4_LITWIN      1024u                   /* literal window (the slow path uses its first ZSW_LITWIN bytes) */
-#define ZP4_PER_WARP    (WX_RING + ZP4_LITWIN)
+#define ZP4_DESC        (ZP_MAXB * ZP_BF * 4u)  /* the frame's block descriptors */
+#define ZP4_PER_WARP    (WX_RING + ZP4_LITWIN + ZP4_DESC)
 #define ZP4_SMEM        (ZP4_WARPS * ZP4_PER_WARP)
 #define ZP4_SPAN        1024u                   /* output bytes of one sub-batch: it is written ahead of o.pos in the ring */
 #define ZP4_BIG_LL      96u                     /* longer runs leave the batch path */
@@ -1474,9 +1543,15 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 /* stage 4 body: one warp, frame f */
 CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lane)
 {
-    if (f >= a.n || a.methods[f] != ZP_METHOD_ZSTD || a.flag[f] != 0 || a.fr[(size_t) f * ZP_FF + 3] != 0)
+    if (f >= a.n)
         return;
+    /* (loaded side by side: a chain of || would make them four round trips) */
+    const int32_t  method = a.methods[f];
+    const uint32_t flagged = a.flag[f], routed = a.fr[(size_t) f * ZP_FF + 3];
     const uint32_t nb = a.fr[(size_t) f * ZP_FF], cap = a.cap;
+
+    if (method != ZP_METHOD_ZSTD || flagged != 0 || routed != 0)
+        return;
     const uint8_t *in = a.src + a.src_off[f], *fin = in;    /* fin: for ZP4_CONFIRM, where `in` is shadowed */
     WOut     o;
     int      err = ST_OK;
@@ -1486,10 +1561,36 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
     uint32_t rle_lo = 0, rle_hi = 0;                       /* [rle_lo, rle_hi): skipped RLE blocks, all bytes = rle_byte */
     uint8_t  rle_byte = 0;
 
+    const uint32_t le_mask = 0xFFFFFFFFu >> (31u - lane);  /* lanes up to this one */
+    /*
+     * The frame's block descriptors -> shared memory in one go.  Read from global memory block by block, field
+     * after field, they were two dozen dependent round trips per frame while the raw / RLE stage keeps HBM busy:
+     * a tenth of the executor's stall samples (profiles/r02q).
+     */
+    uint32_t *sdesc = reinterpret_cast<uint32_t *>(smem + WX_RING + ZP4_LITWIN);
+
+    {
+        const uint32_t *gdesc = a.blk + (size_t) f * ZP_MAXB * ZP_BF;
+        const uint32_t words = nb * ZP_BF;
+
+        for (uint32_t k0 = 0; k0 < words; k0 += 128u)
+        {
+            uint32_t v[4];
+
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++)
+                v[q] = k0 + 32u * q + lane < words ? gdesc[k0 + 32u * q + lane] : 0u;
+#pragma unroll
+            for (uint32_t q = 0; q < 4; q++)
+                if (k0 + 32u * q + lane < words)
+                    sdesc[k0 + 32u * q + lane] = v[q];
+        }
+        __syncwarp();
+    }
     wx_init(o, a.dst + (size_t) f * a.dst_stride, cap, smem);
     for (uint32_t j = 0; j < nb && err == ST_OK; j++)
     {
-        const uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
+        const uint32_t *b = sdesc + j * ZP_BF;
         const uint32_t off = b[ZPB_OFF], bsize = b[ZPB_BSIZE], kind = b[ZPB_KIND], type = kind & 3u;
 
         if (type < 2)
@@ -1514,7 +1615,8 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                 o.flushed = o.pos & ~15u;
                 o.lo = o.flushed;
                 if (lane < o.pos - o.flushed)
-                    o.ring[(o.flushed + lane) & WX_RMASK] = type == 0 ? in[off + bsize - (o.pos - o.flushed) + lane] : in[off];
+                    o.ring[(o.flushed + lane) & WX_RMASK] = type == 0 ? in[off + bsize - (o.pos - o.flushed) + lane]
+                                                                      : (uint8_t) b[ZPB_RLEBYTE];
                 __syncwarp();
                 if (!early)
                 {
@@ -1523,13 +1625,13 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                     guard = o.pos;
                 }
                 /* consecutive RLE blocks of one byte form one range whose content is known */
-                if (type == 1 && rle_hi == o.pos - bsize && rle_byte == in[off] && rle_hi > rle_lo)
+                if (type == 1 && rle_hi == o.pos - bsize && rle_byte == (uint8_t) b[ZPB_RLEBYTE] && rle_hi > rle_lo)
                     rle_hi = o.pos;
                 else if (type == 1)
                 {
                     rle_lo = o.pos - bsize;
                     rle_hi = o.pos;
-                    rle_byte = in[off];
+                    rle_byte = (uint8_t) b[ZPB_RLEBYTE];
                 }
                 else
                     rle_lo = rle_hi = 0;
@@ -1538,7 +1640,7 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
             if (type == 0)
                 wx_literals(o, in + off, bsize, lane);
             else
-                wx_fill_byte(o, in[off], bsize, lane);
+                wx_fill_byte(o, (uint8_t) b[ZPB_RLEBYTE], bsize, lane);
             continue;
         }
         const uint32_t lt = (kind >> 2) & 3u, regen = b[ZPB_REGEN], nseq = b[ZPB_NSEQ];
@@ -1599,8 +1701,36 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                 /* repeat offsets, in order (RFC 8878 3.1.1.5) */
                 {
                     const uint32_t zmask = __ballot_sync(CRYO_FULL, my_ll == 0);
+                    /* the sequences in front of the load's first repeat code only push their offsets: done at once */
+                    const uint32_t repmask = __ballot_sync(CRYO_FULL, have && my_ov <= 3u);
+                    const uint32_t kfirst = repmask ? (uint32_t) __ffs((int) repmask) - 1u : g;
 
-                    for (uint32_t k = 0; k < g; k++)
+                    if (kfirst)
+                    {
+                        const uint32_t o1 = __shfl_sync(CRYO_FULL, my_ov, (int) (kfirst - 1u)) - 3u;
+                        const uint32_t o2 = __shfl_sync(CRYO_FULL, my_ov, (int) ((kfirst - 2u) & 31u)) - 3u;
+                        const uint32_t o3 = __shfl_sync(CRYO_FULL, my_ov, (int) ((kfirst - 3u) & 31u)) - 3u;
+
+                        if (lane < kfirst)
+                            my_off = my_ov - 3u;
+                        if (kfirst >= 3u)
+                        {
+                            rep2 = o3;
+                            rep1 = o2;
+                        }
+                        else if (kfirst == 2u)
+                        {
+                            rep2 = rep0;
+                            rep1 = o2;
+                        }
+                        else
+                        {
+                            rep2 = rep1;
+                            rep1 = rep0;
+                        }
+                        rep0 = o1;
+                    }
+                    for (uint32_t k = kfirst; k < g; k++)
                     {
                         const uint32_t ov = __shfl_sync(CRYO_FULL, my_ov, (int) k);
                         uint32_t moff;
@@ -1737,28 +1867,26 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                     /* match start | (window index of the first literal - start, biased) of this lane's sequence */
                     const uint32_t my_pack = ((my_mpos - pos0) & 0xFFFFu) |
                                              ((L.delta + my_lit - wb + 2048u - (my_start - pos0)) << 16);
+                    /* ring and window are one array (the window follows the ring): a byte's source is one index */
+                    const bool     far = __any_sync(CRYO_FULL, in && my_mpos - my_off < floor);    /* sources in global memory */
                     uint32_t       seqbase = k0;
 
                     for (uint32_t R = 0; R < span; R += 32)
                     {
                         const uint32_t d = e_rel - R;
                         const uint32_t marks = __reduce_or_sync(CRYO_FULL, (in && d < 32u) ? 1u << d : 0u);
-                        const uint32_t idx = (seqbase + __popc(marks & (0xFFFFFFFFu >> (31u - lane)))) & 31u;
+                        const uint32_t idx = (seqbase + __popc(marks & le_mask)) & 31u;
                         const uint32_t s_pack = __shfl_sync(CRYO_FULL, my_pack, (int) idx);
                         const uint32_t s_off = __shfl_sync(CRYO_FULL, my_off, (int) idx);
                         const uint32_t r = R + lane, p = pos0 + r, x = p - s_off;
                         const bool     live = r < span, lit = r < (s_pack & 0xFFFFu);
                         const bool     inside = live && !lit && s_off <= lane;     /* source in this step */
+                        const uint32_t at = lit ? r + (s_pack >> 16) + (WX_RING - 2048u) : x & WX_RMASK;
                         uint32_t       v = 0;
 
                         seqbase += __popc(marks);
                         if (live && !inside)
-                        {
-                            if (lit)
-                                v = L.win[r + (s_pack >> 16) - 2048u];
-                            else
-                                v = x >= floor ? o.ring[x & WX_RMASK] : o.out[x];
-                        }
+                            v = (far && !lit && x < floor) ? o.out[x] : o.ring[at];
                         uint32_t pend = __ballot_sync(CRYO_FULL, inside);
 
                         if (pend)

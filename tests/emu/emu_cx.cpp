@@ -104,14 +104,14 @@ emu_zstdc_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap,
         if (threadIdx.x == 0)
             zp_stage1(a, 0);
     });
-    emu::launch(dim3(ZP_MAXB), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
-        zp_stage2a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    emu::launch(dim3(split), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
+        ZP_FOR_GROUP_BLOCKS_CTA(a, blockIdx.x, split, ZPF_HUFMASK, threadIdx.x, zp_stage2a(a, g, j, CRYO_SMEM_BASE(), threadIdx.x));
     });
     emu::launch(dim3(split), dim3(32), ZP2B_SMEM, [&]() {
         ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_HUFMASK, threadIdx.x, zp_stage2b(a, g, j, CRYO_SMEM_BASE(), threadIdx.x));
     });
-    emu::launch(dim3(ZP_MAXB), dim3(32 * ZP3A_WARPS), ZP3A_SMEM, [&]() {
-        zp_stage3a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    emu::launch(dim3(split), dim3(32 * ZP3A_WARPS), ZP3A_SMEM, [&]() {
+        ZP_FOR_GROUP_BLOCKS_CTA(a, blockIdx.x, split, ZPF_SEQMASK, threadIdx.x, zp_stage3a(a, g, j, CRYO_SMEM_BASE(), threadIdx.x));
     });
     emu::launch(dim3(split), dim3(32), ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), [&]() {
         ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_SEQMASK, threadIdx.x,

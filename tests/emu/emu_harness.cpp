@@ -332,14 +332,14 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
                         zp_stage0(a, (f << 8) | j, pos[j], threadIdx.x, 128);
             }
         });
-    emu::launch(dim3((((unsigned) n + 31) / 32) * ZP_MAXB), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
-        zp_stage2a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    emu::launch(dim3(ngroups * split), dim3(32 * ZP2A_WARPS), ZP2A_SMEM, [&]() {
+        ZP_FOR_GROUP_BLOCKS_CTA(a, blockIdx.x, split, ZPF_HUFMASK, threadIdx.x, zp_stage2a(a, g, j, CRYO_SMEM_BASE(), threadIdx.x));
     });
     emu::launch(dim3(ngroups * split), dim3(32), ZP2B_SMEM, [&]() {
         ZP_FOR_GROUP_BLOCKS(a, blockIdx.x, split, ZPF_HUFMASK, threadIdx.x, zp_stage2b(a, g, j, CRYO_SMEM_BASE(), threadIdx.x));
     });
-    emu::launch(dim3((((unsigned) n + 31) / 32) * ZP_MAXB), dim3(32 * ZP3A_WARPS), ZP3A_SMEM, [&]() {
-        zp_stage3a(a, blockIdx.x / ZP_MAXB, blockIdx.x % ZP_MAXB, CRYO_SMEM_BASE(), threadIdx.x);
+    emu::launch(dim3(ngroups * split), dim3(32 * ZP3A_WARPS), ZP3A_SMEM, [&]() {
+        ZP_FOR_GROUP_BLOCKS_CTA(a, blockIdx.x, split, ZPF_SEQMASK, threadIdx.x, zp_stage3a(a, g, j, CRYO_SMEM_BASE(), threadIdx.x));
     });
     emu::launch(dim3(ngroups * split), dim3(32),
                 ZP3B_SMEM(ZP3B_SMALL, ZP3B_SMALL_LANES), [&]() {
