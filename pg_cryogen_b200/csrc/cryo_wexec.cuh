@@ -90,6 +90,32 @@ CRYO_DEV void wx_after_bulk(WOut &o, uint32_t n, uint32_t lane)
     __syncwarp();
 }
 
+/* the same when the bytes written were all b: the ring's tail needs no read-back (a load of bytes stored a moment
+ * ago waits for the store to land: the zero runs of a sparse block each cost a round trip that way) */
+CRYO_DEV void wx_after_fill(WOut &o, uint32_t n, uint8_t b, uint32_t lane)
+{
+    o.pos += n;
+    o.flushed = o.pos & ~15u;
+    __syncwarp();
+    if (n >= WX_RING)
+    {
+        /* the ring's whole reach lies inside the run: it can serve the matches that copy from the run's end
+         * (the first tuples after the zero run of a sparse block do) without a read of global memory */
+        const uint32_t w = (uint32_t) b * 0x01010101u;
+
+        for (uint32_t k = 16u * lane; k < WX_RING; k += 512u)
+            st16(o.ring + k, make_uint4(w, w, w, w));
+        o.lo = o.pos - (WX_RING - 64u);
+    }
+    else
+    {
+        o.lo = o.flushed;
+        if (lane < o.pos - o.flushed)
+            o.ring[(o.flushed + lane) & WX_RMASK] = b;
+    }
+    __syncwarp();
+}
+
 /* n literal bytes from src (shared or global memory, readable by every lane) */
 CRYO_DEV void wx_literals(WOut &o, const uint8_t *src, uint32_t n, uint32_t lane)
 {
@@ -113,7 +139,7 @@ CRYO_DEV void wx_fill_byte(WOut &o, uint8_t b, uint32_t n, uint32_t lane)
     {
         wx_drain_all(o, lane);
         team_fill_byte(o.out + o.pos, b, n, lane, 32);
-        wx_after_bulk(o, n, lane);
+        wx_after_fill(o, n, b, lane);
         return;
     }
     for (uint32_t i = lane; i < n; i += 32)
@@ -207,6 +233,18 @@ CRYO_DEV void wx_match(WOut &o, uint32_t off, uint32_t n, uint32_t lane)
 {
     if (n >= WX_BULK)
     {
+        if (off == 1 && o.pos > o.lo)
+        {
+            /* a run of the previous byte, which the ring still holds */
+            const uint8_t b = o.ring[(o.pos - 1u) & WX_RMASK];
+
+            wx_drain_all(o, lane);
+#ifndef ZP_ABLATE_FILLS         /* timing experiment only: the long runs are not written */
+            team_fill_byte(o.out + o.pos, b, n, lane, 32);
+#endif
+            wx_after_fill(o, n, b, lane);
+            return;
+        }
         wx_drain_all(o, lane);
         wx_bulk_match(o, off, n, lane);
         wx_after_bulk(o, n, lane);

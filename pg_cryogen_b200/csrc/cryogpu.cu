@@ -167,11 +167,14 @@ k_zstd_decode_w(const int32_t *methods, const uint8_t *src, const uint64_t *src_
 #ifndef ZP_EXEC_PREFETCH_DEFAULT
 #define ZP_EXEC_PREFETCH_DEFAULT 0
 #endif
+#ifndef ZP_PF_INFLIGHT_DEFAULT
+#define ZP_PF_INFLIGHT_DEFAULT 2        /* bulk groups (one per raw / RLE block) a CTA of the raw / RLE stage keeps in flight */
+#endif
 #ifndef ZP_EARLY_CTAS_DEFAULT
-#define ZP_EARLY_CTAS_DEFAULT 0         /* CTAs of the early pass of the raw / RLE stage (0: no early pass -- measured slower, see launch_zstd_decode) */
+#define ZP_EARLY_CTAS_DEFAULT (-1)      /* CTAs of the early pass of the raw / RLE stage (-1: one per SM, 0: no early pass) */
 #endif
 #ifndef ZP_EARLY_PCT_DEFAULT
-#define ZP_EARLY_PCT_DEFAULT 40         /* share of the batch's frames it takes, from the end */
+#define ZP_EARLY_PCT_DEFAULT 55         /* share of the batch's frames it takes, from the end */
 #endif
 
 /* phase-split pipeline (default zstd path): zstd_decode_p.cuh */
@@ -181,6 +184,27 @@ k_zp_parse(const ZpArgs a)
     ZP_TL_BEGIN(0)
     const uint32_t f = blockIdx.x * 32u + threadIdx.x;
 
+    /*
+     * The warp's frames are asked into L2 first (the first 32 KiB of each: a sparse or medium frame whole), line by
+     * line across the lanes.  Everything after this reads them piecemeal -- the walk from block header to block
+     * header below, the table descriptions, the 256-byte window refills of the lane-serial stages -- and each piece
+     * that has to come from HBM stalls a chain (pf_hint bit 4; CRYOGPU_ZP_SRC_PREFETCH=0: off).
+     */
+    if (a.pf_hint & 16u)
+    {
+        const bool     mine = f < a.n && a.methods[f] == ZP_METHOD_ZSTD;
+        const uint64_t my_off = mine ? a.src_off[f] : 0;
+        const uint32_t my_size = mine ? a.src_size[f] : 0;
+
+        for (uint32_t t = 0; t < 32u; t++)
+        {
+            const uint64_t off = __shfl_sync(CRYO_FULL, my_off, (int) t);
+            const uint32_t size = min(__shfl_sync(CRYO_FULL, my_size, (int) t), 32768u);
+
+            for (uint32_t o = 128u * threadIdx.x; o < size; o += 4096u)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.src + off + o));
+        }
+    }
     if (f < a.n)
         zp_stage1(a, f);
     ZP_TL_END(0)
@@ -207,25 +231,176 @@ zp0_bulk_store_hint(uint8_t *dst, const uint8_t *smem_src, uint32_t bytes, uint6
 
 #define ZP0_THREADS 128u                /* few registers beside the executor's three CTAs per SM */
 
+/* wait until at most k of the thread's bulk groups are pending (the instruction takes an immediate) */
+__device__ __forceinline__ void
+zp0_wait_pending(uint32_t k)
+{
+    switch (k)
+    {
+        case 0: asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.bulk.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.bulk.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.bulk.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.bulk.wait_group 6;" ::: "memory"); break;
+        case 7: asm volatile("cp.async.bulk.wait_group 7;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group 8;" ::: "memory"); break;
+    }
+}
+
+/*
+ * The raw / RLE stage.  Persistent, one CTA per SM.  Its unit of work is a run of one byte -- an RLE block (the zero
+ * runs of sparse cryo blocks: 73 % of the headline table's bytes), or a long run stage 4 hands over (ZP_JOBS: another
+ * 24 %) -- written by the bulk-copy engine: a 16 KiB pattern in shared memory, one elected thread issuing cp.async.bulk
+ * stores of it, no LSU or register traffic on an SM that is executing sequences at the same time.  One bulk group per
+ * unit, a.pf_inflight of them in flight; a unit is published (pf_done of its frame) when its group has completed.
+ * Raw blocks and unaligned edges go through ordinary stores.
+ */
+struct Zp0
+{
+    uint8_t  *pat;              /* shared: ZP0_CHUNK bytes of the current byte */
+    int       cur;              /* that byte, -1: none yet */
+    uint32_t  window;           /* groups in flight */
+    uint32_t  issued, published;        /* units committed / published (thread 0) */
+    uint32_t  ticket;           /* number of the job this CTA is waiting for, ~0u: none taken (thread 0) */
+    uint32_t  ring[8];          /* frames of the units not yet published (thread 0) */
+};
+
+/* n bytes of `byte` at dst (every thread of the CTA calls this with the same arguments); the unit belongs to frame f */
+__device__ __forceinline__ void
+zp0_unit_fill(const ZpArgs &a, Zp0 &z, uint8_t *dst, uint32_t n, int byte)
+{
+    if (byte != z.cur)
+    {
+        /* new pattern: the engine must have read the old one out first (every store so far is in a committed group) */
+        if (threadIdx.x == 0)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();
+        const uint32_t w = (uint32_t) byte * 0x01010101u;
+
+        for (uint32_t k = threadIdx.x; k < ZP0_CHUNK / 16u; k += ZP0_THREADS)
+            reinterpret_cast<uint4 *>(z.pat)[k] = make_uint4(w, w, w, w);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        z.cur = byte;
+    }
+    /* edges by hand, the 16-byte aligned body by the engine */
+    const uint32_t head = (16u - (uint32_t) ((uintptr_t) dst & 15u)) & 15u;
+    const uint32_t h = head < n ? head : n, body = (n - h) & ~15u, tail = n - h - body;
+
+    if (threadIdx.x < h)
+        dst[threadIdx.x] = (uint8_t) byte;
+    if (threadIdx.x < tail)
+        dst[h + body + threadIdx.x] = (uint8_t) byte;
+    if (threadIdx.x < h || threadIdx.x < tail)
+        __threadfence();                /* ordinary stores: fenced before the barrier in front of the unit's publication */
+    if (threadIdx.x == 0)
+    {
+        if (a.pf_hint & 1u)
+        {
+            uint64_t policy;
+
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            for (uint32_t o = 0; o < body; o += ZP0_CHUNK)
+                zp0_bulk_store_hint(dst + h + o, z.pat, body - o < ZP0_CHUNK ? body - o : ZP0_CHUNK, policy);
+        }
+        else
+            for (uint32_t o = 0; o < body; o += ZP0_CHUNK)
+                zp0_bulk_store(dst + h + o, z.pat, body - o < ZP0_CHUNK ? body - o : ZP0_CHUNK);
+    }
+}
+
+/* the unit just written (bulk stores issued by thread 0, ordinary stores fenced) is committed; units whose groups have
+ * completed are published.  publish = false: the early pass (nobody waits for its blocks: the kernel's end says it all) */
+__device__ __forceinline__ void
+zp0_unit_done(const ZpArgs &a, Zp0 &z, uint32_t f, bool publish, bool drain)
+{
+    __syncthreads();                    /* every thread's ordinary stores of the unit, fenced, before its publication */
+    if (threadIdx.x != 0)
+        return;
+    if (!drain)
+    {
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        z.ring[z.issued & 7u] = f;
+        z.issued++;
+    }
+    zp0_wait_pending(drain ? 0u : z.window - 1u);
+    const uint32_t complete = drain ? z.issued : (z.issued >= z.window - 1u ? z.issued - (z.window - 1u) : 0u);
+
+    if (z.published < complete)
+    {
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (; z.published < complete; z.published++)
+            if (publish)
+                zp_stage0_done(a, z.ring[z.published & 7u] << 8, 1u);
+    }
+}
+
+/*
+ * One job of stage 4's, if the CTA's ticket has come up.  Jobs are numbered as they are queued; a CTA holds one ticket
+ * (a fetch-and-add on the head: no two CTAs ever contend for a job -- claiming with compare-and-swap, 148 CTAs
+ * took 3.3 ms over the step's 6 898 jobs) and looks at its number's slot whenever it passes here.  Returns 1: served
+ * one; 0: not there yet; 2: never will be (stage 4 has finished and queued fewer).
+ */
+__device__ __forceinline__ uint32_t
+zp0_serve_job(const ZpArgs &a, Zp0 &z, uint32_t *s_job)
+{
+    uint32_t *ctl = reinterpret_cast<uint32_t *>(a.seq_alloc);
+
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint32_t w3 = 0, over = 0;
+
+        if (z.ticket == ~0u)
+            z.ticket = atomicAdd(ctl + ZPC_JOB_HEAD, 1u);
+        if (z.ticket < a.n * ZP_JOBS)
+            w3 = zp_ld_acquire(a.jobs + 4u * (size_t) z.ticket + 3);
+        if (!(w3 & ZP_JOB_READY) && zp_ld_acquire(ctl + ZPC_EXEC_DONE) >= a.exec_warps)
+        {
+            /* no more jobs will be queued: either ours is among them (its fields follow the slot's allocation at once) or not */
+            if (z.ticket < zp_ld_acquire(ctl + ZPC_JOB_TAIL))
+                for (uint32_t spin = 0; spin < 200000u && !(w3 & ZP_JOB_READY); spin++)
+                    w3 = zp_ld_acquire(a.jobs + 4u * (size_t) z.ticket + 3);
+            else
+                over = 1;
+        }
+        if (w3 & ZP_JOB_READY)
+        {
+            const uint32_t *job = a.jobs + 4u * (size_t) z.ticket;
+
+            s_job[0] = job[0];
+            s_job[1] = job[1];
+            s_job[2] = job[2];
+            z.ticket = ~0u;
+        }
+        s_job[3] = w3 | (over << 31);
+    }
+    __syncthreads();
+    if (!(s_job[3] & ZP_JOB_READY))
+        return (s_job[3] >> 31) ? 2u : 0u;
+    const uint32_t f = s_job[0];
+
+    zp0_unit_fill(a, z, a.dst + (size_t) f * a.dst_stride + s_job[1], s_job[2], (int) (s_job[3] & 0xFFu));
+    zp0_unit_done(a, z, f, true, false);
+    return 1u;
+}
+
 template <bool EARLY>
 __device__ __forceinline__ void zp_prefill_body(const ZpArgs &a)
 {
-    /*
-     * Persistent, one CTA per SM.  Frames are taken in index order, which is the order the
-     * executor's CTAs are dispatched in.  RLE blocks (the zero runs of sparse cryo blocks: 73 % of
-     * the headline table's bytes) are written by the bulk-copy engine: a 16 KiB pattern in shared
-     * memory, one elected thread issuing cp.async.bulk stores of it, no LSU or register traffic on
-     * an SM that is executing sequences at the same time.  Two frames are kept in flight; a
-     * frame is published (pf_done) when its bulk group has completed.  Raw blocks and unaligned
-     * edges go through ordinary stores.
-     */
     __shared__ __align__(128) uint8_t pat[ZP0_CHUNK];
-    __shared__ uint32_t spec[ZP_MAXB];
-    __shared__ uint32_t next_f;
-    int      cur = -1;                  /* byte the pattern holds */
-    uint32_t prev_f = ~0u, prev_did = 0;
+    __shared__ uint32_t spec[ZP_MAXB], s_len[ZP_MAXB], s_what[ZP_MAXB], s_off[ZP_MAXB];
+    __shared__ uint32_t next_f, s_job[4];
     uint32_t *counter = reinterpret_cast<uint32_t *>(a.seq_alloc) + (EARLY ? 5 : 4);    /* zeroed with seq_alloc */
+    Zp0       z;
 
+    z.pat = pat;
+    z.cur = -1;
+    z.window = a.pf_inflight > 8u ? 8u : a.pf_inflight < 1u ? 1u : a.pf_inflight;
+    z.issued = z.published = 0;
+    z.ticket = ~0u;
     /*
      * Frames are handed out by a counter, not by blockIdx: the CTAs of this kernel do not all become resident at
      * once beside the executor's (in some states of the process a third of them start a millisecond late, and
@@ -251,97 +426,76 @@ __device__ __forceinline__ void zp_prefill_body(const ZpArgs &a)
             /* EARLY: guessed by stage 1; otherwise exact: stage 3b has measured the Compressed blocks */
             const uint32_t at = zp_frame_positions_warp<EARLY>(a, f, threadIdx.x);
 
+            /* what the blocks are, side by side with their positions: read in the loop below, block after block, the
+             * descriptor and then the frame's byte were two dependent round trips per block, 10 us of a sparse frame's 25 */
             if (threadIdx.x < ZP_MAXB)
+            {
+                const uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + threadIdx.x) * ZP_BF;
+
                 spec[threadIdx.x] = at;
+                if (at != ~0u)
+                {
+                    s_len[threadIdx.x] = b[ZPB_BSIZE];
+                    s_off[threadIdx.x] = b[ZPB_OFF];
+                    s_what[threadIdx.x] = (b[ZPB_KIND] & 3u) == 0 ? ~0u : b[ZPB_RLEBYTE];   /* Raw, or the byte of the run */
+                }
+            }
         }
         __syncthreads();
-        uint32_t did = 0;
-
         for (uint32_t j = 0; j < nb; j++)
         {
             if (spec[j] == ~0u)
                 continue;
-            const uint32_t *b = a.blk + ((size_t) f * ZP_MAXB + j) * ZP_BF;
-            const uint32_t n = b[ZPB_BSIZE];
-            uint8_t *dst = out + spec[j];
-
-            did++;
-            if ((b[ZPB_KIND] & 3u) == 0)
+            if (s_what[j] == ~0u)
             {
-                team_copy(dst, in + b[ZPB_OFF], n, threadIdx.x, ZP0_THREADS);
+                team_copy(out + spec[j], in + s_off[j], s_len[j], threadIdx.x, ZP0_THREADS);
+                __threadfence();
+            }
+            else
+                zp0_unit_fill(a, z, out + spec[j], s_len[j], (int) s_what[j]);
+            zp0_unit_done(a, z, f, !EARLY, false);
+        }
+        /* (CRYOGPU_ZP_JOBS=2, pf_hint bit 5: a run stage 4 has handed over meanwhile after every frame, so that they do not
+         * pile up behind the frames.  Measured no better, and less even from run to run: off) */
+        if (!EARLY && a.jobs && (a.pf_hint & 32u))
+            zp0_serve_job(a, z, s_job);
+    }
+    if (!EARLY && a.jobs)
+    {
+        /* the frames are done: serve stage 4's runs until its warps have all finished and the queue is empty.  The wait is
+         * bounded (about 50 ms); a run nobody served is noticed afterwards (zp_stage5_check) */
+        for (uint32_t idle = 0; idle < 200000u;)
+        {
+            const uint32_t r = zp0_serve_job(a, z, s_job);
+
+            if (r == 2u)
+                break;
+            if (r == 1u)
+            {
+                idle = 0;
                 continue;
             }
-            const int byte = in[b[ZPB_OFF]];
-
-            if (byte != cur)
-            {
-                /* new pattern: the engine must have read the old one out first */
-                if (threadIdx.x == 0)
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                __syncthreads();
-                const uint32_t w = (uint32_t) byte * 0x01010101u;
-
-                for (uint32_t k = threadIdx.x; k < ZP0_CHUNK / 16u; k += ZP0_THREADS)
-                    reinterpret_cast<uint4 *>(pat)[k] = make_uint4(w, w, w, w);
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncthreads();
-                cur = byte;
-            }
-            /* edges by hand, the 16-byte aligned body by the engine */
-            const uint32_t head = (16u - (uint32_t) ((uintptr_t) dst & 15u)) & 15u;
-            const uint32_t h = head < n ? head : n, body = (n - h) & ~15u, tail = n - h - body;
-
-            if (threadIdx.x < h)
-                dst[threadIdx.x] = (uint8_t) byte;
-            if (threadIdx.x < tail)
-                dst[h + body + threadIdx.x] = (uint8_t) byte;
-            if (threadIdx.x == 0)
-            {
-                if (a.pf_hint & 1u)
-                {
-                    uint64_t policy;
-
-                    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-                    for (uint32_t o = 0; o < body; o += ZP0_CHUNK)
-                        zp0_bulk_store_hint(dst + h + o, pat, body - o < ZP0_CHUNK ? body - o : ZP0_CHUNK, policy);
-                }
-                else
-                    for (uint32_t o = 0; o < body; o += ZP0_CHUNK)
-                        zp0_bulk_store(dst + h + o, pat, body - o < ZP0_CHUNK ? body - o : ZP0_CHUNK);
-            }
+            __nanosleep(256);
+            idle++;
         }
-        /* one bulk group per frame; publish the previous frame once at most this one is pending */
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0)
-        {
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            if (prev_did)
-            {
-                asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
-                asm volatile("fence.proxy.async;" ::: "memory");
-                if (!EARLY)
-                    zp_stage0_done(a, prev_f << 8, prev_did);
-            }
-        }
-        prev_f = f;
-        prev_did = did;
     }
-    if (threadIdx.x == 0 && prev_did)
-    {
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-        asm volatile("fence.proxy.async;" ::: "memory");
-        if (!EARLY)
-            zp_stage0_done(a, prev_f << 8, prev_did);
-    }
+    zp0_unit_done(a, z, 0, !EARLY, true);
 }
 
 __global__ void __launch_bounds__(ZP0_THREADS)
 k_zp_prefill(const ZpArgs a)
 {
     ZP_TL_BEGIN(1)
+#ifndef ZP_ABLATE_PREFILL       /* timing experiment only: the raw / RLE blocks are left to the executor's time-out */
     zp_prefill_body<false>(a);
+#endif
     ZP_TL_END(1)
+}
+
+__global__ void __launch_bounds__(256)
+k_zp_check(const ZpArgs a)
+{
+    zp_stage5_check(a, blockIdx.x * 256u + threadIdx.x);
 }
 
 /*
@@ -358,20 +512,6 @@ k_zp_prefill_early(const ZpArgs a)
     ZP_TL_END(13)
 }
 
-/* the compressed frames into L2 ahead of the stages that read them lane by lane (hints only) */
-__global__ void __launch_bounds__(256)
-k_zp_prefetch_src(const ZpArgs a)
-{
-    const uint32_t f = blockIdx.x * 8u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
-
-    if (f >= a.n || a.methods[f] != ZP_METHOD_ZSTD)
-        return;
-    const uint8_t *p = a.src + a.src_off[f];
-    const uint32_t n = a.src_size[f];
-
-    for (uint32_t o = 128u * lane; o < n; o += 4096u)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
-}
 
 __global__ void __launch_bounds__(32 * ZP2A_WARPS)
 k_zp_huftab(const ZpArgs a, uint32_t split)
@@ -425,6 +565,12 @@ k_zp_execute(const ZpArgs a)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     zp_stage4(a, blockIdx.x * ZP4_WARPS + warp, CRYO_SMEM_BASE() + warp * ZP4_PER_WARP, lane);
+    /* stage 0 serves the runs this kernel hands over until every warp of it has said it is done */
+    if (a.jobs && lane == 0)
+    {
+        __threadfence();
+        atomicAdd(reinterpret_cast<uint32_t *>(a.seq_alloc) + ZPC_EXEC_DONE, 1u);
+    }
     ZP_TL_END(7)
 }
 
@@ -755,7 +901,7 @@ zp_bytes(size_t n, uint32_t cap)
 {
     return zp_al(n * ZP_FF * 4) + 3 * zp_al(n * 4) + zp_al(n * 8) + 256 + zp_al(n * ZP_MAXB * ZP_BF * 4) +
            zp_al(n * zp_lit_stride(cap)) + zp_al(zp_seq_cap(n, cap) * 8) + zp_al(n * ZP_MAXB * 4096) +
-           zp_al(n * ZP_MAXB * ZP3_CELLS * 4);
+           zp_al(n * ZP_MAXB * ZP3_CELLS * 4) + zp_al(n * ZP_JOBS * 16) + zp_al(n * 4);
 }
 
 static void
@@ -787,6 +933,10 @@ zp_carve(ZpArgs &a, void *base, size_t n, uint32_t cap)
     a.huftab = (uint16_t *) p;
     p += zp_al(n * ZP_MAXB * 4096);
     a.fsetab = (uint32_t *) p;
+    p += zp_al(n * ZP_MAXB * ZP3_CELLS * 4);
+    a.jobs = (uint32_t *) p;
+    p += zp_al(n * ZP_JOBS * 16);
+    a.pf_expect = (uint32_t *) p;
 }
 
 static void
@@ -825,9 +975,11 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
 
             if (hint < 0)
             {
-                const char *e = getenv("CRYOGPU_ZP_PREFILL_L2HINT"), *x = getenv("CRYOGPU_ZP_EXEC_PREFETCH");
+                const char *e = getenv("CRYOGPU_ZP_PREFILL_L2HINT"), *x = getenv("CRYOGPU_ZP_EXEC_PREFETCH"),
+                           *s = getenv("CRYOGPU_ZP_SRC_PREFETCH");
 
-                hint = (e ? atoi(e) != 0 : ZP_L2HINT_DEFAULT) | ((x ? atoi(x) != 0 : ZP_EXEC_PREFETCH_DEFAULT) << 1);
+                hint = (e ? atoi(e) != 0 : ZP_L2HINT_DEFAULT) | ((x ? atoi(x) != 0 : ZP_EXEC_PREFETCH_DEFAULT) << 1) |
+                       ((s ? atoi(s) != 0 : 1) << 4);
             }
             a.pf_hint = (uint32_t) hint;
         }
@@ -852,7 +1004,28 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             a.pf_hint |= 4u;
         else if (exec_choice == 1)
             a.pf_hint |= 8u;
-        cudaMemsetAsync(a.seq_alloc, 0, 32, st);       /* + the work counters of k_zp_execute_c and k_zp_prefill */
+        cudaMemsetAsync(a.seq_alloc, 0, 64, st);       /* + the work counters of k_zp_execute_c and k_zp_prefill, the job queue's */
+        {
+            /* long runs of stage 4 handed to stage 0 (ZP_JOBS); CRYOGPU_ZP_JOBS=0: stage 4 writes them itself */
+            static int use_jobs = -1;
+
+            if (use_jobs < 0)
+            {
+                const char *e = getenv("CRYOGPU_ZP_JOBS");
+
+                use_jobs = e ? atoi(e) : 1;
+            }
+            if (use_jobs == 2)
+                a.pf_hint |= 32u;
+            if (!use_jobs || all_cx)
+            {
+                a.jobs = nullptr;
+                a.pf_expect = nullptr;
+            }
+            else
+                cudaMemsetAsync(a.jobs, 0, n * ZP_JOBS * 16, st);
+            a.exec_warps = (uint32_t) ((n + ZP4_WARPS - 1) / ZP4_WARPS) * ZP4_WARPS;
+        }
         k_zp_parse<<<(unsigned) ((n + 31) / 32), 32, 0, st>>>(a);
         /*
          * literals (st) and sequences (aux 0) are independent of each other and bound by latency.
@@ -898,37 +1071,41 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
         for (int k = 0; k < 5; k++)
             split[k] = std::min<unsigned>(ZP_MAXB, std::max<unsigned>(1u, (unsigned) wave[k] / ngroups));
         /*
-         * The compressed frames are asked into L2 first (aux 1): the lane-serial stages refill their windows from
-         * them one 256-byte piece per lane at a time, and a refill that goes to HBM stalls 32 chains
-         * (CRYOGPU_ZP_SRC_PREFETCH=0: off).
-         * Optional, off by default (CRYOGPU_ZP_EARLY_CTAS, CRYOGPU_ZP_EARLY_PCT): an early pass of the raw / RLE
-         * stage beside the entropy stages, which leave HBM idle for a third of the step -- the last PCT % of the
-         * frames at the positions stage 1 guessed.  Measured on the headline table: the stores stretch the literal
-         * stage (183 -> 270-300 us) by more than the executor's phase gains, 1.04-1.36 ms per step against 1.02
-         * (profiles/r02_early_pass.txt).
+         * The early pass of the raw / RLE stage (aux 1; CRYOGPU_ZP_EARLY_CTAS, CRYOGPU_ZP_EARLY_PCT): beside the entropy
+         * stages, which leave HBM idle for a third of the step, the raw / RLE blocks of the last PCT % of the frames are
+         * written at the positions stage 1 guessed.  Alone it gained nothing (its stores stretch the literal stage, and the
+         * executor took its 480 us with or without the raw / RLE stage beside it: 1.04-1.36 ms per step against 1.02);
+         * with the executor's long runs handed to stage 0 as well (ZP_JOBS) the executor is down to its sequence work and
+         * the step follows the bytes: 0.90 ms at 50-60 %, 1.0-1.15 at 70-100 % (profiles/r02_early_pass.txt).
          */
-        static int early_ctas = -1, early_pct = -1, src_prefetch = -1;
+        static int early_ctas = -1, early_pct = -1;
 
         if (early_ctas < 0)
         {
-            const char *e = getenv("CRYOGPU_ZP_EARLY_CTAS"), *q = getenv("CRYOGPU_ZP_EARLY_PCT"),
-                       *x = getenv("CRYOGPU_ZP_SRC_PREFETCH");
+            const char *e = getenv("CRYOGPU_ZP_EARLY_CTAS"), *q = getenv("CRYOGPU_ZP_EARLY_PCT");
 
             early_ctas = e ? atoi(e) : ZP_EARLY_CTAS_DEFAULT;
+            if (early_ctas < 0)
+                early_ctas = sm_count;
             early_pct = q ? std::min(100, std::max(0, atoi(q))) : ZP_EARLY_PCT_DEFAULT;
-            src_prefetch = x ? atoi(x) != 0 : 1;
         }
         a.early_frames = (early_ctas > 0 && !all_cx) ? (uint32_t) (n * (size_t) early_pct / 100) : 0u;
+        {
+            static int inflight = -1;           /* 128 KiB groups of the raw / RLE stage in flight per CTA */
+
+            if (inflight < 0)
+            {
+                const char *e = getenv("CRYOGPU_ZP_PF_INFLIGHT");
+
+                inflight = e && atoi(e) > 0 ? atoi(e) : ZP_PF_INFLIGHT_DEFAULT;
+            }
+            a.pf_inflight = (uint32_t) inflight;
+        }
         cudaEventRecord(ev[0], st);
         cudaStreamWaitEvent(aux[0], ev[0], 0);
-        const bool do_prefetch = src_prefetch && !all_cx;      /* (aux 1 joins st again after the raw / RLE stage) */
-
-        if (a.early_frames || do_prefetch)
-            cudaStreamWaitEvent(aux[1], ev[0], 0);
-        if (do_prefetch)
-            k_zp_prefetch_src<<<(unsigned) ((n + 7) / 8), 256, 0, aux[1]>>>(a);
         if (a.early_frames)
         {
+            cudaStreamWaitEvent(aux[1], ev[0], 0);
             k_zp_prefill_early<<<(unsigned) std::min<size_t>(a.early_frames, (size_t) early_ctas), ZP0_THREADS, 0, aux[1]>>>(a);
             cudaEventRecord(ev[3], aux[1]);
         }
@@ -961,6 +1138,8 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
             if (exec_choice != 1)
                 k_zp_execute_c<<<(unsigned) std::min<size_t>(n, (size_t) sm_count), CX_THREADS, ZC_SMEM, st>>>(a, cx_counter);
             cudaStreamWaitEvent(st, ev[2], 0);
+            if (a.jobs)
+                k_zp_check<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(a);
         }
         /* frames the pipeline declined (flag set): decoded from scratch, one warp per frame */
         k_zstd_decode_w<<<(unsigned) ((n + ZSW_WARPS - 1) / ZSW_WARPS), ZSW_THREADS, ZSW_SMEM, st>>>(

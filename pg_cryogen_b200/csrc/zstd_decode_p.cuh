@@ -38,6 +38,18 @@
 #define ZP_PREFILL_MIN 2048u     /* raw / RLE blocks at least this long are written ahead by stage 0 */
 #define ZP_FF     6u            /* u32 fields per frame descriptor: nblk, fcs, has_fcs, route (1: stage 4 by a CTA, zstd_decode_c.cuh),
                                  * mask of the blocks with Huffman-coded literals, mask of the blocks with sequences */
+/*
+ * Long runs handed from stage 4 to stage 0 (round 2): the ~120 KB zero-run matches of a sparse frame, 96 % of the bytes
+ * the warp executor wrote, stalled it for a quarter of its time beside the raw / RLE stage (profiles/r02_ablation.txt);
+ * stage 0 has the bulk-copy engine.  A job is (frame, position, length, byte | ZP_JOB_READY), queued by stage 4 and
+ * taken by stage 0's CTAs once their frames are done; it counts as one more block in pf_done.
+ */
+#define ZP_JOBS        2u       /* per frame */
+#define ZP_JOB_MIN     32768u   /* bytes */
+#define ZP_JOB_READY   0x100u
+#define ZPC_JOB_TAIL   8u       /* u32 indices into the control words at seq_alloc: jobs queued, */
+#define ZPC_JOB_HEAD   9u       /* tickets taken, */
+#define ZPC_EXEC_DONE  10u      /* warps of k_zp_execute that have finished */
 #define ZPB_RLEBYTE ZPB_LHDR     /* RLE blocks: the byte of the run (stage 4 then need not read the frame for it) */
 #define ZPF_HUFMASK 4u
 #define ZPF_SEQMASK 5u
@@ -90,7 +102,11 @@ struct ZpArgs
     uint32_t        early_frames; /* the early pass of stage 0 takes the last early_frames frames of the batch (0: there is none) */
     uint32_t        pf_hint;    /* bit 0: stage 0 bulk stores with the L2 evict_first policy; bit 1: stage 4 asks L2 for
                                  * sequences and literals a few loads ahead; bit 2: every frame takes the CTA-per-frame
-                                 * stage 4 (small batches); bit 3: none does */
+                                 * stage 4 (small batches); bit 3: none does; bit 4: stage 1 asks the frames into L2 */
+    uint32_t       *jobs;       /* n x ZP_JOBS x 4 words, zeroed per call; nullptr: stage 4 writes its long runs itself */
+    uint32_t       *pf_expect;  /* n; blocks + jobs stage 4 left to stage 0 (checked against pf_done after both) */
+    uint32_t        exec_warps; /* warps of the k_zp_execute launch */
+    uint32_t        pf_inflight; /* stage 0: 128 KiB bulk groups a CTA keeps in flight (head-of-line blocking, see k_zp_prefill) */
     uint8_t        *lit;        /* n x lit_stride: Huffman-decoded literals */
     uint64_t        lit_stride; /* multiple of 16, >= cap + 16 * ZP_MAXB */
     uint64_t       *seq;        /* ll | ml << 17 | offset_value << 35 */
@@ -350,6 +366,8 @@ CRYO_DEV void zp_stage1(const ZpArgs &a, uint32_t f)
     fr[ZPF_SEQMASK] = 0;
     a.flag[f] = 0;
     a.pf_done[f] = 0;
+    if (a.pf_expect)
+        a.pf_expect[f] = 0;
     if (a.methods[f] != ZP_METHOD_ZSTD)
         return;
     uint32_t seq_total = 0;
@@ -541,6 +559,15 @@ CRYO_DEV void zp_stage0_done(const ZpArgs &a, uint32_t item, uint32_t blocks)
 {
     __threadfence();
     atomicAdd(a.pf_done + (item >> 8), blocks);
+}
+
+CRYO_DEV void zp_st_release(uint32_t *p, uint32_t v)
+{
+#ifdef CRYO_EMU
+    *reinterpret_cast<volatile uint32_t *>(p) = v;
+#else
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
 }
 
 CRYO_DEV uint32_t zp_ld_acquire(const uint32_t *p)
@@ -1228,7 +1255,7 @@ CRYO_DEV void zp_stage3a(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 #define ZP3B_LARGE      ZP3_CELLS
 #define ZP3B_WIN        256u
 #define ZP3B_WSTRIDE    (ZP3B_WIN / 4u + 1u)
-#define ZP3B_SMEM(cells, lanes) ((lanes) * (cells) * 4u + 32u * ZP3B_WSTRIDE * 4u + 96u * 4u)   /* cells | windows | LL, ML code tables */
+#define ZP3B_SMEM(cells, lanes) ((lanes) * (cells) * 4u + (lanes) * ZP3B_WSTRIDE * 4u + 96u * 4u)   /* cells | windows | LL, ML code tables */
 #define ZP3B_SMALL_LANES 8u                     /* blocks per warp in the small class (32 measured slower: 265 vs 221 us) */
 
 template <uint32_t CELLS, uint32_t BELOW, uint32_t LANES>   /* groups of LANES frames needing > BELOW and <= CELLS cells */
@@ -1333,7 +1360,9 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
      * store hang off it.  Round 1 drew every field from one shift-register accumulator with three
      * conditional refills per sequence: 154 dependent instructions, 1 300 cycles per sequence.
      */
-    uint32_t *win = reinterpret_cast<uint32_t *>(smem + LANES * CELLS * 4u) + lane * ZP3B_WSTRIDE;
+    /* a window per working lane (the others only read: with windows for all 32 the small class took 18.9 KB a warp, and
+     * the sequence warps of the sparse table left room for two of its three literal warps per SM) */
+    uint32_t *win = reinterpret_cast<uint32_t *>(smem + LANES * CELLS * 4u) + (lane & (LANES - 1u)) * ZP3B_WSTRIDE;
     const uint8_t *abase = src - ((uintptr_t) src & 15u);
     const int32_t  delta = (int32_t) ((uintptr_t) src & 15u);
     int32_t  P = 0;                             /* bit offset from abase */
@@ -1368,14 +1397,15 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
                 const int32_t o_ = g0 + 16 * (8 * r_ + k_);                  \
                 v_[k_] = (act && o_ >= 0) ? ld16(abase + o_) : make_uint4(0, 0, 0, 0); \
             }                                                                \
-            _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++)                 \
-            {                                                                \
-                uint32_t *w_ = win + 4 * (8 * r_ + k_);                      \
-                w_[0] = v_[k_].x;                                            \
-                w_[1] = v_[k_].y;                                            \
-                w_[2] = v_[k_].z;                                            \
-                w_[3] = v_[k_].w;                                            \
-            }                                                                \
+            if (lane < LANES)                                                \
+                _Pragma("unroll") for (int k_ = 0; k_ < 8; k_++)             \
+                {                                                            \
+                    uint32_t *w_ = win + 4 * (8 * r_ + k_);                  \
+                    w_[0] = v_[k_].x;                                        \
+                    w_[1] = v_[k_].y;                                        \
+                    w_[2] = v_[k_].z;                                        \
+                    w_[3] = v_[k_].w;                                        \
+                }                                                            \
         }                                                                    \
         /* the bytes of the next refill into L2 meanwhile */                 \
         if (act && g0 >= 256)                                                \
@@ -1405,7 +1435,7 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
     }
     ZP3B_FILL();
     /* code -> baseline | extra bits << 24, from shared memory in the loop */
-    uint32_t *packs = reinterpret_cast<uint32_t *>(smem + LANES * CELLS * 4u + 32u * ZP3B_WSTRIDE * 4u);
+    uint32_t *packs = reinterpret_cast<uint32_t *>(smem + LANES * CELLS * 4u + LANES * ZP3B_WSTRIDE * 4u);
 
     for (uint32_t k = lane; k < 36u + 53u; k += 32)
         packs[k] = k < 36u ? CRYO_GLD(ZS_LL_PACK[k]) : CRYO_GLD(ZS_ML_PACK[k - 36u]);
@@ -1483,7 +1513,7 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
 #endif
 #define ZP4_THREADS     (32u * ZP4_WARPS)
 #define ZP4_LITWIN      1024u                   /* literal window (the slow path uses its first ZSW_LITWIN bytes) */
-#define ZP4_DESC        (ZP_MAXB * ZP_BF * 4u)  /* the frame's block descriptors */
+#define ZP4_DESC        (ZP_MAXB * ZP_BF * 4u + ZP_JOBS * 16u)  /* the frame's block descriptors | the runs handed to stage 0 (position, length, byte) */
 #define ZP4_PER_WARP    (WX_RING + ZP4_LITWIN + ZP4_DESC)
 #define ZP4_SMEM        (ZP4_WARPS * ZP4_PER_WARP)
 #define ZP4_SPAN        1024u                   /* output bytes of one sub-batch: it is written ahead of o.pos in the ring */
@@ -1535,9 +1565,12 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
                 }                                                                            \
                 at_ += bb_[ZPB_OUTSZ];                                                       \
             }                                                                                \
+            for (uint32_t kk_ = 0; kk_ < njobs; kk_++)                                       \
+                team_fill_byte(o.out + sjobs[4u * kk_], (uint8_t) sjobs[4u * kk_ + 2u], sjobs[4u * kk_ + 1u], lane, 32); \
             __syncwarp();                                                                    \
         }                                                                                    \
         confirmed = skipped;                                                                 \
+        hull_lo = ~0u;                                                                       \
     }
 
 /* stage 4 body: one warp, frame f */
@@ -1558,6 +1591,7 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
     uint32_t rep0 = 1, rep1 = 4, rep2 = 8;
     uint32_t skipped = 0, confirmed = 0, skipmask = 0;     /* blocks left to stage 0 */
     uint32_t guard = 0;                                    /* positions below may not be written yet (see ZP4_CONFIRM) */
+    uint32_t hull_lo = ~0u;                                /* ... and none below this is stage 0's to write: [hull_lo, guard) spans what it owes */
     uint32_t rle_lo = 0, rle_hi = 0;                       /* [rle_lo, rle_hi): skipped RLE blocks, all bytes = rle_byte */
     uint8_t  rle_byte = 0;
 
@@ -1568,6 +1602,8 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
      * a tenth of the executor's stall samples (profiles/r02q).
      */
     uint32_t *sdesc = reinterpret_cast<uint32_t *>(smem + WX_RING + ZP4_LITWIN);
+    uint32_t *sjobs = sdesc + ZP_MAXB * ZP_BF;
+    uint32_t  njobs = 0;                                   /* runs handed to stage 0 */
 
     {
         const uint32_t *gdesc = a.blk + (size_t) f * ZP_MAXB * ZP_BF;
@@ -1620,6 +1656,8 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                 __syncwarp();
                 if (!early)
                 {
+                    if (skipped == confirmed)
+                        hull_lo = o.pos - bsize;
                     skipped++;
                     skipmask |= 1u << j;
                     guard = o.pos;
@@ -1816,8 +1854,13 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
 
                         const uint32_t sp1 = o.pos + ll - moff, need = ml < moff ? ml : moff;
                         const bool     known = sp1 >= rle_lo && sp1 + need <= rle_hi;
+                        /* a copy that starts inside the known range and runs out of its end (the zeros in front of a block's
+                         * first tuple and the tuple's first bytes): the known part is a fill, the rest an ordinary match */
+                        const uint32_t head_known = (!known && moff >= ml && sp1 >= rle_lo && sp1 < rle_hi) ? rle_hi - sp1 : 0u;
 
-                        if (!known && sp1 < guard && skipped > confirmed)
+                        /* (a source the ring still holds is read from there whether or not stage 0 has written it) */
+                        if (!known && sp1 + head_known < guard && sp1 + need > hull_lo && skipped > confirmed &&
+                            !(ll < WX_BULK && ml < WX_BULK && moff <= WX_RING - 64u && sp1 >= o.lo))
                         {
                             need_confirm = true;
                             continue;
@@ -1826,6 +1869,53 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                         zsw_lits_emit(o, L, ll, lane);
                         if (known)
                             wx_fill_byte(o, rle_byte, ml, lane);        /* a copy of known bytes: no read */
+                        else if (a.jobs && moff == 1u && ml >= ZP_JOB_MIN && njobs < ZP_JOBS && o.pos > o.lo)
+                        {
+                            /* a long run of the previous byte: stage 0's job (see ZP_JOBS) */
+                            const uint8_t  rb = o.ring[(o.pos - 1u) & WX_RMASK];
+                            const uint32_t at = o.pos;
+
+                            wx_drain_all(o, lane);
+                            if (lane == 0)
+                            {
+                                uint32_t *ctl = reinterpret_cast<uint32_t *>(a.seq_alloc);
+                                uint32_t *job = a.jobs + 4u * (size_t) atomicAdd(ctl + ZPC_JOB_TAIL, 1u);
+
+                                job[0] = f;
+                                job[1] = at;
+                                job[2] = ml;
+                                __threadfence();
+                                zp_st_release(job + 3, (uint32_t) rb | ZP_JOB_READY);
+                                sjobs[4u * njobs] = at;
+                                sjobs[4u * njobs + 1u] = ml;
+                                sjobs[4u * njobs + 2u] = rb;
+                            }
+                            /* the known range goes on through a few literals of the same byte (a sparse block's second
+                             * zero run starts one literal zero after its RLE blocks) */
+                            const uint32_t gap = at - rle_hi;
+                            const bool     joins = rle_hi > rle_lo && rle_byte == rb && at >= rle_hi && gap <= 8u && rle_hi >= o.lo &&
+                                                   __all_sync(CRYO_FULL, lane >= gap || o.ring[(rle_hi + lane) & WX_RMASK] == rb);
+
+                            wx_after_fill(o, ml, rb, lane);
+                            if (skipped == confirmed)
+                                hull_lo = at;
+                            njobs++;
+                            skipped++;
+                            guard = o.pos;
+                            if (joins)
+                                rle_hi = o.pos;
+                            else
+                            {
+                                rle_lo = at;
+                                rle_hi = o.pos;
+                                rle_byte = rb;
+                            }
+                        }
+                        else if (head_known)
+                        {
+                            wx_fill_byte(o, rle_byte, head_known, lane);
+                            wx_match(o, moff, ml - head_known, lane);
+                        }
                         else
                             wx_match(o, moff, ml, lane);
                         k0++;
@@ -1833,12 +1923,24 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                     }
                     const bool     in = lane >= k0 && lane < k1;
 
-                    if (skipped > confirmed && __any_sync(CRYO_FULL, in && my_mpos - my_off < guard))
-                    {
-                        need_confirm = true;
-                        continue;
-                    }
                     const uint32_t end = __shfl_sync(CRYO_FULL, my_epos, (int) (k1 - 1u));
+                    const uint32_t floor0 = end + 64u > WX_RING ? end + 64u - WX_RING : 0u;
+                    const uint32_t floor = floor0 > o.lo ? floor0 : o.lo;
+
+                    /* stage 0's bytes are needed by a source that is below what it may not have written yet (guard), older
+                     * than the ring (floor) and not inside the range whose content is known (those bytes are not read) */
+                    {
+                        const uint32_t s0 = my_mpos - my_off, sl = my_ml < my_off ? my_ml : my_off;
+                        /* (the bytes of a source that lie in the known range are not read: what counts is where the rest begins) */
+                        const uint32_t u0 = s0 >= rle_lo && s0 < rle_hi ? rle_hi : s0;
+
+                        if (skipped > confirmed &&
+                            __any_sync(CRYO_FULL, in && u0 < s0 + sl && u0 < guard && s0 + sl > hull_lo && u0 < floor))
+                        {
+                            need_confirm = true;
+                            continue;
+                        }
+                    }
                     const uint32_t litend = __shfl_sync(CRYO_FULL, my_lit + my_ll, (int) (k1 - 1u));
 
                     /* literals of the run -> window (coalesced), then every lane places its own */
@@ -1860,8 +1962,6 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                      * INSIDE the step is another lane's byte -- those are resolved by pointer jumping
                      * over the lanes (a chain of overlapping copies of any length takes five rounds).
                      */
-                    const uint32_t floor0 = end + 64u > WX_RING ? end + 64u - WX_RING : 0u;
-                    const uint32_t floor = floor0 > o.lo ? floor0 : o.lo;
                     const uint32_t span = end - pos0;
                     const uint32_t e_rel = my_epos - pos0;
                     /* match start | (window index of the first literal - start, biased) of this lane's sequence */
@@ -1886,7 +1986,8 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
 
                         seqbase += __popc(marks);
                         if (live && !inside)
-                            v = (far && !lit && x < floor) ? o.out[x] : o.ring[at];
+                            v = (far && !lit && x < floor) ? (x - rle_lo < rle_hi - rle_lo ? (uint32_t) rle_byte : (uint32_t) o.out[x])
+                                                           : (uint32_t) o.ring[at];
                         uint32_t pend = __ballot_sync(CRYO_FULL, inside);
 
                         if (pend)
@@ -1950,8 +2051,18 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
         {
             a.out_size[f] = o.pos;
             a.status[f] = ST_OK;
+            if (a.pf_expect)
+                a.pf_expect[f] = skipped;       /* what stage 0 has to have published when both kernels are done */
         }
         else
             a.flag[f] = 1;                      /* the warp-per-frame decoder rules on it */
     }
+}
+
+/* after stage 0 and stage 4: a frame whose blocks / runs stage 0 did not all publish (it gave up waiting for a job that came
+ * late) goes to the warp-per-frame decoder like any other frame the pipeline declined */
+CRYO_DEV void zp_stage5_check(const ZpArgs &a, uint32_t f)
+{
+    if (f < a.n && a.pf_expect && a.flag[f] == 0 && a.pf_expect[f] != 0 && a.pf_done[f] < a.pf_expect[f])
+        a.flag[f] = 1;
 }

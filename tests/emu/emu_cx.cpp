@@ -89,6 +89,10 @@ emu_zstdc_decode(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t cap,
     a.cxcount = &cxcount;
     a.cxlist = cxlist.data();
     a.pf_done = pf_done.data();
+    a.pf_inflight = 2;
+    a.jobs = nullptr;
+    a.pf_expect = nullptr;
+    a.exec_warps = 0;
     a.early_frames = 0;
     a.pf_hint = 4u;                     /* every frame to the CTA-per-frame stage 4 */
     a.lit = (uint8_t *) ((((uintptr_t) lit.data() + 15) & ~(uintptr_t) 15));

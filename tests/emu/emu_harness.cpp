@@ -227,7 +227,8 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     std::vector<uint8_t>  lit((size_t) n * lit_stride + 64, 0x99);
     std::vector<uint16_t> huftab((size_t) n * ZP_MAXB * 2048, 0x3333);
     std::vector<uint32_t> fsetab((size_t) n * ZP_MAXB * ZP3_CELLS, 0x44444444);
-    unsigned long long    seq_alloc = 0;
+    unsigned long long    ctl[8] = {0, 0, 0, 0, 0, 0, 0, 0};    /* seq_alloc and the control words behind it */
+    std::vector<uint32_t> jobs((size_t) n * ZP_JOBS * 4, 0), pf_expect(n, 0xCDCDCDCD);
     uint32_t              cxcount = 0;
     std::vector<uint32_t> pf_done(n, 0xCDCDCDCD);
     ZpArgs a;
@@ -246,13 +247,17 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     a.blk = blk.data();
     a.flag = flag.data();
     a.seqbase = seqbase.data();
-    a.seq_alloc = &seq_alloc;
+    a.seq_alloc = ctl;
+    a.jobs = getenv("ZP_EMU_NO_JOBS") ? nullptr : jobs.data();
+    a.pf_expect = a.jobs ? pf_expect.data() : nullptr;
+    a.exec_warps = (((unsigned) n + ZP4_WARPS - 1) / ZP4_WARPS) * ZP4_WARPS;
     a.cxcount = &cxcount;
     a.cxlist = cxlist.data();
     a.pf_done = pf_done.data();
     /* every frame to the warp stage 4 (the CTA stage: emu_cx.cpp); bit 4: the early pass of stage 0 runs (ZP_EMU_NO_EARLY: not) */
     const bool early_pass = getenv("ZP_EMU_NO_EARLY") == nullptr;
     a.pf_hint = 8u;
+    a.pf_inflight = 2;
     a.early_frames = early_pass ? ((uint32_t) n + 1u) / 2u : 0u;     /* the last half of the batch */
     a.lit = (uint8_t *) ((((uintptr_t) lit.data() + 15) & ~(uintptr_t) 15));
     a.lit_stride = lit_stride;
@@ -356,6 +361,30 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         zp_stage4(a, blockIdx.x * ZP4_WARPS + warp, CRYO_SMEM_BASE() + warp * ZP4_PER_WARP, lane);
     });
+    /* the runs stage 4 handed over: served here AFTER it (so a frame whose matches read such a run has waited in vain
+     * and written it itself), then the check of what stage 0 published */
+    if (a.jobs)
+    {
+        const uint32_t njobs = reinterpret_cast<uint32_t *>(ctl)[ZPC_JOB_TAIL];
+
+        emu::launch(dim3(1), dim3(128), 0, [&]() {
+            for (uint32_t k = 0; k < njobs; k++)
+            {
+                const uint32_t *job = jobs.data() + 4 * (size_t) k;
+
+                if (!(job[3] & ZP_JOB_READY))
+                    abort();
+                team_fill_byte(a.dst + (size_t) job[0] * a.dst_stride + job[1], (uint8_t) job[3], job[2], threadIdx.x, 128);
+                __syncthreads();
+                if (threadIdx.x == 0 && !getenv("ZP_EMU_DROP_JOBS"))
+                    zp_stage0_done(a, job[0] << 8, 1);
+            }
+        });
+    }
+    if (late_prefill)
+        prefill();
+    if (a.jobs)
+        emu::launch(dim3(((unsigned) n + 255) / 256), dim3(256), 0, [&]() { zp_stage5_check(a, blockIdx.x * 256 + threadIdx.x); });
     if (getenv("ZP_DEBUG"))
         for (int i = 0; i < n; i++)
             for (uint32_t j = 0; j < fr[(size_t) i * ZP_FF]; j++)
@@ -366,8 +395,6 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
                             (b[ZPB_KIND] >> 2) & 3, b[ZPB_REGEN], b[ZPB_HINFO] & 0xFF, b[ZPB_NSEQ], b[ZPB_SLOGS] & 0xFF,
                             (b[ZPB_SLOGS] >> 8) & 0xFF, (b[ZPB_SLOGS] >> 16) & 0x7F);
             }
-    if (late_prefill)
-        prefill();
     for (int i = 0; i < n; i++)
     {
         flags[i] = flag[i];

@@ -263,3 +263,25 @@ def test_emulated_pipeline_decodes_own_encoder_frames(oracle_ref, late_prefill, 
     for i, blk in enumerate(blocks):
         assert st[i] == 0 and osz[i] == MiB and np.array_equal(outs[i], blk), i
         assert fl[i] == 0, i
+
+
+@pytest.mark.parametrize("mode", ["jobs", "dropped", "off"])
+def test_emulated_pipeline_long_runs_handed_to_stage0(oracle_ref, mode, monkeypatch):
+    """The ~120 KB zero runs of a sparse frame are jobs stage 4 queues for stage 0 (ZP_JOBS).  'dropped': stage 0
+    writes them but never publishes them, as if it had given up waiting -- the check after both kernels must send
+    those frames to the warp-per-frame decoder; 'off': stage 4 writes its runs itself.  Right bytes every time."""
+    if mode == "dropped":
+        monkeypatch.setenv("ZP_EMU_DROP_JOBS", "1")
+    if mode == "off":
+        monkeypatch.setenv("ZP_EMU_NO_JOBS", "1")
+    L = _pipeline_lib()
+    blocks = [bg.make_block("S", "hex", 41), bg.make_block("S", "lowcard", 42), bg.make_block("M", "hex", 43),
+              bg.make_block("S", "hex", 44)]
+    comp = [oracle_ref.compress(1, 1, b)[0][0] for b in blocks]
+    st, osz, outs, fl = _run_pipeline(L, comp, shift=7)
+    for i in range(len(comp)):
+        assert st[i] == 0 and osz[i] == MiB and np.array_equal(outs[i], blocks[i]), (mode, i)
+    if mode == "dropped":
+        assert fl[0] != 0 and fl[3] != 0, fl      # the sparse hex frames have two such runs each
+    else:
+        assert fl == [0, 0, 0, 0], fl

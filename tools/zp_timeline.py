@@ -5,7 +5,7 @@ os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-so = os.path.join(ROOT, "tools", "_prof", "libcryogpu_tl.so")      # prebuilt in the build container, or built here
+so = os.environ.get("TL_LIB") or os.path.join(ROOT, "tools", "_prof", "libcryogpu_tl.so")      # prebuilt in the build container, or built here
 os.makedirs(os.path.dirname(so), exist_ok=True)
 if not os.path.exists(so):
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-DZP_TIMELINE",
