@@ -904,6 +904,7 @@ def main():
                              % (nblk * CRYO_BLCKSZ / 1e9),
                        "parallelism": f"block-range shards x{world}, no collective",
                        "gate": "status, size and a 128-bit digest of every decoded block, before and after the timed steps"},
+            "ms_per_step_min_median_max": [min(step_ms), statistics.median(step_ms), max(step_ms)],
             "clocks": clocks, "e2e": e2e, "gpu_launches": LAUNCHES_PER_STEP * args.steps, "roofline": roofline,
             "cpu_baseline": cpu, "secondary": secondary, "next_rows": next_rows,
         }

@@ -263,7 +263,7 @@ struct Zp0
     int       cur;              /* that byte, -1: none yet */
     uint32_t  window;           /* groups in flight */
     uint32_t  issued, published;        /* units committed / published (thread 0) */
-    uint32_t  ticket;           /* number of the job this CTA is waiting for, ~0u: none taken (thread 0) */
+    uint32_t  ticket;           /* number of the job this lane of warp 0 is waiting for, ~0u: none taken */
     uint32_t  ring[8];          /* frames of the units not yet published (thread 0) */
 };
 
@@ -338,53 +338,72 @@ zp0_unit_done(const ZpArgs &a, Zp0 &z, uint32_t f, bool publish, bool drain)
 }
 
 /*
- * One job of stage 4's, if the CTA's ticket has come up.  Jobs are numbered as they are queued; a CTA holds one ticket
- * (a fetch-and-add on the head: no two CTAs ever contend for a job -- claiming with compare-and-swap, 148 CTAs
- * took 3.3 ms over the step's 6 898 jobs) and looks at its number's slot whenever it passes here.  Returns 1: served
- * one; 0: not there yet; 2: never will be (stage 4 has finished and queued fewer).
+ * Jobs of stage 4's, if the CTA's tickets have come up.  Jobs are numbered as they are queued; a ticket is a fetch-and-add
+ * on the head (no two CTAs ever contend for a job -- claiming with compare-and-swap, 148 CTAs took 3.3 ms over the
+ * step's 6 898 jobs).  A CTA holds ZP0_TAKE tickets, one per lane of warp 0, and looks at their slots side by side
+ * whenever it passes here: a job is 120 KB, 2.6 us of the engine's time, and ticket + flag + fields are three dependent
+ * round trips of 1-2 us each -- taken one job at a time they left the engine idle half the time.
+ * Returns the number served; ~0u: none ever will be (stage 4 has finished and queued fewer).
  */
+#define ZP0_TAKE 4u
+
 __device__ __forceinline__ uint32_t
-zp0_serve_job(const ZpArgs &a, Zp0 &z, uint32_t *s_job)
+zp0_serve_jobs(const ZpArgs &a, Zp0 &z, uint32_t (*s_job)[4], uint32_t *s_over)
 {
     uint32_t *ctl = reinterpret_cast<uint32_t *>(a.seq_alloc);
 
     __syncthreads();
-    if (threadIdx.x == 0)
+    if (threadIdx.x < 32u)
     {
-        uint32_t w3 = 0, over = 0;
+        bool over = true;
 
-        if (z.ticket == ~0u)
-            z.ticket = atomicAdd(ctl + ZPC_JOB_HEAD, 1u);
-        if (z.ticket < a.n * ZP_JOBS)
-            w3 = zp_ld_acquire(a.jobs + 4u * (size_t) z.ticket + 3);
-        if (!(w3 & ZP_JOB_READY) && zp_ld_acquire(ctl + ZPC_EXEC_DONE) >= a.exec_warps)
+        if (threadIdx.x < ZP0_TAKE)
         {
-            /* no more jobs will be queued: either ours is among them (its fields follow the slot's allocation at once) or not */
-            if (z.ticket < zp_ld_acquire(ctl + ZPC_JOB_TAIL))
-                for (uint32_t spin = 0; spin < 200000u && !(w3 & ZP_JOB_READY); spin++)
-                    w3 = zp_ld_acquire(a.jobs + 4u * (size_t) z.ticket + 3);
-            else
-                over = 1;
-        }
-        if (w3 & ZP_JOB_READY)
-        {
-            const uint32_t *job = a.jobs + 4u * (size_t) z.ticket;
+            uint32_t w3 = 0;
 
-            s_job[0] = job[0];
-            s_job[1] = job[1];
-            s_job[2] = job[2];
-            z.ticket = ~0u;
+            over = false;
+            if (z.ticket == ~0u)
+                z.ticket = atomicAdd(ctl + ZPC_JOB_HEAD, 1u);
+            if (z.ticket < a.n * ZP_JOBS)
+                w3 = zp_ld_acquire(a.jobs + 4u * (size_t) z.ticket + 3);
+            if (!(w3 & ZP_JOB_READY) && zp_ld_acquire(ctl + ZPC_EXEC_DONE) >= a.exec_warps)
+            {
+                /* no more jobs will be queued: either ours is among them (its fields follow the slot's allocation at once) or not */
+                if (z.ticket < zp_ld_acquire(ctl + ZPC_JOB_TAIL))
+                    for (uint32_t spin = 0; spin < 200000u && !(w3 & ZP_JOB_READY); spin++)
+                        w3 = zp_ld_acquire(a.jobs + 4u * (size_t) z.ticket + 3);
+                else
+                    over = true;
+            }
+            if (w3 & ZP_JOB_READY)
+            {
+                const uint32_t *job = a.jobs + 4u * (size_t) z.ticket;
+
+                s_job[threadIdx.x][0] = job[0];
+                s_job[threadIdx.x][1] = job[1];
+                s_job[threadIdx.x][2] = job[2];
+                z.ticket = ~0u;
+            }
+            s_job[threadIdx.x][3] = w3;
         }
-        s_job[3] = w3 | (over << 31);
+        over = __all_sync(CRYO_FULL, over);
+        if (threadIdx.x == 0)
+            *s_over = over ? 1u : 0u;
     }
     __syncthreads();
-    if (!(s_job[3] & ZP_JOB_READY))
-        return (s_job[3] >> 31) ? 2u : 0u;
-    const uint32_t f = s_job[0];
+    uint32_t served = 0;
 
-    zp0_unit_fill(a, z, a.dst + (size_t) f * a.dst_stride + s_job[1], s_job[2], (int) (s_job[3] & 0xFFu));
-    zp0_unit_done(a, z, f, true, false);
-    return 1u;
+    for (uint32_t t = 0; t < ZP0_TAKE; t++)
+    {
+        if (!(s_job[t][3] & ZP_JOB_READY))
+            continue;
+        const uint32_t f = s_job[t][0];
+
+        zp0_unit_fill(a, z, a.dst + (size_t) f * a.dst_stride + s_job[t][1], s_job[t][2], (int) (s_job[t][3] & 0xFFu));
+        zp0_unit_done(a, z, f, true, false);
+        served++;
+    }
+    return served ? served : (*s_over ? ~0u : 0u);
 }
 
 template <bool EARLY>
@@ -392,7 +411,7 @@ __device__ __forceinline__ void zp_prefill_body(const ZpArgs &a)
 {
     __shared__ __align__(128) uint8_t pat[ZP0_CHUNK];
     __shared__ uint32_t spec[ZP_MAXB], s_len[ZP_MAXB], s_what[ZP_MAXB], s_off[ZP_MAXB];
-    __shared__ uint32_t next_f, s_job[4];
+    __shared__ uint32_t next_f, s_job[ZP0_TAKE][4], s_over;
     uint32_t *counter = reinterpret_cast<uint32_t *>(a.seq_alloc) + (EARLY ? 5 : 4);    /* zeroed with seq_alloc */
     Zp0       z;
 
@@ -458,19 +477,23 @@ __device__ __forceinline__ void zp_prefill_body(const ZpArgs &a)
         /* (CRYOGPU_ZP_JOBS=2, pf_hint bit 5: a run stage 4 has handed over meanwhile after every frame, so that they do not
          * pile up behind the frames.  Measured no better, and less even from run to run: off) */
         if (!EARLY && a.jobs && (a.pf_hint & 32u))
-            zp0_serve_job(a, z, s_job);
+            zp0_serve_jobs(a, z, s_job, &s_over);
     }
     if (!EARLY && a.jobs)
     {
         /* the frames are done: serve stage 4's runs until its warps have all finished and the queue is empty.  The wait is
          * bounded (about 50 ms); a run nobody served is noticed afterwards (zp_stage5_check) */
-        for (uint32_t idle = 0; idle < 200000u;)
+        /* (the bound: ~20 ms without a job.  Under a tool that runs kernels one after the other -- ncu, the sanitizer --
+         * stage 4 has not even started: this stage then waits the bound out and the check sends the frames to the fallback) */
+        if (z.window < ZP0_TAKE)
+            z.window = ZP0_TAKE;        /* a round's jobs in flight together */
+        for (uint32_t idle = 0; idle < 20000u;)
         {
-            const uint32_t r = zp0_serve_job(a, z, s_job);
+            const uint32_t r = zp0_serve_jobs(a, z, s_job, &s_over);
 
-            if (r == 2u)
+            if (r == ~0u)
                 break;
-            if (r == 1u)
+            if (r)
             {
                 idle = 0;
                 continue;
@@ -980,6 +1003,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
 
                 hint = (e ? atoi(e) != 0 : ZP_L2HINT_DEFAULT) | ((x ? atoi(x) != 0 : ZP_EXEC_PREFETCH_DEFAULT) << 1) |
                        ((s ? atoi(s) != 0 : 1) << 4);
+
             }
             a.pf_hint = (uint32_t) hint;
         }
