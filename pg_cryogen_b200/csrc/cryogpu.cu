@@ -420,6 +420,8 @@ __device__ __forceinline__ void zp_prefill_body(const ZpArgs &a)
     z.window = a.pf_inflight > 8u ? 8u : a.pf_inflight < 1u ? 1u : a.pf_inflight;
     z.issued = z.published = 0;
     z.ticket = ~0u;
+    if (!EARLY && a.jobs && threadIdx.x == 0)
+        atomicAdd(reinterpret_cast<uint32_t *>(a.seq_alloc) + ZPC_SERVERS, 1u);     /* stage 4 may queue jobs: somebody will take them */
     /*
      * Frames are handed out by a counter, not by blockIdx: the CTAs of this kernel do not all become resident at
      * once beside the executor's (in some states of the process a third of them start a millisecond late, and
@@ -485,9 +487,26 @@ __device__ __forceinline__ void zp_prefill_body(const ZpArgs &a)
          * bounded (about 50 ms); a run nobody served is noticed afterwards (zp_stage5_check) */
         /* (the bound: ~20 ms without a job.  Under a tool that runs kernels one after the other -- ncu, the sanitizer --
          * stage 4 has not even started: this stage then waits the bound out and the check sends the frames to the fallback) */
+        uint32_t *ctl = reinterpret_cast<uint32_t *>(a.seq_alloc);
+        __shared__ uint32_t s_up;
+
         if (z.window < ZP0_TAKE)
             z.window = ZP0_TAKE;        /* a round's jobs in flight together */
-        for (uint32_t idle = 0; idle < 20000u;)
+        /* stage 4 runs beside this kernel, or (under a profiler, a sanitizer) only after it: then nothing is to come */
+        if (threadIdx.x == 0)
+        {
+            uint32_t up = 0;
+
+            for (uint32_t spin = 0; spin < 400u && !up; spin++)
+            {
+                up = zp_ld_acquire(ctl + ZPC_EXEC_UP);
+                if (!up)
+                    __nanosleep(256);
+            }
+            s_up = up;
+        }
+        __syncthreads();
+        for (uint32_t idle = s_up ? 0u : 20000u; idle < 20000u;)
         {
             const uint32_t r = zp0_serve_jobs(a, z, s_job, &s_over);
 
@@ -503,6 +522,8 @@ __device__ __forceinline__ void zp_prefill_body(const ZpArgs &a)
         }
     }
     zp0_unit_done(a, z, 0, !EARLY, true);
+    if (!EARLY && a.jobs && threadIdx.x == 0)
+        atomicSub(reinterpret_cast<uint32_t *>(a.seq_alloc) + ZPC_SERVERS, 1u);
 }
 
 __global__ void __launch_bounds__(ZP0_THREADS)
@@ -587,6 +608,8 @@ k_zp_execute(const ZpArgs a)
     ZP_TL_BEGIN(7)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    if (a.jobs && threadIdx.x == 0)
+        zp_st_release(reinterpret_cast<uint32_t *>(a.seq_alloc) + ZPC_EXEC_UP, 1u);
     zp_stage4(a, blockIdx.x * ZP4_WARPS + warp, CRYO_SMEM_BASE() + warp * ZP4_PER_WARP, lane);
     /* stage 0 serves the runs this kernel hands over until every warp of it has said it is done */
     if (a.jobs && lane == 0)

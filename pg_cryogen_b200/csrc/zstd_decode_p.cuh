@@ -49,7 +49,11 @@
 #define ZP_JOB_READY   0x100u
 #define ZPC_JOB_TAIL   8u       /* u32 indices into the control words at seq_alloc: jobs queued, */
 #define ZPC_JOB_HEAD   9u       /* tickets taken, */
-#define ZPC_EXEC_DONE  10u      /* warps of k_zp_execute that have finished */
+#define ZPC_EXEC_DONE  10u      /* warps of k_zp_execute that have finished, */
+#define ZPC_EXEC_UP    11u      /* non-zero once k_zp_execute has started, */
+#define ZPC_SERVERS    12u      /* CTAs of stage 0's late pass that are running: stage 4 queues a job only while there are some
+                                 * (under a tool that runs the kernels one after the other there are none: it then writes its
+                                 * runs itself, as in round 1, and stage 0 does not wait for jobs that cannot come) */
 #define ZPB_RLEBYTE ZPB_LHDR     /* RLE blocks: the byte of the run (stage 4 then need not read the frame for it) */
 #define ZPF_HUFMASK 4u
 #define ZPF_SEQMASK 5u
@@ -1869,7 +1873,8 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                         zsw_lits_emit(o, L, ll, lane);
                         if (known)
                             wx_fill_byte(o, rle_byte, ml, lane);        /* a copy of known bytes: no read */
-                        else if (a.jobs && moff == 1u && ml >= ZP_JOB_MIN && njobs < ZP_JOBS && o.pos > o.lo)
+                        else if (a.jobs && moff == 1u && ml >= ZP_JOB_MIN && njobs < ZP_JOBS && o.pos > o.lo &&
+                                 zp_ld_acquire(reinterpret_cast<const uint32_t *>(a.seq_alloc) + ZPC_SERVERS) != 0)
                         {
                             /* a long run of the previous byte: stage 0's job (see ZP_JOBS) */
                             const uint8_t  rb = o.ring[(o.pos - 1u) & WX_RMASK];

@@ -357,6 +357,7 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
     });
     if (!late_prefill)
         prefill();
+    reinterpret_cast<uint32_t *>(ctl)[ZPC_SERVERS] = getenv("ZP_EMU_NO_SERVER") ? 0u : 1u;     /* stage 0's late pass is "running" */
     emu::launch(dim3(((unsigned) n + ZP4_WARPS - 1) / ZP4_WARPS), dim3(ZP4_THREADS), ZP4_SMEM, [&]() {
         const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         zp_stage4(a, blockIdx.x * ZP4_WARPS + warp, CRYO_SMEM_BASE() + warp * ZP4_PER_WARP, lane);

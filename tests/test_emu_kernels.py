@@ -265,15 +265,18 @@ def test_emulated_pipeline_decodes_own_encoder_frames(oracle_ref, late_prefill, 
         assert fl[i] == 0, i
 
 
-@pytest.mark.parametrize("mode", ["jobs", "dropped", "off"])
+@pytest.mark.parametrize("mode", ["jobs", "dropped", "off", "no_server"])
 def test_emulated_pipeline_long_runs_handed_to_stage0(oracle_ref, mode, monkeypatch):
     """The ~120 KB zero runs of a sparse frame are jobs stage 4 queues for stage 0 (ZP_JOBS).  'dropped': stage 0
     writes them but never publishes them, as if it had given up waiting -- the check after both kernels must send
-    those frames to the warp-per-frame decoder; 'off': stage 4 writes its runs itself.  Right bytes every time."""
+    those frames to the warp-per-frame decoder; 'off': stage 4 writes its runs itself; 'no_server': so it does when no CTA
+    of stage 0's late pass is running (kernels one after the other, as under a profiler).  Right bytes every time."""
     if mode == "dropped":
         monkeypatch.setenv("ZP_EMU_DROP_JOBS", "1")
     if mode == "off":
         monkeypatch.setenv("ZP_EMU_NO_JOBS", "1")
+    if mode == "no_server":
+        monkeypatch.setenv("ZP_EMU_NO_SERVER", "1")
     L = _pipeline_lib()
     blocks = [bg.make_block("S", "hex", 41), bg.make_block("S", "lowcard", 42), bg.make_block("M", "hex", 43),
               bg.make_block("S", "hex", 44)]
