@@ -5,6 +5,8 @@ the reference's compressor can emit (levels -5..22, compression.c:53) for all bl
 kinds and payloads, plus hand-crafted conformance frames for format branches libzstd
 never emits and malformed inputs.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -299,3 +301,19 @@ def test_host_api_zero_runs_returned_to_the_kernel(gpu, oracle_ref):
         out, osz, st = gpu.decompress_host(methods, comp, out=out)
         assert (st == 0).all() and np.array_equal(out, blocks), on
     gpu.lib.cryogpu_set_zero_by_unmap(gpu.handle, 0)
+
+
+@pytest.mark.parametrize("knobs", [{}, {"CRYOGPU_ZP_JOBS": "0", "CRYOGPU_ZP_EARLY_CTAS": "0"},
+                                   {"CRYOGPU_ZP_JOBS": "0"}, {"CRYOGPU_ZP_EARLY_CTAS": "0"},
+                                   {"CRYOGPU_ZP_JOBS": "2", "CRYOGPU_ZP_EARLY_PCT": "100", "CRYOGPU_ZP_PF_INFLIGHT": "1"}])
+def test_zstd_pipeline_jobs_and_early_pass_settings(knobs):
+    """The executor's long runs as jobs of the raw / RLE stage and that stage's early pass at guessed positions, in every
+    combination of their switches (read once per process, hence a fresh one each: tests/zp_knobs_case.py): 400 frames,
+    a quarter of them with every guess wrong, bit-exact and none left to the fallback decoder."""
+    import subprocess
+    import sys
+    env = dict(os.environ)
+    env.update(knobs)
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "zp_knobs_case.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
