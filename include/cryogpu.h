@@ -105,7 +105,9 @@ void        cryogpu_host_free(void *p);
  *                  d_dst and dst_stride must be multiples of 16
  *   d_out_size[i]  bytes produced (the reference only Asserts == CRYO_BLCKSZ,
  *                  compression.c:88, :120)
- *   d_status[i]    CRYOGPU_ST_*
+ *   d_status[i]    CRYOGPU_ST_*; a block whose status is not CRYOGPU_ST_OK leaves its
+ *                  block_size bytes of d_dst unspecified (as ZSTD_decompress / LZ4_decompress_safe
+ *                  do when they fail part-way: the zstd pipeline writes runs ahead of the decode)
  *   stream         a cudaStream_t (NULL = the context's own stream); the call only
  *                  enqueues work, it does not synchronise
  *
