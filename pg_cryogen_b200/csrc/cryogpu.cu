@@ -264,7 +264,7 @@ struct Zp0
     uint32_t  window;           /* groups in flight */
     uint32_t  issued, published;        /* units committed / published (thread 0) */
     uint32_t  ticket;           /* number of the job this lane of warp 0 is waiting for, ~0u: none taken */
-    uint32_t  ring[8];          /* frames of the units not yet published (thread 0) */
+    uint32_t  ring[8];          /* the units not yet published: a block's frame, or 1 << 31 | a job's slot (thread 0) */
 };
 
 /* n bytes of `byte` at dst (every thread of the CTA calls this with the same arguments); the unit belongs to frame f */
@@ -332,8 +332,20 @@ zp0_unit_done(const ZpArgs &a, Zp0 &z, uint32_t f, bool publish, bool drain)
     {
         asm volatile("fence.proxy.async;" ::: "memory");
         for (; z.published < complete; z.published++)
-            if (publish)
-                zp_stage0_done(a, z.ring[z.published & 7u] << 8, 1u);
+        {
+            const uint32_t unit = z.ring[z.published & 7u];
+
+            if (!publish)
+                continue;
+            if (unit & 0x80000000u)
+            {
+                /* a job: done in its own slot (pf_done counts a frame's blocks, in block order) */
+                __threadfence();
+                atomicOr(a.jobs + 4u * (size_t) (unit & 0x7FFFFFFFu) + 3, ZP_JOB_DONE);
+            }
+            else
+                zp_stage0_done(a, unit << 8, 1u);
+        }
     }
 }
 
@@ -348,7 +360,7 @@ zp0_unit_done(const ZpArgs &a, Zp0 &z, uint32_t f, bool publish, bool drain)
 #define ZP0_TAKE 4u
 
 __device__ __forceinline__ uint32_t
-zp0_serve_jobs(const ZpArgs &a, Zp0 &z, uint32_t (*s_job)[4], uint32_t *s_over)
+zp0_serve_jobs(const ZpArgs &a, Zp0 &z, uint32_t (*s_job)[5], uint32_t *s_over)
 {
     uint32_t *ctl = reinterpret_cast<uint32_t *>(a.seq_alloc);
 
@@ -382,6 +394,7 @@ zp0_serve_jobs(const ZpArgs &a, Zp0 &z, uint32_t (*s_job)[4], uint32_t *s_over)
                 s_job[threadIdx.x][0] = job[0];
                 s_job[threadIdx.x][1] = job[1];
                 s_job[threadIdx.x][2] = job[2];
+                s_job[threadIdx.x][4] = z.ticket;
                 z.ticket = ~0u;
             }
             s_job[threadIdx.x][3] = w3;
@@ -400,7 +413,7 @@ zp0_serve_jobs(const ZpArgs &a, Zp0 &z, uint32_t (*s_job)[4], uint32_t *s_over)
         const uint32_t f = s_job[t][0];
 
         zp0_unit_fill(a, z, a.dst + (size_t) f * a.dst_stride + s_job[t][1], s_job[t][2], (int) (s_job[t][3] & 0xFFu));
-        zp0_unit_done(a, z, f, true, false);
+        zp0_unit_done(a, z, 0x80000000u | s_job[t][4], true, false);
         served++;
     }
     return served ? served : (*s_over ? ~0u : 0u);
@@ -411,7 +424,7 @@ __device__ __forceinline__ void zp_prefill_body(const ZpArgs &a)
 {
     __shared__ __align__(128) uint8_t pat[ZP0_CHUNK];
     __shared__ uint32_t spec[ZP_MAXB], s_len[ZP_MAXB], s_what[ZP_MAXB], s_off[ZP_MAXB];
-    __shared__ uint32_t next_f, s_job[ZP0_TAKE][4], s_over;
+    __shared__ uint32_t next_f, s_job[ZP0_TAKE][5], s_over;
     uint32_t *counter = reinterpret_cast<uint32_t *>(a.seq_alloc) + (EARLY ? 5 : 4);    /* zeroed with seq_alloc */
     Zp0       z;
 
@@ -1186,7 +1199,7 @@ launch_zstd_decode(cudaStream_t st, size_t n, const int32_t *methods, const uint
                 k_zp_execute_c<<<(unsigned) std::min<size_t>(n, (size_t) sm_count), CX_THREADS, ZC_SMEM, st>>>(a, cx_counter);
             cudaStreamWaitEvent(st, ev[2], 0);
             if (a.jobs)
-                k_zp_check<<<(unsigned) ((n + 255) / 256), 256, 0, st>>>(a);
+                k_zp_check<<<(unsigned) ((n * ZP_JOBS + 255) / 256), 256, 0, st>>>(a);
         }
         /* frames the pipeline declined (flag set): decoded from scratch, one warp per frame */
         k_zstd_decode_w<<<(unsigned) ((n + ZSW_WARPS - 1) / ZSW_WARPS), ZSW_THREADS, ZSW_SMEM, st>>>(

@@ -42,11 +42,15 @@
  * Long runs handed from stage 4 to stage 0 (round 2): the ~120 KB zero-run matches of a sparse frame, 96 % of the bytes
  * the warp executor wrote, stalled it for a quarter of its time beside the raw / RLE stage (profiles/r02_ablation.txt);
  * stage 0 has the bulk-copy engine.  A job is (frame, position, length, byte | ZP_JOB_READY), queued by stage 4 and
- * taken by stage 0's CTAs once their frames are done; it counts as one more block in pf_done.
+ * taken by stage 0's CTAs once their frames are done.  A job is published in its own slot (ZP_JOB_DONE), not in
+ * pf_done: that counter says how many of a frame's BLOCKS stage 0 has written, in block order, and jobs finish in any
+ * order relative to them (counted together, the later blocks of a frame passed for its jobs: a copy from a run not
+ * yet written read whatever was there -- found by tests/test_emu_kernels.py's blocks with copies around long runs).
  */
 #define ZP_JOBS        2u       /* per frame */
 #define ZP_JOB_MIN     32768u   /* bytes */
-#define ZP_JOB_READY   0x100u
+#define ZP_JOB_READY   0x100u   /* word 3 of a job: the byte | READY once stage 4 has filled the slot in | DONE once stage 0 has written the run */
+#define ZP_JOB_DONE    0x200u
 #define ZPC_JOB_TAIL   8u       /* u32 indices into the control words at seq_alloc: jobs queued, */
 #define ZPC_JOB_HEAD   9u       /* tickets taken, */
 #define ZPC_EXEC_DONE  10u      /* warps of k_zp_execute that have finished, */
@@ -1537,22 +1541,26 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
  * reach back into a skipped block never waits: the zero run that follows the RLE blocks of a
  * sparse cryo block is recognised as a fill of the RLE byte (see rle_lo / rle_hi below).
  */
+/* stage 0 owes this frame something stage 4 has not seen published: blocks (skipped) or jobs (njobs) */
+#define ZP4_OWED() (skipped > confirmed || njobs > jconfirmed)
 #define ZP4_CONFIRM()                                                                        \
-    if (skipped > confirmed)                                                                 \
+    if (ZP4_OWED())                                                                          \
     {                                                                                        \
-        uint32_t seen_ = 0;                                                                  \
+        uint32_t ok_ = 0;                                                                    \
                                                                                              \
         if (lane == 0)                                                                       \
             for (uint32_t spin_ = 0; spin_ < ZP4_SPINS; spin_++)                             \
             {                                                                                \
-                seen_ = zp_ld_acquire(a.pf_done + f);                                        \
-                if (seen_ >= skipped)                                                        \
+                ok_ = zp_ld_acquire(a.pf_done + f) >= skipped;                               \
+                for (uint32_t kk_ = jconfirmed; kk_ < njobs && ok_; kk_++)                   \
+                    ok_ = (zp_ld_acquire(a.jobs + 4u * (size_t) sjobs[4u * kk_ + 3u] + 3) & ZP_JOB_DONE) != 0; \
+                if (ok_)                                                                     \
                     break;                                                                   \
                 __nanosleep(256);                                                            \
             }                                                                                \
-        seen_ = __shfl_sync(CRYO_FULL, seen_, 0);                                            \
+        ok_ = __shfl_sync(CRYO_FULL, ok_, 0);                                                \
         __threadfence();        /* every lane's later reads of stage 0's output after lane 0's acquire */ \
-        if (seen_ < skipped)                                                                 \
+        if (!ok_)                                                                            \
         {                                                                                    \
             uint32_t at_ = 0;                                                                \
                                                                                              \
@@ -1574,6 +1582,7 @@ CRYO_DEV void zp_stage3b(const ZpArgs &a, uint32_t g, uint32_t j, uint8_t *smem,
             __syncwarp();                                                                    \
         }                                                                                    \
         confirmed = skipped;                                                                 \
+        jconfirmed = njobs;                                                                  \
         hull_lo = ~0u;                                                                       \
     }
 
@@ -1607,7 +1616,7 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
      */
     uint32_t *sdesc = reinterpret_cast<uint32_t *>(smem + WX_RING + ZP4_LITWIN);
     uint32_t *sjobs = sdesc + ZP_MAXB * ZP_BF;
-    uint32_t  njobs = 0;                                   /* runs handed to stage 0 */
+    uint32_t  njobs = 0, jconfirmed = 0;                   /* runs handed to stage 0; how many of them it is known to have written */
 
     {
         const uint32_t *gdesc = a.blk + (size_t) f * ZP_MAXB * ZP_BF;
@@ -1660,7 +1669,7 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                 __syncwarp();
                 if (!early)
                 {
-                    if (skipped == confirmed)
+                    if (!ZP4_OWED())
                         hull_lo = o.pos - bsize;
                     skipped++;
                     skipmask |= 1u << j;
@@ -1863,7 +1872,7 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                         const uint32_t head_known = (!known && moff >= ml && sp1 >= rle_lo && sp1 < rle_hi) ? rle_hi - sp1 : 0u;
 
                         /* (a source the ring still holds is read from there whether or not stage 0 has written it) */
-                        if (!known && sp1 + head_known < guard && sp1 + need > hull_lo && skipped > confirmed &&
+                        if (!known && sp1 + head_known < guard && sp1 + need > hull_lo && ZP4_OWED() &&
                             !(ll < WX_BULK && ml < WX_BULK && moff <= WX_RING - 64u && sp1 >= o.lo))
                         {
                             need_confirm = true;
@@ -1884,8 +1893,10 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                             if (lane == 0)
                             {
                                 uint32_t *ctl = reinterpret_cast<uint32_t *>(a.seq_alloc);
-                                uint32_t *job = a.jobs + 4u * (size_t) atomicAdd(ctl + ZPC_JOB_TAIL, 1u);
+                                const uint32_t slot = atomicAdd(ctl + ZPC_JOB_TAIL, 1u);
+                                uint32_t *job = a.jobs + 4u * (size_t) slot;
 
+                                sjobs[4u * njobs + 3u] = slot;
                                 job[0] = f;
                                 job[1] = at;
                                 job[2] = ml;
@@ -1902,10 +1913,9 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                                                    __all_sync(CRYO_FULL, lane >= gap || o.ring[(rle_hi + lane) & WX_RMASK] == rb);
 
                             wx_after_fill(o, ml, rb, lane);
-                            if (skipped == confirmed)
+                            if (!ZP4_OWED())
                                 hull_lo = at;
                             njobs++;
-                            skipped++;
                             guard = o.pos;
                             if (joins)
                                 rle_hi = o.pos;
@@ -1939,7 +1949,7 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
                         /* (the bytes of a source that lie in the known range are not read: what counts is where the rest begins) */
                         const uint32_t u0 = s0 >= rle_lo && s0 < rle_hi ? rle_hi : s0;
 
-                        if (skipped > confirmed &&
+                        if (ZP4_OWED() &&
                             __any_sync(CRYO_FULL, in && u0 < s0 + sl && u0 < guard && s0 + sl > hull_lo && u0 < floor))
                         {
                             need_confirm = true;
@@ -2064,10 +2074,20 @@ CRYO_DEV void zp_stage4(const ZpArgs &a, uint32_t f, uint8_t *smem, uint32_t lan
     }
 }
 
-/* after stage 0 and stage 4: a frame whose blocks / runs stage 0 did not all publish (it gave up waiting for a job that came
+/* after stage 0 and stage 4 (one thread per job slot, n x ZP_JOBS): a frame whose blocks / runs stage 0 did not all publish (it gave up waiting for a job that came
  * late) goes to the warp-per-frame decoder like any other frame the pipeline declined */
-CRYO_DEV void zp_stage5_check(const ZpArgs &a, uint32_t f)
+CRYO_DEV void zp_stage5_check(const ZpArgs &a, uint32_t t)
 {
-    if (f < a.n && a.pf_expect && a.flag[f] == 0 && a.pf_expect[f] != 0 && a.pf_done[f] < a.pf_expect[f])
-        a.flag[f] = 1;
+    if (!a.pf_expect)
+        return;
+    /* thread t: frame t's blocks, and job slot t */
+    if (t < a.n && a.flag[t] == 0 && a.pf_expect[t] != 0 && a.pf_done[t] < a.pf_expect[t])
+        a.flag[t] = 1;
+    if (t < a.n * ZP_JOBS && t < reinterpret_cast<const uint32_t *>(a.seq_alloc)[ZPC_JOB_TAIL])
+    {
+        const uint32_t *job = a.jobs + 4u * (size_t) t;
+
+        if (!(job[3] & ZP_JOB_DONE))
+            a.flag[job[0]] = 1;
+    }
 }

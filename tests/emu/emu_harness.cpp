@@ -378,14 +378,14 @@ emu_zstdp_decode_multi(int n, const uint8_t *const *srcs, const uint32_t *csizes
                 team_fill_byte(a.dst + (size_t) job[0] * a.dst_stride + job[1], (uint8_t) job[3], job[2], threadIdx.x, 128);
                 __syncthreads();
                 if (threadIdx.x == 0 && !getenv("ZP_EMU_DROP_JOBS"))
-                    zp_stage0_done(a, job[0] << 8, 1);
+                    jobs[4 * (size_t) k + 3] |= ZP_JOB_DONE;
             }
         });
     }
     if (late_prefill)
         prefill();
     if (a.jobs)
-        emu::launch(dim3(((unsigned) n + 255) / 256), dim3(256), 0, [&]() { zp_stage5_check(a, blockIdx.x * 256 + threadIdx.x); });
+        emu::launch(dim3(((unsigned) n * ZP_JOBS + 255) / 256), dim3(256), 0, [&]() { zp_stage5_check(a, blockIdx.x * 256 + threadIdx.x); });
     if (getenv("ZP_DEBUG"))
         for (int i = 0; i < n; i++)
             for (uint32_t j = 0; j < fr[(size_t) i * ZP_FF]; j++)

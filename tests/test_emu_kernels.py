@@ -288,3 +288,47 @@ def test_emulated_pipeline_long_runs_handed_to_stage0(oracle_ref, mode, monkeypa
         assert fl[0] != 0 and fl[3] != 0, fl      # the sparse hex frames have two such runs each
     else:
         assert fl == [0, 0, 0, 0], fl
+
+
+@pytest.mark.parametrize("late_prefill", [False, True])
+def test_emulated_pipeline_matches_around_long_runs(oracle_port, late_prefill, monkeypatch):
+    """Blocks built to stress what stage 4 does around the runs it hands to stage 0: long runs of one byte (jobs), of
+    several different bytes (the known range holds only the last), data after a run that copies from before it (below
+    what stage 0 owes), from inside it, from across its end (a copy that starts in the run and runs out of it), and from
+    far behind the ring; raw and RLE blocks in between.  Stage 0's late pass after stage 4 as well, so every wait for it
+    times out and stage 4 writes the runs itself."""
+    import benchdata
+    if late_prefill:
+        monkeypatch.setenv("ZP_EMU_LATE_PREFILL", "1")
+    L = _pipeline_lib()
+    _, zstd = benchdata._libs()
+    rng = np.random.default_rng(20260202)
+    plain, comp = [], []
+    for k in range(12):
+        head = rng.integers(0, 256, size=int(rng.integers(300, 3000)), dtype=np.uint8)
+        text = rng.integers(97, 103, size=int(rng.integers(2000, 30000)), dtype=np.uint8)
+        parts = [head, np.zeros(int(rng.integers(40_000, 300_000)), dtype=np.uint8)]
+        parts.append(head[: head.size // 2])                                   # copies from before the first run
+        parts.append(np.full(int(rng.integers(33_000, 90_000)), 7 if k % 3 == 0 else 0, dtype=np.uint8))
+        parts.append(np.concatenate([np.zeros(40, dtype=np.uint8), text[:200]]))
+        parts.append(text)
+        parts.append(np.concatenate([np.zeros(24, dtype=np.uint8), text[:64]]))  # across the end of a run, far behind
+        if k % 2:
+            parts.append(rng.integers(0, 256, size=140_000, dtype=np.uint8))    # a Raw block for stage 0
+        parts.append(np.zeros(int(rng.integers(1000, 70_000)), dtype=np.uint8))
+        parts.append(text[::-1].copy())
+        buf = np.concatenate(parts)
+        if buf.size < MiB:
+            buf = np.concatenate([buf, np.zeros(MiB - buf.size, dtype=np.uint8)])
+        buf = buf[:MiB].copy()
+        scratch = np.zeros(MiB + MiB // 128 + 4096, dtype=np.uint8)
+        got = zstd.ZSTD_compress(scratch.ctypes.data, scratch.size, buf.ctypes.data, buf.size, [1, 3, -1, 2][k % 4])
+        assert 0 < got <= scratch.size
+        plain.append(buf)
+        comp.append(scratch[:got].copy())
+    st, osz, outs, fl = _run_pipeline(L, comp, shift=9)
+    for k in range(len(comp)):
+        want_n, want = oracle_port.zstd_decode(comp[k], cap=MiB)[:2]
+        assert want_n == MiB and np.array_equal(want, plain[k]), "oracle disagrees with libzstd"
+        assert st[k] == 0 and osz[k] == MiB, (k, st[k], osz[k])
+        assert np.array_equal(outs[k], plain[k]), (k, int(np.argmax(outs[k] != plain[k])))
