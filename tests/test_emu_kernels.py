@@ -332,3 +332,49 @@ def test_emulated_pipeline_matches_around_long_runs(oracle_port, late_prefill, m
         assert want_n == MiB and np.array_equal(want, plain[k]), "oracle disagrees with libzstd"
         assert st[k] == 0 and osz[k] == MiB, (k, st[k], osz[k])
         assert np.array_equal(outs[k], plain[k]), (k, int(np.argmax(outs[k] != plain[k])))
+
+
+@pytest.mark.parametrize("nframes,cap,seed", [(10, MiB, 1), (11, 384 * 1024, 2), (7, MiB, 3), (13, 200 * 1024, 4)])
+def test_emulated_pipeline_random_run_layouts(oracle_port, nframes, cap, seed):
+    """Random layouts of long one-byte runs (more of them than a frame may hand to stage 0, of several bytes, some just
+    under the job size), random bytes, text, and copies taken from anywhere earlier in the block, at several capacities
+    and batch sizes (the emulated grid shares the groups' block indices 1, 3 or 16 ways by the batch size; the early
+    pass takes the last half of the batch)."""
+    import benchdata
+    L = _pipeline_lib()
+    _, zstd = benchdata._libs()
+    rng = np.random.default_rng(20260300 + seed)
+    plain, comp = [], []
+    for k in range(nframes):
+        parts, size = [], 0
+        while size < cap:
+            kind = int(rng.integers(0, 6))
+            if kind == 0:
+                p = np.full(int(rng.integers(20_000, 140_000)), int(rng.integers(0, 3)) * 7, dtype=np.uint8)
+            elif kind == 1:
+                p = rng.integers(0, 256, size=int(rng.integers(100, 5000)), dtype=np.uint8)
+            elif kind == 2:
+                p = rng.integers(97, 101, size=int(rng.integers(500, 20000)), dtype=np.uint8)
+            elif kind == 3 and size > 100:
+                cur = np.concatenate(parts)
+                at = int(rng.integers(0, size - 50))
+                p = cur[at: at + int(rng.integers(8, 3000))].copy()      # a copy from anywhere earlier
+            elif kind == 4:
+                p = np.full(int(rng.integers(31_000, 34_000)), 0, dtype=np.uint8)   # around the job size
+            else:
+                p = rng.integers(0, 256, size=int(rng.integers(60_000, 150_000)), dtype=np.uint8) if rng.integers(0, 4) == 0 \
+                    else np.zeros(int(rng.integers(1, 300)), dtype=np.uint8)
+            parts.append(p)
+            size += p.size
+        buf = np.concatenate(parts)[:cap].copy()
+        scratch = np.zeros(cap + cap // 128 + 4096, dtype=np.uint8)
+        got = zstd.ZSTD_compress(scratch.ctypes.data, scratch.size, buf.ctypes.data, buf.size, int(rng.integers(-3, 4)))
+        assert 0 < got <= scratch.size
+        plain.append(buf)
+        comp.append(scratch[:got].copy())
+    st, osz, outs, fl = _run_pipeline(L, comp, cap=cap, shift=seed)
+    for k in range(nframes):
+        want_n, want = oracle_port.zstd_decode(comp[k], cap=cap)[:2]
+        assert want_n == cap and np.array_equal(want[:cap], plain[k]), "oracle disagrees with libzstd"
+        assert st[k] == 0 and osz[k] == cap, (k, st[k], osz[k])
+        assert np.array_equal(outs[k][:cap], plain[k]), (k, int(np.argmax(outs[k][:cap] != plain[k])), fl[k])
