@@ -252,6 +252,14 @@ CRYO_DEV void wx_match(WOut &o, uint32_t off, uint32_t n, uint32_t lane)
     }
     const uint32_t src = o.pos - off;
     const bool in_ring = off <= WX_RING - 64u;
+    /*
+     * The steps of a copy (32 bytes each) must not overtake one another when a later step's destination falls on the
+     * ring slot an earlier step still has to read: the match overlaps itself (off < n), or it is so far back that
+     * the destination wraps round onto its own source (off + n beyond the ring).  The second case went unsynchronised
+     * until the end of round 2: lockstep execution hid it on the device, the emulator, which runs the lanes one after
+     * the other between barriers, did not (a 490-byte match at distance 1 878).
+     */
+    const bool ordered = off < n || off + n + 64u > WX_RING;
 
     if (in_ring && src >= o.lo)
     {
@@ -264,7 +272,7 @@ CRYO_DEV void wx_match(WOut &o, uint32_t off, uint32_t n, uint32_t lane)
 
                 if (i < n)
                     o.ring[(o.pos + i) & WX_RMASK] = o.ring[(src + i) & WX_RMASK];
-                if (off < n)
+                if (ordered)
                     __syncwarp();
             }
         }
@@ -323,7 +331,7 @@ CRYO_DEV void wx_match(WOut &o, uint32_t off, uint32_t n, uint32_t lane)
 
                 o.ring[(o.pos + i) & WX_RMASK] = b;
             }
-            if (off < n)
+            if (ordered)
                 __syncwarp();
         }
     }

@@ -378,3 +378,25 @@ def test_emulated_pipeline_random_run_layouts(oracle_port, nframes, cap, seed):
         assert want_n == cap and np.array_equal(want[:cap], plain[k]), "oracle disagrees with libzstd"
         assert st[k] == 0 and osz[k] == cap, (k, st[k], osz[k])
         assert np.array_equal(outs[k][:cap], plain[k]), (k, int(np.argmax(outs[k][:cap] != plain[k])), fl[k])
+
+
+def test_emulated_warp_decoders_far_match_wraps_the_ring(emu, oracle_ref):
+    """A match short enough for the ring path and so far back that its destination wraps round onto the ring slots
+    of its own source (distance + length beyond the 2 KiB ring): the steps of the copy must run in order.  They did
+    not (no barrier between them) until the end of round 2; the device hid it by running a warp's lanes in lockstep."""
+    rng = np.random.default_rng(20260401)
+    blk = np.zeros(MiB, dtype=np.uint8)
+    blk[:6000] = rng.integers(97, 101, size=6000, dtype=np.uint8)
+    pos = 6000
+    for dist, length in [(1500, 200), (1878, 490), (1984, 511), (1985, 300), (2040, 64), (1700, 400), (1990, 480), (1600, 500)]:
+        # text of four letters: short matches, so the bytes in front of the far copy are in the ring (a long literal run would
+        # have gone to global memory and the copy would have read it from there)
+        more = rng.integers(97, 101, size=dist - 200, dtype=np.uint8)
+        blk[pos: pos + more.size] = more
+        pos += more.size
+        blk[pos: pos + length] = blk[pos - dist: pos - dist + length]
+        pos += length
+    for method, lv in ((0, 1), (1, 1), (1, 3)):
+        c = oracle_ref.compress(method, lv, blk)[0][0]
+        st, sz, out = emu(method, c, shift=lv)
+        assert st == 0 and sz == MiB and np.array_equal(out, blk), (method, lv, int(np.argmax(out != blk)))
