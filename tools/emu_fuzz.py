@@ -1,0 +1,100 @@
+"""dev tool (CPU): random block layouts through the kernel bodies under the SIMT emulator (tests/emu), checked against
+the plain-C restatement / the system libraries' output.  Long one-byte runs, random bytes, four-letter text and copies
+taken from anywhere earlier -- the shapes that found the two bugs fixed at the end of round 2 (a job of the raw / RLE
+stage passing for a later block of its frame; an in-ring match wrapping round onto its own source).
+
+usage: python tools/emu_fuzz.py pipeline|warp|cta FIRST_SEED LAST_SEED
+  pipeline: the phase-split zstd pipeline (early pass, jobs; ZP_EMU_* environment switches of tests/emu apply)
+  warp:     the warp-per-block LZ4 and zstd decoders
+  cta:      the CTA-per-block LZ4 decoder and the CTA executor of the zstd pipeline (64-thread build)"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import benchdata                          # noqa: E402
+import test_emu_cx as tc                  # noqa: E402
+import test_emu_kernels as tk             # noqa: E402
+from oracle import port                   # noqa: E402
+
+MiB = 1 << 20
+
+
+def layout(rng, cap, long_runs):
+    parts, size = [], 0
+    while size < cap:
+        kind = int(rng.integers(0, 6))
+        if kind == 0:
+            p = np.full(int(rng.integers(2_000, 140_000 if long_runs else 40_000)), int(rng.integers(0, 3)) * 7, dtype=np.uint8)
+        elif kind == 1:
+            p = rng.integers(0, 256, size=int(rng.integers(100, 3000)), dtype=np.uint8)
+        elif kind == 2:
+            p = rng.integers(97, 101, size=int(rng.integers(500, 9000)), dtype=np.uint8)
+        elif kind == 3 and size > 100:
+            cur = np.concatenate(parts)
+            at = int(rng.integers(0, size - 50))
+            p = cur[at: at + int(rng.integers(8, 3000))].copy()
+        elif kind == 4:
+            p = np.zeros(int(rng.integers(31_000, 34_000) if long_runs else rng.integers(400, 9000)), dtype=np.uint8)
+        else:
+            p = np.zeros(int(rng.integers(1, 300)), dtype=np.uint8)
+        parts.append(p)
+        size += p.size
+    return np.concatenate(parts)[:cap].copy()
+
+
+def zstd_compress(buf, level):
+    _, zstd = benchdata._libs()
+    scratch = np.zeros(buf.size + buf.size // 128 + 4096, dtype=np.uint8)
+    got = zstd.ZSTD_compress(scratch.ctypes.data, scratch.size, buf.ctypes.data, buf.size, level)
+    assert 0 < got <= scratch.size
+    return scratch[:got].copy()
+
+
+def main():
+    what, first, last = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    bad = 0
+    for seed in range(first, last):
+        rng = np.random.default_rng(99_000 + seed)
+        if what == "pipeline":
+            n = [5, 8, 9, 14, 16][seed % 5]
+            cap = [MiB, 300 * 1024, 160 * 1024, 640 * 1024][seed % 4]
+            plain = [layout(rng, cap, True) for _ in range(n)]
+            comp = [zstd_compress(b, int(rng.integers(-3, 4))) for b in plain]
+            st, osz, outs, fl = tk._run_pipeline(tk._pipeline_lib(), comp, cap=cap, shift=seed % 16)
+            ok = all(st[k] == 0 and osz[k] == cap and np.array_equal(outs[k][:cap], plain[k]) for k in range(n))
+            print(seed, "pipeline", n, cap, "ok" if ok else "MISMATCH", "fallback", sum(1 for f in fl if f), flush=True)
+        else:
+            warp = what == "warp"
+            L = C.CDLL(os.path.join(ROOT, "tests", "emu", "libcryoemu.so" if warp else "libcryoemu_cx64.so"))
+            cap = ([MiB, 300_000, 777_777, 65_536] if warp else [70_000, 150_000, 40_000, 100_000])[seed % 4]
+            buf = layout(rng, cap, warp)
+            lz = L.emu_lz4w_decode if warp else L.emu_lz4c_decode
+            lz.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint, C.POINTER(C.c_uint32)]
+            c = tc.lz4_compress(buf, accel=1 + seed % 4)
+            out, sz = np.zeros(cap, dtype=np.uint8), C.c_uint32(0)
+            st = lz(c.ctypes.data, c.size, out.ctypes.data, cap, seed % 16, C.byref(sz))
+            ok = st == 0 and sz.value == cap and np.array_equal(out, buf)
+            z = zstd_compress(buf, int(rng.integers(-3, 4)))
+            want_n, want = port.zstd_decode(z, cap=cap)[:2]
+            assert want_n == cap and np.array_equal(want[:cap], buf)
+            out2, sz2, fl = np.zeros(cap, dtype=np.uint8), C.c_uint32(0), C.c_uint32(0)
+            if warp:
+                L.emu_zstdw_decode.argtypes = lz.argtypes
+                st2 = L.emu_zstdw_decode(z.ctypes.data, z.size, out2.ctypes.data, cap, seed % 16, C.byref(sz2))
+            else:
+                L.emu_zstdc_decode.argtypes = lz.argtypes + [C.POINTER(C.c_uint32)]
+                st2 = L.emu_zstdc_decode(z.ctypes.data, z.size, out2.ctypes.data, cap, seed % 16, C.byref(sz2), C.byref(fl))
+            ok = ok and st2 == 0 and sz2.value == cap and np.array_equal(out2, buf)
+            print(seed, what, cap, "ok" if ok else "MISMATCH", flush=True)
+        bad += not ok
+    print("mismatches:", bad)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
