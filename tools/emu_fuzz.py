@@ -3,10 +3,15 @@ the plain-C restatement / the system libraries' output.  Long one-byte runs, ran
 taken from anywhere earlier -- the shapes that found the two bugs fixed at the end of round 2 (a job of the raw / RLE
 stage passing for a later block of its frame; an in-ring match wrapping round onto its own source).
 
-usage: python tools/emu_fuzz.py pipeline|warp|cta FIRST_SEED LAST_SEED
+usage: python tools/emu_fuzz.py pipeline|corrupt|warp|cta|warp-corrupt|cta-corrupt FIRST_SEED LAST_SEED
+  corrupt:  the pipeline over batches in which about half of the frames carry a mutation (flipped bytes, a cut, bytes
+            appended): every frame's verdict and, when accepted, bytes are the plain-C restatement's, and the intact
+            frames beside them come out right
   pipeline: the phase-split zstd pipeline (early pass, jobs; ZP_EMU_* environment switches of tests/emu apply)
   warp:     the warp-per-block LZ4 and zstd decoders
-  cta:      the CTA-per-block LZ4 decoder and the CTA executor of the zstd pipeline (64-thread build)"""
+  cta:      the CTA-per-block LZ4 decoder and the CTA executor of the zstd pipeline (64-thread build)
+  warp-corrupt, cta-corrupt: mutated LZ4 blocks and zstd frames through those decoders, one at a time: the verdict and,
+            when accepted, the bytes of the plain-C restatement"""
 import ctypes as C
 import os
 import sys
@@ -68,14 +73,85 @@ def main():
             st, osz, outs, fl = tk._run_pipeline(tk._pipeline_lib(), comp, cap=cap, shift=seed % 16)
             ok = all(st[k] == 0 and osz[k] == cap and np.array_equal(outs[k][:cap], plain[k]) for k in range(n))
             print(seed, "pipeline", n, cap, "ok" if ok else "MISMATCH", "fallback", sum(1 for f in fl if f), flush=True)
+        elif what == "corrupt":
+            n = [6, 9, 12][seed % 3]
+            cap = [160 * 1024, 300 * 1024, 640 * 1024][seed % 3]
+            plain = [layout(rng, cap, bool(seed & 1)) for _ in range(n)]
+            comp = [zstd_compress(b, int(rng.integers(-3, 4))) for b in plain]
+            hit = []
+            for k in range(n):
+                how = int(rng.integers(0, 8))
+                c = comp[k]
+                if how == 0:
+                    for _ in range(int(rng.integers(1, 4))):
+                        c[int(rng.integers(0, c.size))] ^= int(rng.integers(1, 256))
+                elif how == 1:
+                    c[int(rng.integers(0, min(c.size, 24)))] ^= 1 << int(rng.integers(0, 8))      # headers
+                elif how == 2:
+                    comp[k] = c[: int(rng.integers(0, c.size))].copy()
+                elif how == 3:
+                    comp[k] = np.concatenate([c, rng.integers(0, 256, size=int(rng.integers(1, 9)), dtype=np.uint8)])
+                hit.append(how < 4)
+            want = [port.zstd_decode(c, cap=cap)[:2] for c in comp]
+            st, osz, outs, fl = tk._run_pipeline(tk._pipeline_lib(), comp, cap=cap, shift=seed % 16)
+            ok = True
+            for k in range(n):
+                wn, wout = want[k]
+                if wn != cap:           # the C-ABI takes blocks of exactly cap bytes: anything else is an error
+                    good = st[k] != 0
+                else:
+                    good = st[k] == 0 and osz[k] == cap and np.array_equal(outs[k][:cap], wout[:cap])
+                if not hit[k]:
+                    good = good and st[k] == 0 and np.array_equal(outs[k][:cap], plain[k])
+                if not good:
+                    print("  frame", k, "mutated" if hit[k] else "intact", "status", st[k], "size", osz[k], "port", wn)
+                ok = ok and good
+            print(seed, "corrupt", n, cap, "ok" if ok else "MISMATCH", "mutated", sum(hit),
+                  "accepted", sum(1 for k in range(n) if hit[k] and st[k] == 0), flush=True)
         else:
-            warp = what == "warp"
+            warp = what in ("warp", "warp-corrupt")
+            mutate = what.endswith("-corrupt")
             L = C.CDLL(os.path.join(ROOT, "tests", "emu", "libcryoemu.so" if warp else "libcryoemu_cx64.so"))
             cap = ([MiB, 300_000, 777_777, 65_536] if warp else [70_000, 150_000, 40_000, 100_000])[seed % 4]
             buf = layout(rng, cap, warp)
             lz = L.emu_lz4w_decode if warp else L.emu_lz4c_decode
             lz.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint, C.POINTER(C.c_uint32)]
             c = tc.lz4_compress(buf, accel=1 + seed % 4)
+            if mutate:
+                z = zstd_compress(buf, int(rng.integers(-3, 4)))
+                ok = True
+                for name, stream, dec, ref in (("lz4", c, lz, port.lz4_decode), ("zstd", z, None, port.zstd_decode)):
+                    for _ in range(6):
+                        m = stream.copy()
+                        how = int(rng.integers(0, 4))
+                        if how == 0:
+                            for _ in range(int(rng.integers(1, 4))):
+                                m[int(rng.integers(0, m.size))] ^= int(rng.integers(1, 256))
+                        elif how == 1:
+                            m = m[: int(rng.integers(0, m.size))].copy()
+                        elif how == 2:
+                            m = np.concatenate([m, rng.integers(0, 256, size=int(rng.integers(1, 9)), dtype=np.uint8)])
+                        else:
+                            m[int(rng.integers(0, min(m.size, 24)))] ^= 1 << int(rng.integers(0, 8))
+                        wn, wout = ref(m, cap=cap)[:2]
+                        out, sz, fl = np.zeros(cap, dtype=np.uint8), C.c_uint32(0), C.c_uint32(0)
+                        src = m.ctypes.data if m.size else None
+                        if dec is not None:
+                            st = dec(src, m.size, out.ctypes.data, cap, seed % 16, C.byref(sz))
+                        elif warp:
+                            L.emu_zstdw_decode.argtypes = lz.argtypes
+                            st = L.emu_zstdw_decode(src, m.size, out.ctypes.data, cap, seed % 16, C.byref(sz))
+                        else:
+                            L.emu_zstdc_decode.argtypes = lz.argtypes + [C.POINTER(C.c_uint32)]
+                            st = L.emu_zstdc_decode(src, m.size, out.ctypes.data, cap, seed % 16, C.byref(sz), C.byref(fl))
+                        good = st != 0 if wn < 0 else \
+                            (st == 0 and sz.value == wn and np.array_equal(out[:wn], wout[:wn]))
+                        if not good:
+                            print("  ", name, "how", how, "status", st, "size", sz.value, "port", wn)
+                        ok = ok and good
+                print(seed, what, cap, "ok" if ok else "MISMATCH", flush=True)
+                bad += not ok
+                continue
             out, sz = np.zeros(cap, dtype=np.uint8), C.c_uint32(0)
             st = lz(c.ctypes.data, c.size, out.ctypes.data, cap, seed % 16, C.byref(sz))
             ok = st == 0 and sz.value == cap and np.array_equal(out, buf)
