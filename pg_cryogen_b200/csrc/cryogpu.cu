@@ -1586,6 +1586,7 @@ cryogpu_zstd_pipeline_stats(cryogpu_ctx *ctx, uint64_t *frames, uint64_t *fallba
 {
     if (!ctx)
         return fail(CRYOGPU_E_ARG, "ctx is NULL");
+    std::lock_guard<std::recursive_mutex> g(ctx->mu);       /* last_zp_n / last_zp_cap and the work area are the context's */
     uint64_t total = 0, fb = 0;
 
     CU(cudaSetDevice(ctx->device));

@@ -3,13 +3,14 @@ the plain-C restatement / the system libraries' output.  Long one-byte runs, ran
 taken from anywhere earlier -- the shapes that found the two bugs fixed at the end of round 2 (a job of the raw / RLE
 stage passing for a later block of its frame; an in-ring match wrapping round onto its own source).
 
-usage: python tools/emu_fuzz.py pipeline|corrupt|warp|cta|warp-corrupt|cta-corrupt FIRST_SEED LAST_SEED
+usage: python tools/emu_fuzz.py pipeline|corrupt|warp|cta|warp-corrupt|cta-corrupt|encode FIRST_SEED LAST_SEED
   corrupt:  the pipeline over batches in which about half of the frames carry a mutation (flipped bytes, a cut, bytes
             appended): every frame's verdict and, when accepted, bytes are the plain-C restatement's, and the intact
             frames beside them come out right
   pipeline: the phase-split zstd pipeline (early pass, jobs; ZP_EMU_* environment switches of tests/emu apply)
   warp:     the warp-per-block LZ4 and zstd decoders
   cta:      the CTA-per-block LZ4 decoder and the CTA executor of the zstd pipeline (64-thread build)
+  encode:   the LZ4 and zstd encoders over the same layouts at several sizes; the plain-C restatement decodes them back
   warp-corrupt, cta-corrupt: mutated LZ4 blocks and zstd frames through those decoders, one at a time: the verdict and,
             when accepted, the bytes of the plain-C restatement"""
 import ctypes as C
@@ -108,6 +109,24 @@ def main():
                 ok = ok and good
             print(seed, "corrupt", n, cap, "ok" if ok else "MISMATCH", "mutated", sum(hit),
                   "accepted", sum(1 for k in range(n) if hit[k] and st[k] == 0), flush=True)
+        elif what == "encode":
+            L = C.CDLL(os.path.join(ROOT, "tests", "emu", "libcryoemu.so"))
+            cap = [MiB, 300_000, 70_001, 4_099, 131_072 + 5, 777_777, 63, 65_536][seed % 8]
+            buf = layout(rng, cap, bool(seed & 1))
+            ok = True
+            for name, fn, arg, dec in (("lz4", L.emu_lz4_encode, 1 + seed % 5, port.lz4_decode),
+                                       ("zstd", L.emu_zstd_encode, [1, -5, 3, -1][seed % 4], port.zstd_decode)):
+                fn.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_uint32)]
+                fn.restype = C.c_int
+                room = cap + cap // 128 + 4096
+                out, sz = np.zeros(room, dtype=np.uint8), C.c_uint32(0)
+                st = fn(buf.ctypes.data, cap, out.ctypes.data, room, arg, C.byref(sz))
+                got, back = dec(out[: sz.value].copy(), cap=cap)[:2]
+                good = st == 0 and got == cap and np.array_equal(back[:cap], buf)
+                if not good:
+                    print("  ", name, "status", st, "size", sz.value, "decoded", got)
+                ok = ok and good
+            print(seed, "encode", cap, "ok" if ok else "MISMATCH", flush=True)
         else:
             warp = what in ("warp", "warp-corrupt")
             mutate = what.endswith("-corrupt")
