@@ -9,7 +9,8 @@ usage: python tools/emu_fuzz.py pipeline|corrupt|warp|cta|warp-corrupt|cta-corru
             frames beside them come out right
   pipeline: the phase-split zstd pipeline (early pass, jobs; ZP_EMU_* environment switches of tests/emu apply)
   warp:     the warp-per-block LZ4 and zstd decoders
-  cta:      the CTA-per-block LZ4 decoder and the CTA executor of the zstd pipeline (64-thread build)
+  cta:      the CTA-per-block LZ4 decoder and the CTA executor of the zstd pipeline (64-thread build;
+            EMU_FUZZ_CX_LIB=libcryoemu_cx1024.so: the build with the device's 1 024 threads)
   encode:   the LZ4 and zstd encoders over the same layouts at several sizes; the plain-C restatement decodes them back
   warp-corrupt, cta-corrupt: mutated LZ4 blocks and zstd frames through those decoders, one at a time: the verdict and,
             when accepted, the bytes of the plain-C restatement"""
@@ -130,7 +131,7 @@ def main():
         else:
             warp = what in ("warp", "warp-corrupt")
             mutate = what.endswith("-corrupt")
-            L = C.CDLL(os.path.join(ROOT, "tests", "emu", "libcryoemu.so" if warp else "libcryoemu_cx64.so"))
+            L = C.CDLL(os.path.join(ROOT, "tests", "emu", "libcryoemu.so" if warp else os.environ.get("EMU_FUZZ_CX_LIB", "libcryoemu_cx64.so")))
             cap = ([MiB, 300_000, 777_777, 65_536] if warp else [70_000, 150_000, 40_000, 100_000])[seed % 4]
             buf = layout(rng, cap, warp)
             lz = L.emu_lz4w_decode if warp else L.emu_lz4c_decode
