@@ -29,6 +29,9 @@ import test_emu_kernels as tk             # noqa: E402
 from oracle import port                   # noqa: E402
 
 MiB = 1 << 20
+# zstd levels of the frames fed to the decoders: -3 .. 3 (what the GUC's default neighbourhood writes); EMU_FUZZ_LEVELS=lo,hi
+# widens it (the GUC allows -5 .. 22: Repeat_Mode tables, single-stream literals, long windows)
+LO, HI = (int(x) for x in os.environ.get("EMU_FUZZ_LEVELS", "-3,4").split(","))
 
 
 def layout(rng, cap, long_runs):
@@ -71,7 +74,7 @@ def main():
             n = [5, 8, 9, 14, 16][seed % 5]
             cap = [MiB, 300 * 1024, 160 * 1024, 640 * 1024][seed % 4]
             plain = [layout(rng, cap, True) for _ in range(n)]
-            comp = [zstd_compress(b, int(rng.integers(-3, 4))) for b in plain]
+            comp = [zstd_compress(b, int(rng.integers(LO, HI))) for b in plain]
             st, osz, outs, fl = tk._run_pipeline(tk._pipeline_lib(), comp, cap=cap, shift=seed % 16)
             ok = all(st[k] == 0 and osz[k] == cap and np.array_equal(outs[k][:cap], plain[k]) for k in range(n))
             print(seed, "pipeline", n, cap, "ok" if ok else "MISMATCH", "fallback", sum(1 for f in fl if f), flush=True)
@@ -79,7 +82,7 @@ def main():
             n = [6, 9, 12][seed % 3]
             cap = [160 * 1024, 300 * 1024, 640 * 1024][seed % 3]
             plain = [layout(rng, cap, bool(seed & 1)) for _ in range(n)]
-            comp = [zstd_compress(b, int(rng.integers(-3, 4))) for b in plain]
+            comp = [zstd_compress(b, int(rng.integers(LO, HI))) for b in plain]
             hit = []
             for k in range(n):
                 how = int(rng.integers(0, 8))
@@ -138,7 +141,7 @@ def main():
             lz.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint, C.POINTER(C.c_uint32)]
             c = tc.lz4_compress(buf, accel=1 + seed % 4)
             if mutate:
-                z = zstd_compress(buf, int(rng.integers(-3, 4)))
+                z = zstd_compress(buf, int(rng.integers(LO, HI)))
                 ok = True
                 for name, stream, dec, ref in (("lz4", c, lz, port.lz4_decode), ("zstd", z, None, port.zstd_decode)):
                     for _ in range(6):
@@ -175,7 +178,7 @@ def main():
             out, sz = np.zeros(cap, dtype=np.uint8), C.c_uint32(0)
             st = lz(c.ctypes.data, c.size, out.ctypes.data, cap, seed % 16, C.byref(sz))
             ok = st == 0 and sz.value == cap and np.array_equal(out, buf)
-            z = zstd_compress(buf, int(rng.integers(-3, 4)))
+            z = zstd_compress(buf, int(rng.integers(LO, HI)))
             want_n, want = port.zstd_decode(z, cap=cap)[:2]
             assert want_n == cap and np.array_equal(want[:cap], buf)
             out2, sz2, fl = np.zeros(cap, dtype=np.uint8), C.c_uint32(0), C.c_uint32(0)
