@@ -72,6 +72,7 @@ def main():
         rng = np.random.default_rng(99_000 + seed)
         if what == "pipeline":
             n = [5, 8, 9, 14, 16][seed % 5]
+            n = int(os.environ.get("EMU_FUZZ_N", n))           # frames per batch
             cap = [MiB, 300 * 1024, 160 * 1024, 640 * 1024][seed % 4]
             plain = [layout(rng, cap, True) for _ in range(n)]
             comp = [zstd_compress(b, int(rng.integers(LO, HI))) for b in plain]
