@@ -402,11 +402,12 @@ def test_emulated_warp_decoders_far_match_wraps_the_ring(emu, oracle_ref):
         assert st == 0 and sz == MiB and np.array_equal(out, blk), (method, lv, int(np.argmax(out != blk)))
 
 
-@pytest.mark.parametrize("mode, first, last", [("corrupt", 1, 2), ("warp-corrupt", 0, 1), ("cta-corrupt", 2, 3)])
-def test_emulated_decoders_give_the_restatements_verdict_on_mutated_streams(oracle_port, mode, first, last):
+@pytest.mark.parametrize("mode, first, last", [("corrupt", 1, 2), ("warp-corrupt", 0, 1), ("cta-corrupt", 2, 3), ("encode", 2, 5)])
+def test_emulated_bodies_on_fuzzed_streams(oracle_port, mode, first, last):
     """Batches in which half of the frames carry flipped bytes, a cut or appended bytes (tools/emu_fuzz.py, one seed
     of each mode): every frame's verdict and, when accepted, bytes are the plain-C restatement's; the intact frames of the
-    same batch come out right (a rejected frame's jobs and ring never leak into its neighbours)."""
+    same batch come out right (a rejected frame's jobs and ring never leak into its neighbours).  "encode": the LZ4 and
+    zstd encoder bodies over random layouts of 70 001, 4 099 and 131 077 bytes, decoded back by the restatement."""
     import sys
     r = subprocess.run([sys.executable, os.path.join(os.path.dirname(HERE), "tools", "emu_fuzz.py"), mode, str(first), str(last)],
                        capture_output=True, text=True, timeout=600)
